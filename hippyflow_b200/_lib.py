@@ -1,0 +1,272 @@
+"""ctypes binding of libhfb200.so (the C ABI in include/hfb200.h) plus thin torch-tensor wrappers.
+
+PyTorch is plumbing here: it owns device memory and streams; every numerical operation of the hot
+path goes through the C ABI below.  There is NO fallback: if the shared library is missing or a
+call returns an error code the wrappers raise.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhfb200.so")
+
+HFB_NN, HFB_TN, HFB_NT = 0, 1, 2
+
+_ERRORS = {
+    -1: "invalid argument",
+    -2: "operand not 16-byte aligned or odd leading dimension",
+    -3: "workspace too small",
+    -4: "CUDA driver entry point cuTensorMapEncodeTiled unavailable",
+    -5: "unsupported size",
+}
+
+
+class HfbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libhfb200.so (built by ``__graft_entry__.build()`` / ``make -C hippyflow_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HfbError(
+            "libhfb200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the hot path)")
+    L = ctypes.CDLL(LIB_PATH)
+    i64, i32, dbl, vp, sz, u64 = (ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.c_uint64)
+    sigs = {
+        "hfb_version": (i32, []),
+        "hfb_launch_count": (i64, []),
+        "hfb_dgemm_workspace_bytes": (sz, [i32, i64, i64, i64, i32]),
+        "hfb_dgemm_auto_splits": (i32, [i32, i64, i64, i64]),
+        "hfb_dgemm": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, vp, i64, vp, sz, i32, vp]),
+        "hfb_dgemm_batched_small": (i32, [i32, i64, i64, i64, dbl, vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, vp]),
+        "hfb_csr_spmm": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
+        "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
+        "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
+        "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
+        "hfb_colscale": (i32, [i64, i64, vp, i64, vp, vp]),
+        "hfb_colmean_workspace_bytes": (sz, [i64, i64]),
+        "hfb_colsum": (i32, [i64, i64, vp, i64, dbl, vp, vp, sz, vp]),
+        "hfb_subtract_row": (i32, [i64, i64, vp, i64, vp, vp]),
+        "hfb_axpby": (i32, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
+        "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm",
+            "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
+            "hfb_coldot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
+            "hfb_axpby", "hfb_fill_random"]
+
+
+def _check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise HfbError("%s: %s (code %d)" % (what, _ERRORS.get(rc, "error"), rc))
+    raise HfbError("%s: CUDA error code %d" % (what, rc))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
+        raise HfbError("%s must be a 2-D float64 CUDA tensor with unit inner stride" % name)
+    return t
+
+
+def _ld(t):
+    # leading dimension of a 2-D row-major view (a single row may report any stride)
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+# workspace cache: one growable byte buffer per device (caller-owned memory from the C ABI's viewpoint)
+_ws = {}
+
+
+def workspace(nbytes, device):
+    key = (device.type, device.index)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def padded_empty(rows, cols, device, pad=16):
+    """(rows, cols) float64 view of a buffer whose leading dimension is a multiple of ``pad`` elements
+    (TMA needs an even ld; 16 keeps every row 128-byte aligned)."""
+    ld = ((cols + pad - 1) // pad) * pad
+    return torch.empty((rows, ld), dtype=torch.float64, device=device)[:, :cols]
+
+
+def padded_zeros(rows, cols, device, pad=16):
+    ld = ((cols + pad - 1) // pad) * pad
+    return torch.zeros((rows, ld), dtype=torch.float64, device=device)[:, :cols]
+
+
+def to_padded(a, device, pad=16):
+    """Copy a host/device (rows, cols) array into a padded-ld device buffer."""
+    t = torch.as_tensor(a)
+    out = padded_empty(t.shape[0], t.shape[1], device, pad)
+    out.copy_(t.to(dtype=torch.float64), non_blocking=True)
+    return out
+
+
+def dgemm(layout, A, B, out=None, alpha=1.0, splits=0):
+    """out[M,N] = alpha * op(A) op(B) on the DMMA/TMA kernel.  layout: HFB_NN (A MxK, B KxN),
+    HFB_TN (A KxM), HFB_NT (B NxK)."""
+    L = lib()
+    _req(A, "A"), _req(B, "B")
+    if layout == HFB_NN:
+        M, K = A.shape
+        K2, N = B.shape
+    elif layout == HFB_TN:
+        K, M = A.shape
+        K2, N = B.shape
+    elif layout == HFB_NT:
+        M, K = A.shape
+        N, K2 = B.shape
+    else:
+        raise HfbError("unknown layout")
+    if K != K2:
+        raise HfbError("dgemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        out = padded_empty(M, N, A.device)
+    _req(out, "out")
+    if tuple(out.shape) != (M, N):
+        raise HfbError("dgemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
+    nbytes = L.hfb_dgemm_workspace_bytes(layout, M, N, K, splits)
+    ws = workspace(nbytes, A.device) if nbytes else None
+    rc = L.hfb_dgemm(layout, M, N, K, float(alpha), A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
+                     ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, int(splits),
+                     _stream())
+    _check(rc, "hfb_dgemm")
+    return out
+
+
+def dgemm_batched_small(layout, A, B, out, alpha=1.0):
+    """out[b] = alpha * op(A[b]) @ B[b]; A/B/out are 3-D (batch, rows, cols) float64 CUDA tensors with unit
+    inner stride; a batch stride of 0 (expanded tensor) shares the operand."""
+    L = lib()
+    batch = out.shape[0]
+    if layout == HFB_TN:
+        K, M = A.shape[1], A.shape[2]
+    else:
+        M, K = A.shape[1], A.shape[2]
+    N = B.shape[2]
+    for t in (A, B, out):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 3 and t.stride(2) == 1):
+            raise HfbError("dgemm_batched_small: operands must be 3-D float64 CUDA tensors")
+    if B.shape[1] != K or tuple(out.shape[1:]) != (M, N):
+        raise HfbError("dgemm_batched_small: shape mismatch")
+    rc = L.hfb_dgemm_batched_small(layout, M, N, K, float(alpha), A.data_ptr(), A.stride(1), A.stride(0) if A.shape[0] > 1 else 0,
+                                   B.data_ptr(), B.stride(1), B.stride(0) if B.shape[0] > 1 else 0, out.data_ptr(),
+                                   out.stride(1), out.stride(0), batch, _stream())
+    _check(rc, "hfb_dgemm_batched_small")
+    return out
+
+
+def csr_spmm(rowptr, colind, val, B, out=None):
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    nrows = rowptr.numel() - 1
+    rc = L.hfb_csr_spmm(nrows, m, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), _ld(B),
+                        out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm")
+    return out
+
+
+def csr_spmm_rows(rowptr, colind, val, X, out=None):
+    L = lib()
+    _req(X, "X")
+    N, n = X.shape
+    if out is None:
+        out = padded_empty(N, n, X.device)
+    rc = L.hfb_csr_spmm_rows(N, n, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), X.data_ptr(), _ld(X),
+                             out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_rows")
+    return out
+
+
+def coldot(X, Y):
+    L = lib()
+    _req(X, "X"), _req(Y, "Y")
+    n, m = X.shape
+    out = torch.empty(m, dtype=torch.float64, device=X.device)
+    nbytes = L.hfb_coldot_workspace_bytes(n, m)
+    ws = workspace(nbytes, X.device)
+    rc = L.hfb_coldot(n, m, X.data_ptr(), _ld(X), Y.data_ptr(), _ld(Y), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _check(rc, "hfb_coldot")
+    return out
+
+
+def colscale_(X, s):
+    L = lib()
+    _req(X, "X")
+    rc = L.hfb_colscale(X.shape[0], X.shape[1], X.data_ptr(), _ld(X), s.data_ptr(), _stream())
+    _check(rc, "hfb_colscale")
+    return X
+
+
+def colsum(X, scale=1.0):
+    """scale * sum over rows (samples) of X -> vector of length X.shape[1]."""
+    L = lib()
+    _req(X, "X")
+    N, n = X.shape
+    out = torch.empty(n, dtype=torch.float64, device=X.device)
+    nbytes = L.hfb_colmean_workspace_bytes(N, n)
+    ws = workspace(nbytes, X.device)
+    rc = L.hfb_colsum(N, n, X.data_ptr(), _ld(X), float(scale), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _check(rc, "hfb_colsum")
+    return out
+
+
+def subtract_row_(X, shift):
+    L = lib()
+    _req(X, "X")
+    rc = L.hfb_subtract_row(X.shape[0], X.shape[1], X.data_ptr(), _ld(X), shift.data_ptr(), _stream())
+    _check(rc, "hfb_subtract_row")
+    return X
+
+
+def axpby_(a, X, b, Y):
+    """Y = a*X + b*Y."""
+    L = lib()
+    _req(X, "X"), _req(Y, "Y")
+    rc = L.hfb_axpby(X.shape[0], X.shape[1], float(a), X.data_ptr(), _ld(X), float(b), Y.data_ptr(), _ld(Y), _stream())
+    _check(rc, "hfb_axpby")
+    return Y
+
+
+def fill_random_(X, seed, row_offset=0, kind="normal"):
+    L = lib()
+    _req(X, "X")
+    rc = L.hfb_fill_random(X.shape[0], X.shape[1], X.data_ptr(), _ld(X), int(seed), int(row_offset),
+                           0 if kind == "normal" else 1, _stream())
+    _check(rc, "hfb_fill_random")
+    return X
+
+
+def launch_count():
+    return int(lib().hfb_launch_count())

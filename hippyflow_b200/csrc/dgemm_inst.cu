@@ -1,0 +1,57 @@
+// Kernel instantiations of the DMMA GEMM for one operand layout (-DHFB_GEMM_LAYOUT=0|1|2), split into
+// three translation units so they compile in parallel.
+#include "../../include/hfb200.h"
+#include "dgemm_dmma.cuh"
+
+#ifndef HFB_GEMM_LAYOUT
+#error "compile with -DHFB_GEMM_LAYOUT=0|1|2"
+#endif
+
+namespace hfb {
+
+template <int LAYOUT, int NT>
+static int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<LAYOUT, NT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<LAYOUT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const long long grid = (long long)p.m_tiles * p.n_tiles * p.splits;
+    dgemm_dmma_kernel<LAYOUT, NT><<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
+template <int LAYOUT>
+static int dispatch_nt(int nt, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
+    switch (nt) {
+        case 4: return launch<LAYOUT, 4>(a, b, p, s);
+        case 9: return launch<LAYOUT, 9>(a, b, p, s);
+        case 10: return launch<LAYOUT, 10>(a, b, p, s);
+        case 14: return launch<LAYOUT, 14>(a, b, p, s);
+        case 16: return launch<LAYOUT, 16>(a, b, p, s);
+        case 17: return launch<LAYOUT, 17>(a, b, p, s);
+        case 18: return launch<LAYOUT, 18>(a, b, p, s);
+    }
+    return HFB_E_UNSUPPORTED;
+}
+
+
+#if HFB_GEMM_LAYOUT == 0
+int dgemm_launch_nn(int nt, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
+    return dispatch_nt<0>(nt, a, b, p, s);
+}
+#elif HFB_GEMM_LAYOUT == 1
+int dgemm_launch_tn(int nt, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
+    return dispatch_nt<1>(nt, a, b, p, s);
+}
+#else
+int dgemm_launch_nt(int nt, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
+    return dispatch_nt<2>(nt, a, b, p, s);
+}
+#endif
+
+}  // namespace hfb

@@ -1,0 +1,431 @@
+// HBM-bound kernels of the hot path: CSR SpMM, column reductions/scalings, sample-mean shift,
+// counter-based random fill, and the small batched GEMM (see include/hfb200.h for the reference call
+// sites each one replaces).  Grids are sized in multiples of the SM count; every reduction is two-stage
+// with a fixed summation order (bitwise reproducible), no atomics.
+#include "../../include/hfb200.h"
+#include "hfb_common.cuh"
+
+namespace hfb {
+
+static inline int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------ CSR SpMM
+// One warp per matrix row; lane l owns columns {2l, 2l+1} + 64*i (16-byte loads, a warp reads 512
+// contiguous bytes of a B row per chunk).  CH = ceil(m/64) chunks live in registers.
+template <int CH>
+__global__ void __launch_bounds__(256) csr_spmm_kernel(long long nrows, int m, const int* __restrict__ rowptr,
+                                                       const int* __restrict__ colind, const double* __restrict__ val,
+                                                       const double* __restrict__ B, long long ldb,
+                                                       double* __restrict__ C, long long ldc, int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < nrows; row += nwarps) {
+        double2 acc[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) acc[i] = make_double2(0.0, 0.0);
+        const int beg = rowptr[row], end = rowptr[row + 1];
+        for (int j = beg; j < end; ++j) {
+            const double v = __ldg(val + j);
+            const double* brow = B + (long long)__ldg(colind + j) * ldb;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int c = 2 * lane + 64 * i;
+                if (vec_ok && c + 1 < m) {
+                    const double2 b = *reinterpret_cast<const double2*>(brow + c);
+                    acc[i].x = fma(v, b.x, acc[i].x);
+                    acc[i].y = fma(v, b.y, acc[i].y);
+                } else {
+                    if (c < m) acc[i].x = fma(v, brow[c], acc[i].x);
+                    if (c + 1 < m) acc[i].y = fma(v, brow[c + 1], acc[i].y);
+                }
+            }
+        }
+        double* crow = C + row * ldc;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int c = 2 * lane + 64 * i;
+            if (vec_ok && c + 1 < m) {
+                *reinterpret_cast<double2*>(crow + c) = acc[i];
+            } else {
+                if (c < m) crow[c] = acc[i].x;
+                if (c + 1 < m) crow[c + 1] = acc[i].y;
+            }
+        }
+    }
+}
+
+// Sparse matrix applied to sample-major data: C[s, r] = sum_j val[j] X[s, col[j]], j in row r.
+// Thread = matrix row r (consecutive threads -> consecutive r -> near-contiguous gathers from a sample
+// row); a CTA reuses each CSR entry for SB samples held in registers.
+template <int SB>
+__global__ void __launch_bounds__(256) csr_spmm_rows_kernel(long long nsamples, long long n, const int* __restrict__ rowptr,
+                                                            const int* __restrict__ colind, const double* __restrict__ val,
+                                                            const double* __restrict__ X, long long ldx,
+                                                            double* __restrict__ C, long long ldc) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long s0 = (long long)blockIdx.y * SB;
+    if (r >= n) return;
+    double acc[SB];
+#pragma unroll
+    for (int s = 0; s < SB; ++s) acc[s] = 0.0;
+    const int beg = rowptr[r], end = rowptr[r + 1];
+    for (int j = beg; j < end; ++j) {
+        const double v = __ldg(val + j);
+        const double* x = X + s0 * ldx + __ldg(colind + j);
+#pragma unroll
+        for (int s = 0; s < SB; ++s)
+            if (s0 + s < nsamples) acc[s] = fma(v, __ldg(x + s * ldx), acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < SB; ++s)
+        if (s0 + s < nsamples) C[(s0 + s) * ldc + r] = acc[s];
+}
+
+// ------------------------------------------------------------------------------------------ column reductions
+// stage 1: block b sums rows [b*rows_per_block, ...) of X.*Y (or X) per column into part[b][col]
+__global__ void __launch_bounds__(256) colreduce_stage1(long long nrows, long long ncols, const double* __restrict__ X,
+                                                        long long ldx, const double* __restrict__ Y, long long ldy,
+                                                        long long rows_per_block, double* __restrict__ part) {
+    const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > nrows) r1 = nrows;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long long r = r0;
+    if (Y) {
+        for (; r + 3 < r1; r += 4) {
+            s0 = fma(X[r * ldx + col], Y[r * ldy + col], s0);
+            s1 = fma(X[(r + 1) * ldx + col], Y[(r + 1) * ldy + col], s1);
+            s2 = fma(X[(r + 2) * ldx + col], Y[(r + 2) * ldy + col], s2);
+            s3 = fma(X[(r + 3) * ldx + col], Y[(r + 3) * ldy + col], s3);
+        }
+        for (; r < r1; ++r) s0 = fma(X[r * ldx + col], Y[r * ldy + col], s0);
+    } else {
+        for (; r + 3 < r1; r += 4) {
+            s0 += X[r * ldx + col];
+            s1 += X[(r + 1) * ldx + col];
+            s2 += X[(r + 2) * ldx + col];
+            s3 += X[(r + 3) * ldx + col];
+        }
+        for (; r < r1; ++r) s0 += X[r * ldx + col];
+    }
+    part[(long long)blockIdx.y * ncols + col] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(256) colreduce_stage2(long long ncols, int nparts, const double* __restrict__ part,
+                                                        double scale, double* __restrict__ out) {
+    const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    double s = 0.0;
+    for (int b = 0; b < nparts; ++b) s += part[(long long)b * ncols + col];
+    out[col] = scale * s;
+}
+
+static int reduce_parts(long long nrows, long long ncols) {
+    // enough row blocks to fill the GPU given ceil(ncols/256) column blocks, at most 512
+    const long long colblocks = (ncols + 255) / 256;
+    long long want = (4LL * num_sms() + colblocks - 1) / colblocks;
+    if (want < 1) want = 1;
+    if (want > 512) want = 512;
+    const long long maxparts = (nrows + 15) / 16;  // >= 16 rows per block
+    if (want > maxparts) want = maxparts < 1 ? 1 : maxparts;
+    return (int)want;
+}
+
+// ------------------------------------------------------------------------------------------ elementwise
+__global__ void __launch_bounds__(256) colscale_kernel(long long n, long long m, double* __restrict__ X, long long ldx,
+                                                       const double* __restrict__ s) {
+    const long long total = n * m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / m;
+        const long long c = idx - r * m;
+        X[r * ldx + c] *= s[c];
+    }
+}
+__global__ void __launch_bounds__(256) subtract_row_kernel(long long N, long long n, double* __restrict__ X,
+                                                           long long ldx, const double* __restrict__ shift) {
+    const long long total = N * n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / n;
+        const long long c = idx - r * n;
+        X[r * ldx + c] -= shift[c];
+    }
+}
+__global__ void __launch_bounds__(256) axpby_kernel(long long n, long long m, double a, const double* __restrict__ X,
+                                                    long long ldx, double b, double* __restrict__ Y, long long ldy) {
+    const long long total = n * m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / m;
+        const long long c = idx - r * m;
+        const double y = (b == 0.0) ? 0.0 : b * Y[r * ldy + c];
+        Y[r * ldy + c] = fma(a, X[r * ldx + c], y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ random fill
+// Philox-4x32-10 keyed by seed, counter = (global row, column pair); Box-Muller for normals.
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0;
+        c[1] = lo1;
+        c[2] = n2;
+        c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__global__ void __launch_bounds__(256) fill_random_kernel(long long nrows, long long ncols, double* __restrict__ X,
+                                                          long long ldx, unsigned long long seed, long long row_offset,
+                                                          int kind) {
+    const long long pairs = (ncols + 1) / 2;
+    const long long total = nrows * pairs;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / pairs;
+        const long long pc = idx - r * pairs;
+        const unsigned long long gr = (unsigned long long)(r + row_offset);
+        uint32_t c[4] = {(uint32_t)gr, (uint32_t)(gr >> 32), (uint32_t)pc, (uint32_t)((unsigned long long)pc >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        // two 53-bit uniforms in (0,1)
+        const double u0 = ((double)(((unsigned long long)c[0] << 21) ^ (c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        const double u1 = ((double)(((unsigned long long)c[2] << 21) ^ (c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        double v0, v1;
+        if (kind == 0) {
+            const double rad = sqrt(-2.0 * log(u0));
+            double sn, cs;
+            sincospi(2.0 * u1, &sn, &cs);
+            v0 = rad * cs;
+            v1 = rad * sn;
+        } else {
+            v0 = u0;
+            v1 = u1;
+        }
+        const long long col = 2 * pc;
+        X[r * ldx + col] = v0;
+        if (col + 1 < ncols) X[r * ldx + col + 1] = v1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ batched small GEMM
+// C_b[M x N] = alpha * op(A_b) * B_b.  32x32 output tile per CTA (256 threads, 2x2 per thread), K in
+// chunks of 32 staged through shared memory.  TRANS_A: A_b is K x M row-major.
+template <bool TRANS_A>
+__global__ void __launch_bounds__(256) dgemm_batched_small_kernel(int M, int N, int K, double alpha,
+                                                                  const double* __restrict__ A, long long lda,
+                                                                  long long strideA, const double* __restrict__ B,
+                                                                  long long ldb, long long strideB,
+                                                                  double* __restrict__ C, long long ldc,
+                                                                  long long strideC) {
+    __shared__ double sA[32][33];  // [m][k]
+    __shared__ double sB[32][33];  // [k][n]
+    const long long b = blockIdx.z;
+    const double* Ab = A + b * strideA;
+    const double* Bb = B + b * strideB;
+    double* Cb = C + b * strideC;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each 2 x 2 outputs
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int e = threadIdx.x; e < 1024; e += 256) {
+            const int i = e >> 5, j = e & 31;
+            if (TRANS_A) {  // element (m = j, k = i) read with m fastest
+                const int k = k0 + i, mm = m0 + j;
+                sA[j][i] = (k < K && mm < M) ? Ab[(long long)k * lda + mm] : 0.0;
+            } else {  // element (m = i, k = j) read with k fastest
+                const int mm = m0 + i, k = k0 + j;
+                sA[i][j] = (k < K && mm < M) ? Ab[(long long)mm * lda + k] : 0.0;
+            }
+            const int kb = k0 + i, nn = n0 + j;
+            sB[i][j] = (kb < K && nn < N) ? Bb[(long long)kb * ldb + nn] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const double a0 = sA[ty][k], a1 = sA[ty + 16][k];
+            const double b0 = sB[k][tx], b1 = sB[k][tx + 16];
+            acc[0][0] = fma(a0, b0, acc[0][0]);
+            acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][0] = fma(a1, b0, acc[1][0]);
+            acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int mm = m0 + ty + 16 * i, nn = n0 + tx + 16 * j;
+            if (mm < M && nn < N) Cb[(long long)mm * ldc + nn] = alpha * acc[i][j];
+        }
+}
+
+static inline unsigned grid_1d(long long total, int per_block = 256) {
+    long long blocks = (total + per_block - 1) / per_block;
+    const long long cap = 32LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace hfb
+
+using namespace hfb;
+
+#define HFB_LAUNCHED()  \
+    do {                \
+        ++g_launch_count; \
+    } while (0)
+
+extern "C" int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind, const double* val,
+                            const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nrows <= 0 || m <= 0 || !rowptr || !colind || !val || !B || !C || ldb < m || ldc < m) return HFB_E_BADARG;
+    if (m > 512) return HFB_E_UNSUPPORTED;
+    if (B == C) return HFB_E_BADARG;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                        (ldb & 1) == 0 && (ldc & 1) == 0)
+                           ? 1
+                           : 0;
+    const int ch = (int)((m + 63) / 64);
+    long long blocks = (nrows + 7) / 8;  // 8 warps (rows) per CTA
+    const long long cap = 16LL * num_sms();
+    if (blocks > cap) blocks = cap;
+#define SPMM_CASE(CH)                                                                                               \
+    case CH:                                                                                                        \
+        csr_spmm_kernel<CH><<<(unsigned)blocks, 256, 0, stream>>>(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, \
+                                                                  vec_ok);                                          \
+        break;
+    switch (ch) {
+        SPMM_CASE(1) SPMM_CASE(2) SPMM_CASE(3) SPMM_CASE(4) SPMM_CASE(5) SPMM_CASE(6) SPMM_CASE(7) SPMM_CASE(8)
+        default: return HFB_E_UNSUPPORTED;
+    }
+#undef SPMM_CASE
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_csr_spmm_rows(int64_t nsamples, int64_t n, const int32_t* rowptr, const int32_t* colind,
+                                 const double* val, const double* X, int64_t ldx, double* C, int64_t ldc,
+                                 void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nsamples <= 0 || n <= 0 || !rowptr || !colind || !val || !X || !C || ldx < n || ldc < n || X == C)
+        return HFB_E_BADARG;
+    constexpr int SB = 16;
+    const long long by = (nsamples + SB - 1) / SB;
+    if (by > 65535) return HFB_E_UNSUPPORTED;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)by);
+    csr_spmm_rows_kernel<SB><<<grid, 256, 0, stream>>>(nsamples, n, rowptr, colind, val, X, ldx, C, ldc);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t hfb_coldot_workspace_bytes(int64_t n, int64_t m) {
+    if (n <= 0 || m <= 0) return 0;
+    return (size_t)reduce_parts(n, m) * (size_t)m * 8;
+}
+extern "C" int hfb_coldot(int64_t n, int64_t m, const double* X, int64_t ldx, const double* Y, int64_t ldy, double* out,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n <= 0 || m <= 0 || !X || !Y || !out || ldx < m || ldy < m) return HFB_E_BADARG;
+    const int parts = reduce_parts(n, m);
+    if (!workspace || workspace_bytes < (size_t)parts * (size_t)m * 8) return HFB_E_WORKSPACE;
+    const long long rpb = (n + parts - 1) / parts;
+    dim3 grid((unsigned)((m + 255) / 256), (unsigned)parts);
+    colreduce_stage1<<<grid, 256, 0, stream>>>(n, m, X, ldx, Y, ldy, rpb, (double*)workspace);
+    HFB_LAUNCHED();
+    colreduce_stage2<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(m, parts, (const double*)workspace, 1.0, out);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t hfb_colmean_workspace_bytes(int64_t N, int64_t n) {
+    if (N <= 0 || n <= 0) return 0;
+    return (size_t)reduce_parts(N, n) * (size_t)n * 8;
+}
+extern "C" int hfb_colsum(int64_t N, int64_t n, const double* X, int64_t ldx, double scale, double* out, void* workspace,
+                          size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N <= 0 || n <= 0 || !X || !out || ldx < n) return HFB_E_BADARG;
+    const int parts = reduce_parts(N, n);
+    if (!workspace || workspace_bytes < (size_t)parts * (size_t)n * 8) return HFB_E_WORKSPACE;
+    const long long rpb = (N + parts - 1) / parts;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)parts);
+    colreduce_stage1<<<grid, 256, 0, stream>>>(N, n, X, ldx, nullptr, 0, rpb, (double*)workspace);
+    HFB_LAUNCHED();
+    colreduce_stage2<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, parts, (const double*)workspace, scale, out);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_colscale(int64_t n, int64_t m, double* X, int64_t ldx, const double* s, void* stream_) {
+    if (n <= 0 || m <= 0 || !X || !s || ldx < m) return HFB_E_BADARG;
+    colscale_kernel<<<grid_1d(n * m), 256, 0, (cudaStream_t)stream_>>>(n, m, X, ldx, s);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+extern "C" int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, const double* shift, void* stream_) {
+    if (N <= 0 || n <= 0 || !X || !shift || ldx < n) return HFB_E_BADARG;
+    subtract_row_kernel<<<grid_1d(N * n), 256, 0, (cudaStream_t)stream_>>>(N, n, X, ldx, shift);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+extern "C" int hfb_axpby(int64_t n, int64_t m, double a, const double* X, int64_t ldx, double b, double* Y, int64_t ldy,
+                         void* stream_) {
+    if (n <= 0 || m <= 0 || !X || !Y || ldx < m || ldy < m) return HFB_E_BADARG;
+    axpby_kernel<<<grid_1d(n * m), 256, 0, (cudaStream_t)stream_>>>(n, m, a, X, ldx, b, Y, ldy);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+extern "C" int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64_t seed, int64_t row_offset,
+                               int kind, void* stream_) {
+    if (nrows <= 0 || ncols <= 0 || !X || ldx < ncols || kind < 0 || kind > 1) return HFB_E_BADARG;
+    fill_random_kernel<<<grid_1d(nrows * ((ncols + 1) / 2)), 256, 0, (cudaStream_t)stream_>>>(nrows, ncols, X, ldx, seed,
+                                                                                           row_offset, kind);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_dgemm_batched_small(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                                       int64_t lda, int64_t strideA, const double* B, int64_t ldb, int64_t strideB,
+                                       double* C, int64_t ldc, int64_t strideC, int64_t batch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if ((layout != HFB_NN && layout != HFB_TN) || M <= 0 || N <= 0 || K <= 0 || batch <= 0 || !A || !B || !C)
+        return HFB_E_BADARG;
+    if (lda < (layout == HFB_TN ? M : K) || ldb < N || ldc < N) return HFB_E_BADARG;
+    if (batch > 65535) {
+        // z-dimension limit: issue in slabs
+        for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+            const int64_t nb = (batch - b0 < 65535) ? batch - b0 : 65535;
+            int rc = hfb_dgemm_batched_small(layout, M, N, K, alpha, A + b0 * strideA, lda, strideA, B + b0 * strideB, ldb,
+                                             strideB, C + b0 * strideC, ldc, strideC, nb, stream_);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32), (unsigned)batch);
+    if (layout == HFB_TN)
+        dgemm_batched_small_kernel<true><<<grid, 256, 0, stream>>>((int)M, (int)N, (int)K, alpha, A, lda, strideA, B, ldb,
+                                                                   strideB, C, ldc, strideC);
+    else
+        dgemm_batched_small_kernel<false><<<grid, 256, 0, stream>>>((int)M, (int)N, (int)K, alpha, A, lda, strideA, B, ldb,
+                                                                    strideB, C, ldc, strideC);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}

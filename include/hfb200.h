@@ -1,0 +1,124 @@
+/*
+ * hfb200.h -- C ABI of the B200-native reduced-basis hot path (libhfb200.so).
+ *
+ * Drop-in boundary for the stored-data eigensolve/projection path of hIPPYflow
+ * (reference = /root/reference, pure Python; there is no native FFI in the reference, so each
+ * entry point cites the reference call site whose arithmetic it replaces).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); the library
+ *     never allocates or frees caller memory; workspace sizes come from *_workspace_bytes;
+ *   - every entry point takes a cudaStream_t (passed as void*) and is asynchronous on it;
+ *   - all dense matrices are float64, ROW-major with an explicit leading dimension (elements);
+ *     a hIPPYlib MultiVector of k vectors of length n is the dense (n, k) array of
+ *     hippyflow/utilities/mv_utilities.py:31-49 (column j = vector j);
+ *   - TMA operands (dgemm A and B) need a 16-byte aligned base and an EVEN leading dimension;
+ *   - return value: 0 ok, <0 invalid argument (HFB_E_*), >0 a cudaError_t / CUresult code.
+ */
+#ifndef HFB200_H
+#define HFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFB_OK 0
+#define HFB_E_BADARG (-1)     /* null pointer, non-positive dimension, unknown enum            */
+#define HFB_E_ALIGN (-2)      /* base not 16-byte aligned or odd leading dimension (TMA)       */
+#define HFB_E_WORKSPACE (-3)  /* workspace too small                                           */
+#define HFB_E_NODRIVER (-4)   /* cuTensorMapEncodeTiled not obtainable (no CUDA driver)        */
+#define HFB_E_UNSUPPORTED (-5)
+
+/* dgemm operand layouts: C[M x N] (row-major, ldc) = alpha * op(A) * op(B)                      */
+#define HFB_NN 0 /* A: M x K row-major (lda>=K);  B: K x N row-major (ldb>=N)                   */
+#define HFB_TN 1 /* A: K x M row-major (lda>=M), C = A^T B;  B: K x N row-major                 */
+#define HFB_NT 2 /* A: M x K row-major;  B: N x K row-major (ldb>=K), C = A B^T                 */
+
+/* Library / device info. hfb_version returns major*10000+minor*100+patch. */
+int hfb_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t hfb_launch_count(void);
+
+/*
+ * FP64 tensor-core (DMMA.8x8x4) GEMM fed by TMA, deterministic split-K.
+ * Replaces, on stored data:
+ *   - W = X^T B  and  Y = X W  of the sample-averaged operator applies
+ *       hp.LowRankOperator.mult            (hippyflow/modeling/PODProjector.py:360, one column per call)
+ *       MeanJTJfromDataOperator.mult       (hippyflow/modeling/operatorWrappers.py:95-114, two einsums)
+ *       H_matvec = MX @ (MX.T @ x)/n_data  (hippyflow/modeling/PODProjector.py:753-754)
+ *   - Gram matrices u_data.T @ M @ u_data  (PODProjector.py:818), T = (AQ)^T Q (hIPPYlib doublePass),
+ *   - lifts phi = u_data @ U               (PODProjector.py:826), U = Q V (hIPPYlib MvDSmatMult),
+ *   - projections data @ encoder, J_i Psi  (dataGenerator.py:177), J_i^T (M Phi) (dataGenerator.py:170,339).
+ * splits: 0 = choose automatically; otherwise the K range is cut into `splits` parts whose partial
+ * tiles go to `workspace` and are summed in fixed order (bitwise run-to-run reproducible).
+ */
+size_t hfb_dgemm_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int splits);
+int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alpha,
+              const double* A, int64_t lda, const double* B, int64_t ldb,
+              double* C, int64_t ldc, void* workspace, size_t workspace_bytes, int splits,
+              void* stream);
+/* The split count hfb_dgemm would choose for splits=0. */
+int hfb_dgemm_auto_splits(int layout, int64_t M, int64_t N, int64_t K);
+
+/*
+ * Batched small GEMM over the sample axis:  C_i[M x N] = alpha * op(A_i) * B_i  for i < batch,
+ * with element strides between consecutive samples (stride 0 = shared operand).
+ * layout is HFB_NN or HFB_TN.  One CTA per (sample, tile); CUDA-core DFMA (operands are tiny).
+ * Replaces: einsum('ij,kj->ki', noise_cov_inv, JX) (operatorWrappers.py:107-109) and the per-sample
+ * products Phi^T (J_i V) of the reduced Jacobians (dataGenerator.py:170-177, north star (c)).
+ */
+int hfb_dgemm_batched_small(int layout, int64_t M, int64_t N, int64_t K, double alpha,
+                            const double* A, int64_t lda, int64_t strideA,
+                            const double* B, int64_t ldb, int64_t strideB,
+                            double* C, int64_t ldc, int64_t strideC, int64_t batch, void* stream);
+
+/*
+ * CSR SpMM  C[n x m] = Mat * B[n x m]  (dense row-major), int32 CSR as exported by the reference
+ * (PODProjector.py:695-697).  Replaces M_csr @ phi (PODProjector.py:750,769,830), hp.MatMvMult(M, decoder,
+ * encoder) (KLEProjector.py:167-168, activeSubspaceProjector.py:452-453,559-560) and the B-applies inside
+ * hIPPYlib's Borthogonalize.
+ */
+int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind,
+                 const double* val, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
+/*
+ * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.
+ * (M X)^T for symmetric M with X stored as u_data (N, n)  (PODProjector.py:750, 818).
+ */
+int hfb_csr_spmm_rows(int64_t nsamples, int64_t n, const int32_t* rowptr, const int32_t* colind,
+                      const double* val, const double* X, int64_t ldx, double* C, int64_t ldc, void* stream);
+
+/* out[j] = sum_i X[i,j] * Y[i,j]  (j < m): diag(X^T Y); weighted_l2_norm_vector (PODProjector.py:658-661)
+ * is sqrt of this with Y = W X.  Deterministic two-stage reduction; workspace >= hfb_coldot_workspace_bytes. */
+size_t hfb_coldot_workspace_bytes(int64_t n, int64_t m);
+int hfb_coldot(int64_t n, int64_t m, const double* X, int64_t ldx, const double* Y, int64_t ldy,
+               double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* X[i,j] *= s[j]  (column scaling, e.g. phi / weighted_l2_norm_vector, PODProjector.py:829). */
+int hfb_colscale(int64_t n, int64_t m, double* X, int64_t ldx, const double* s, void* stream);
+
+/* mean[j] = (1/N) sum_i X[i,j] over the sample axis (np.mean(u_data, axis=0), PODProjector.py:733);
+ * deterministic; workspace >= hfb_colmean_workspace_bytes. */
+size_t hfb_colmean_workspace_bytes(int64_t N, int64_t n);
+int hfb_colsum(int64_t N, int64_t n, const double* X, int64_t ldx, double scale, double* out,
+               void* workspace, size_t workspace_bytes, void* stream);
+/* X[i,j] -= shift[j]  (u_data - u_shift, PODProjector.py:734). */
+int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, const double* shift, void* stream);
+
+/* Y = a*X + b*Y elementwise on an (n x m) block (axpy/scale of MultiVectors; 'avg' scaling of
+ * collective.py:65-68 after the NCCL sum). */
+int hfb_axpby(int64_t n, int64_t m, double a, const double* X, int64_t ldx, double b, double* Y, int64_t ldy,
+              void* stream);
+
+/* Counter-based Gaussian/uniform fill keyed by (seed, global row, column): data generated on device is
+ * independent of how samples are sharded. kind 0 = N(0,1), 1 = U(0,1). */
+int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64_t seed, int64_t row_offset,
+                    int kind, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFB200_H */
