@@ -58,6 +58,8 @@ def lib():
         "hfb_colsum": (i32, [i64, i64, vp, i64, dbl, vp, vp, sz, vp]),
         "hfb_subtract_row": (i32, [i64, i64, vp, i64, vp, vp]),
         "hfb_axpby": (i32, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
+        "hfb_axpby_cols": (i32, [i64, i64, vp, vp, i64, vp, vp, i64, vp]),
+        "hfb_rowscale": (i32, [i64, i64, vp, vp, i64, vp, i64, vp]),
         "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -71,7 +73,7 @@ def lib():
 EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
-            "hfb_axpby", "hfb_fill_random"]
+            "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random"]
 
 
 def _check(rc, what):
@@ -257,6 +259,26 @@ def axpby_(a, X, b, Y):
     rc = L.hfb_axpby(X.shape[0], X.shape[1], float(a), X.data_ptr(), _ld(X), float(b), Y.data_ptr(), _ld(Y), _stream())
     _check(rc, "hfb_axpby")
     return Y
+
+
+def axpby_cols_(a, X, b, Y):
+    """Y[:, j] = a[j] X[:, j] + b[j] Y[:, j]; a / b are device vectors or None (= 1)."""
+    L = lib()
+    _req(X, "X"), _req(Y, "Y")
+    rc = L.hfb_axpby_cols(X.shape[0], X.shape[1], a.data_ptr() if a is not None else None, X.data_ptr(), _ld(X),
+                          b.data_ptr() if b is not None else None, Y.data_ptr(), _ld(Y), _stream())
+    _check(rc, "hfb_axpby_cols")
+    return Y
+
+
+def rowscale(s, X, out=None):
+    L = lib()
+    _req(X, "X")
+    if out is None:
+        out = padded_empty(X.shape[0], X.shape[1], X.device)
+    rc = L.hfb_rowscale(X.shape[0], X.shape[1], s.data_ptr(), X.data_ptr(), _ld(X), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_rowscale")
+    return out
 
 
 def fill_random_(X, seed, row_offset=0, kind="normal"):

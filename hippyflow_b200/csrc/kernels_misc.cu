@@ -175,6 +175,32 @@ __global__ void __launch_bounds__(256) axpby_kernel(long long n, long long m, do
     }
 }
 
+__global__ void __launch_bounds__(256) axpby_cols_kernel(long long n, long long m, const double* __restrict__ a,
+                                                         const double* __restrict__ X, long long ldx,
+                                                         const double* __restrict__ b, double* __restrict__ Y,
+                                                         long long ldy) {
+    const long long total = n * m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / m;
+        const long long c = idx - r * m;
+        const double av = a ? a[c] : 1.0, bv = b ? b[c] : 1.0;
+        const double y = (bv == 0.0) ? 0.0 : bv * Y[r * ldy + c];
+        Y[r * ldy + c] = fma(av, X[r * ldx + c], y);
+    }
+}
+__global__ void __launch_bounds__(256) rowscale_kernel(long long n, long long m, const double* __restrict__ s,
+                                                       const double* __restrict__ X, long long ldx,
+                                                       double* __restrict__ Y, long long ldy) {
+    const long long total = n * m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / m;
+        const long long c = idx - r * m;
+        Y[r * ldy + c] = s[r] * X[r * ldx + c];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ random fill
 // Philox-4x32-10 keyed by seed, counter = (global row, column pair); Box-Muller for normals.
 __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -390,6 +416,20 @@ extern "C" int hfb_axpby(int64_t n, int64_t m, double a, const double* X, int64_
                          void* stream_) {
     if (n <= 0 || m <= 0 || !X || !Y || ldx < m || ldy < m) return HFB_E_BADARG;
     axpby_kernel<<<grid_1d(n * m), 256, 0, (cudaStream_t)stream_>>>(n, m, a, X, ldx, b, Y, ldy);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+extern "C" int hfb_axpby_cols(int64_t n, int64_t m, const double* a, const double* X, int64_t ldx, const double* b,
+                              double* Y, int64_t ldy, void* stream_) {
+    if (n <= 0 || m <= 0 || !X || !Y || ldx < m || ldy < m) return HFB_E_BADARG;
+    axpby_cols_kernel<<<grid_1d(n * m), 256, 0, (cudaStream_t)stream_>>>(n, m, a, X, ldx, b, Y, ldy);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+extern "C" int hfb_rowscale(int64_t n, int64_t m, const double* s, const double* X, int64_t ldx, double* Y, int64_t ldy,
+                            void* stream_) {
+    if (n <= 0 || m <= 0 || !s || !X || !Y || ldx < m || ldy < m) return HFB_E_BADARG;
+    rowscale_kernel<<<grid_1d(n * m), 256, 0, (cudaStream_t)stream_>>>(n, m, s, X, ldx, Y, ldy);
     HFB_LAUNCHED();
     return (int)cudaGetLastError();
 }

@@ -1,0 +1,246 @@
+"""Device-side building blocks of the sample-averaged randomized eigensolves.
+
+Everything numerical here is a call into libhfb200.so (``_lib``); the only host arithmetic is the
+O(m^3) work on (m x m) matrices (Cholesky / eigh of Gram matrices and of T), which the reference also
+does on the host with NumPy (hIPPYlib ``doublePass``: ``np.linalg.eigh(T)``).
+
+Layouts ("operand layouts are fixed by the reference"):
+  * stored samples ``Xt``: (R, n) row-major, rows = samples -- ``u_data`` (N, n) of
+    PODProjector.py:726, ``m_data``, or stored Jacobians (N, dQ, dM) viewed as (N*dQ, dM)
+    (operatorWrappers.py:62-64);
+  * sketches / bases: (n, m) row-major, column j = vector j (mv_utilities.py:31-49).
+"""
+import numpy as np
+import scipy.linalg as sla
+import torch
+
+from . import _lib as K
+
+
+class CsrMatrix:
+    """Sparse SPD weight matrix (mass matrix M, prior precision R) resident on the device as int32 CSR,
+    the format the reference exports (PODProjector.py:695-697)."""
+
+    def __init__(self, M_csr, device):
+        M = M_csr.tocsr()
+        M.sort_indices()
+        self.shape = M.shape
+        self.nnz = M.nnz
+        self.device = device
+        self.rowptr = torch.as_tensor(np.asarray(M.indptr, dtype=np.int32), device=device)
+        self.colind = torch.as_tensor(np.asarray(M.indices, dtype=np.int32), device=device)
+        self.val = torch.as_tensor(np.asarray(M.data, dtype=np.float64), device=device)
+
+    def matmat(self, B, out=None):
+        """out (n, m) = M @ B for a dense row-major (n, m) block."""
+        return K.csr_spmm(self.rowptr, self.colind, self.val, B, out)
+
+    def matmat_rows(self, X, out=None):
+        """out (N, n): row i = M @ X[i]  (= (M X^T)^T for sample-major X)."""
+        return K.csr_spmm_rows(self.rowptr, self.colind, self.val, X, out)
+
+    def spmm_bytes(self, m):
+        """Algorithmic bytes of one SpMM with m columns."""
+        n = self.shape[0]
+        return self.nnz * 12 + (n + 1) * 4 + 2 * n * m * 8
+
+
+class SampleCovariance:
+    """Local shard of the sample-averaged operator  C = (1/N) sum_i X_i X_i^T  (optionally with a
+    per-sample weight Gamma^-1 between the factors), held as the stacked row-major array ``Xt``.
+
+    One object serves all three projectors:
+      POD  : X_i = u_i                      (hp.LowRankOperator(ones/N, U), PODProjector.py:360)
+      AS   : X_i = J_i^T, Gamma^-1 optional (MeanJTJfromDataOperator.mult, operatorWrappers.py:95-114)
+      KLE  : X_i = m_i                      (sample covariance in place of prior.Rsolver, KLEProjector.py:103)
+    ``apply`` is the two-GEMM form  Y = Xt^T (G (Xt B)) / N_loc  of those column-by-column loops.
+    """
+
+    def __init__(self, Xt, block=1, noise_cov_inv=None):
+        self.Xt = K._req(Xt, "Xt")
+        self.rows, self.n = Xt.shape
+        self.block = int(block)  # rows per sample (dQ for Jacobians, 1 for snapshots)
+        assert self.rows % self.block == 0
+        self.nsamples = self.rows // self.block
+        self.noise_cov_inv = None
+        if noise_cov_inv is not None:
+            G = torch.as_tensor(np.asarray(noise_cov_inv, dtype=np.float64), device=Xt.device)
+            assert tuple(G.shape) == (self.block, self.block)
+            self.noise_cov_inv = G.contiguous()
+        self._W = None
+
+    def _wbuf(self, m):
+        if self._W is None or self._W.shape[1] != m:
+            self._W = K.padded_empty(self.rows, m, self.Xt.device)
+            self._W2 = K.padded_empty(self.rows, m, self.Xt.device) if self.noise_cov_inv is not None else None
+        return self._W
+
+    def project(self, B):
+        """W (R, m) = Xt @ B  (and Gamma^-1 applied per sample block when present).  Returns (W, GW)
+        where GW = blockdiag(Gamma^-1) W (or W itself)."""
+        m = B.shape[1]
+        W = self._wbuf(m)
+        K.dgemm(K.HFB_NN, self.Xt, B, out=W)
+        if self.noise_cov_inv is None:
+            return W, W
+        q = self.block
+        W3 = W.as_strided((self.nsamples, q, m), (q * W.stride(0), W.stride(0), 1))
+        GW3 = self._W2.as_strided((self.nsamples, q, m), (q * self._W2.stride(0), self._W2.stride(0), 1))
+        K.dgemm_batched_small(K.HFB_NN, self.noise_cov_inv.unsqueeze(0), W3, GW3)
+        return W, self._W2
+
+    def apply(self, B, out=None, scale=None):
+        """out (n, m) = scale * Xt^T G Xt B with scale = 1/nsamples by default (the local 'average'
+        of SummedListOperator(average=True) / LowRankOperator(ones/N_loc))."""
+        _, GW = self.project(B)
+        if scale is None:
+            scale = 1.0 / self.nsamples
+        return K.dgemm(K.HFB_TN, self.Xt, GW, out=out, alpha=scale)
+
+    def gram_T(self, B, scale=None):
+        """T_local (m, m) = scale * (Xt B)^T G (Xt B): the Rayleigh quotient B^T C B without forming C B
+        (SURVEY.md 7 'T = Q^T A Q shortcut')."""
+        W, GW = self.project(B)
+        if scale is None:
+            scale = 1.0 / self.nsamples
+        return K.dgemm(K.HFB_TN, W, GW, alpha=scale)
+
+    def flops_apply(self, m):
+        return 4.0 * self.rows * self.n * m
+
+    def flops_project(self, m):
+        return 2.0 * self.rows * self.n * m
+
+
+def _sym(G):
+    return 0.5 * (G + G.T)
+
+
+def b_orthonormalize(Y, Bmat=None, max_passes=4, return_BQ=True):
+    """Orthonormalise the columns of the sketch Y (n, m) in the inner product of the sparse SPD matrix
+    ``Bmat`` (None = Euclidean): the role of MultiVector.Borthogonalize / orthogonalize inside hIPPYlib's
+    doublePassG / doublePass.
+
+    hIPPYlib does column-by-column modified Gram-Schmidt (level-1 BLAS, one B-apply per column).  Here the
+    same subspace is orthonormalised with GEMM-shaped passes: Z = B Y (SpMM), G = Y^T Z (DMMA, split-K),
+    host factorisation of the column-scaled (m x m) Gram matrix, Y <- Y S (DMMA).  Cholesky is used when
+    the scaled Gram matrix is numerically positive definite; otherwise an eigen-decomposition with
+    truncation, which -- like hIPPYlib's MGS -- returns ZERO columns for numerically dependent directions.
+    Eigenvalues d and span(U) of the eigensolve do not depend on which B-orthonormal basis of span(Y) is
+    used.  Returns (Q, BQ, info); Q overwrites Y's storage when possible."""
+    n, m = Y.shape
+    eps = np.finfo(np.float64).eps
+    info = {"passes": 0, "truncated": 0, "cond": []}
+    Z = None
+    for it in range(max_passes):
+        Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
+        G = K.dgemm(K.HFB_TN, Y, Z).cpu().numpy()
+        G = _sym(G)
+        d = np.sqrt(np.maximum(np.diag(G), 0.0))
+        dead = d <= 0.0
+        dinv = np.where(dead, 0.0, 1.0 / np.where(dead, 1.0, d))
+        Gs = G * np.outer(dinv, dinv)
+        off = np.abs(Gs - np.diag(np.diag(Gs))).max() if m > 1 else 0.0
+        if it > 0 and off < 64 * eps and np.abs(d[~dead] - 1.0).max(initial=0.0) < 64 * eps:
+            break  # already B-orthonormal to round-off: nothing to apply
+        S = None
+        if not dead.any():
+            try:
+                R = sla.cholesky(Gs, lower=False, check_finite=False)
+                rd = np.abs(np.diag(R))
+                cond = (rd.max() / rd.min()) ** 2
+                if np.isfinite(cond) and cond < 1e14:
+                    S = sla.solve_triangular(R, np.eye(m), lower=False, check_finite=False) * dinv[:, None]
+                    info["cond"].append(float(cond))
+            except (np.linalg.LinAlgError, sla.LinAlgError):
+                S = None
+        if S is None:
+            w, V = np.linalg.eigh(Gs)
+            keep = w > max(m * eps * w.max(), 0.0) * 10.0
+            S = np.zeros((m, m))
+            S[:, : keep.sum()] = (V[:, keep] / np.sqrt(w[keep])) * dinv[:, None]
+            info["truncated"] = int(m - keep.sum())
+            info["cond"].append(float(w.max() / max(w[keep].min(), 1e-300)))
+        Sd = K.to_padded(S, Y.device)
+        Qn = K.dgemm(K.HFB_NN, Y, Sd)
+        Y.copy_(Qn)
+        info["passes"] += 1
+        if info["cond"][-1] * eps * m < 1e-3 and it >= 1:
+            # previous pass left cond(G) ~ 1: this pass is accurate to round-off
+            Z = None
+            break
+    Q = Y
+    BQ = None
+    if return_BQ:
+        BQ = Bmat.matmat(Q) if Bmat is not None else Q
+    return Q, BQ, info
+
+
+def top_k_eig(T, k):
+    """eigh of the small symmetric matrix T on the host, top-k descending
+    (hIPPYlib doublePass: np.linalg.eigh(T), sort descending, keep k)."""
+    T = _sym(np.asarray(T))
+    d, V = np.linalg.eigh(T)
+    perm = np.argsort(d)[::-1][:k]
+    return d[perm], np.ascontiguousarray(V[:, perm])
+
+
+class CsrCGSolver:
+    """Block conjugate gradients with a Jacobi preconditioner for a sparse SPD matrix on the device: the role
+    of ``prior.Msolver`` / ``prior.Rsolver`` inside ``doublePassG`` (KLEProjector.py:163,
+    activeSubspaceProjector.py:449) when the weight matrix is available as CSR.  All m right-hand sides advance
+    together (SpMM + per-column dots/axpys); each column has its own step lengths.  Intended for mass-matrix-like
+    (well conditioned) B; PDE-operator priors keep their upstream solvers."""
+
+    def __init__(self, Bmat, rel_tol=1e-13, max_iter=1000, check_every=8):
+        self.B = Bmat
+        self.rel_tol, self.max_iter, self.check_every = rel_tol, max_iter, check_every
+        n = Bmat.shape[0]
+        dev = Bmat.device
+        # diagonal of B from the CSR arrays
+        rows = torch.repeat_interleave(torch.arange(n, device=dev), (Bmat.rowptr[1:] - Bmat.rowptr[:-1]).long())
+        diag = torch.zeros(n, dtype=torch.float64, device=dev)
+        mask = rows == Bmat.colind.long()
+        diag[rows[mask]] = Bmat.val[mask]
+        self.dinv = 1.0 / diag
+        self.iterations = 0
+
+    def solve_block(self, Y):
+        n, m = Y.shape
+        dev = Y.device
+        X = K.padded_zeros(n, m, dev)
+        R = K.padded_empty(n, m, dev)
+        R.copy_(Y)
+        Z = K.rowscale(self.dinv, R)
+        P = K.padded_empty(n, m, dev)
+        P.copy_(Z)
+        AP = K.padded_empty(n, m, dev)
+        rz = K.coldot(R, Z)
+        r0 = torch.sqrt(K.coldot(R, R))
+        r0 = torch.where(r0 > 0, r0, torch.ones_like(r0))
+        for it in range(self.max_iter):
+            self.B.matmat(P, out=AP)
+            pAp = K.coldot(P, AP)
+            alpha = torch.where(pAp > 0, rz / pAp, torch.zeros_like(rz))
+            K.axpby_cols_(alpha, P, None, X)
+            K.axpby_cols_(-alpha, AP, None, R)
+            if (it + 1) % self.check_every == 0:
+                rn = torch.sqrt(K.coldot(R, R))
+                if bool(((rn / r0) < self.rel_tol).all()):
+                    self.iterations = it + 1
+                    break
+            K.rowscale(self.dinv, R, out=Z)
+            rz_new = K.coldot(R, Z)
+            beta = torch.where(rz > 0, rz_new / rz, torch.zeros_like(rz))
+            rz = rz_new
+            K.axpby_cols_(None, Z, beta, P)
+        else:
+            self.iterations = self.max_iter
+        return X
+
+    def solve(self, x, b):
+        """hippylib solver signature: solve(x, b) writes B^-1 b into x (vectors)."""
+        x.storage_tensor().copy_(self.solve_block(b.storage_tensor()))
+
+    def init_vector(self, x, dim):
+        x.init(self.B.shape[0])

@@ -1,0 +1,239 @@
+"""POD output bases on the device: drop-in counterparts of hippyflow/modeling/PODProjector.py.
+
+``PODProjectorFromData`` keeps the reference signature and return values (PODProjector.py:666-852) and adds
+``method='randomized'``: the M-weighted double-pass solve of the GHEP written at PODProjector.py:750-761
+(A = M X X^T M / N, B = M).  ``PODProjector`` is the collective double-pass path of PODProjector.py:331-390
+for snapshots that are already stored (the PDE solves at :343-357 are upstream).
+"""
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from .. import _lib as K
+from ..collectives import NullCollective
+from ..linalg import CsrMatrix, SampleCovariance
+from ..multivector import DeviceMultiVector, mv_to_dense
+from ..parameterList import ParameterList
+from ..randomized import doublePass, doublePassG
+from .operators import SampleCovarianceOperator, SandwichedCovarianceOperator, _as_device_rows
+
+
+def PODParameterList():
+    """PODProjector.py:35-49."""
+    parameters = {}
+    parameters['sample_per_process'] = [100, 'Number of samples per process']
+    parameters['rank'] = [20, 'Rank of POD subspace']
+    parameters['oversampling'] = [10, 'Oversampling parameter for randomized algorithms']
+    parameters['data_per_process'] = [250, 'Total number of testing and training data to be constructed']
+    parameters['verbose'] = [True, 'Boolean for prints']
+    parameters['output_directory'] = [None, 'output directory for saving arrays and plots']
+    parameters['plot_label_suffix'] = ['', 'suffix for plot label']
+    parameters['save_and_plot'] = [True, 'save the projector arrays (plots are out of scope)']
+    parameters['omega_seed'] = [1, 'seed of the Gaussian test matrix when none is supplied']
+    return ParameterList(parameters)
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("hippyflow_b200 needs a CUDA device: the hot path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_scipy_csr(M):
+    """Accept a SciPy sparse matrix, or a dolfin/PETSc matrix the way the reference does
+    (``dl.as_backend_type(M).mat().getValuesCSR()``, PODProjector.py:695-697)."""
+    if sp.issparse(M):
+        return M.tocsr()
+    if hasattr(M, "mat"):
+        row, col, val = M.mat().getValuesCSR()
+        return sp.csr_matrix((val, col, row))
+    if hasattr(M, "getValuesCSR"):
+        row, col, val = M.getValuesCSR()
+        return sp.csr_matrix((val, col, row))
+    raise TypeError("M_output must be a scipy.sparse matrix or expose getValuesCSR()")
+
+
+def gaussian_omega(n, m, seed, device):
+    """Host-generated Gaussian test matrix (role of hp.parRandom.normal(1., Omega), PODProjector.py:367-372)
+    uploaded as a device multivector; the same (seed, n, m) gives the same Omega on every rank."""
+    Om = np.random.default_rng(seed).standard_normal((n, m))
+    return DeviceMultiVector.from_dense(Om, device)
+
+
+def weighted_l2_norm_vector(x, W):
+    """sqrt(diag(x^T W x)) per column (PODProjector.py:658-661); x a device block, W a CsrMatrix."""
+    Wx = W.matmat(x)
+    return torch.sqrt(K.coldot(Wx, x))
+
+
+class PODProjectorFromData:
+    """M-weighted POD from a stored (n_data, dim_u) snapshot array."""
+
+    def __init__(self, Vh=None, M_output=None, device=None):
+        """``Vh`` is kept for signature compatibility (PODProjector.py:670); the weighting matrix must be
+        given as ``M_output`` (SciPy CSR, or a PETSc-backed matrix) because FEniCS assembly is upstream."""
+        self.Vh = Vh
+        if M_output is None:
+            raise ValueError("M_output is required: assembling the mass matrix from Vh needs FEniCS (upstream)")
+        self.M = M_output
+        self.M_csr = _to_scipy_csr(M_output)
+        self.device = device if device is not None else _default_device()
+        self._Md = None
+        self.timings = {}
+
+    @property
+    def M_device(self):
+        if self._Md is None:
+            self._Md = CsrMatrix(self.M_csr, self.device)
+        return self._Md
+
+    def construct_subspace(self, u_data, u_rank, shifted=True, method='hep', verify=False,
+                           oversampling=10, Omega=None, collective=None, return_device=False, faithful=False):
+        """Same contract as PODProjector.py:699-852: returns (d, phi, Mphi, u_shift) as NumPy arrays of shape
+        (r,), (n, r), (n, r), (n,).  ``u_data`` may be a NumPy array or a float64 CUDA tensor (rows = samples;
+        with a collective, the local shard).  Extra keywords (randomized method only): ``oversampling``,
+        ``Omega`` ((n, r+p) array or DeviceMultiVector fed to the solver), ``collective`` (sample-parallel)."""
+        n_data, dim_u = u_data.shape
+        collective = collective if collective is not None else NullCollective()
+        n_total = n_data * collective.size()
+        assert u_rank <= n_total, "number of samples needs to be greater than rank of projector"
+        if method not in ('hep', 'ghep', 'inverse_ghep', 'randomized'):
+            raise ValueError("Unavailable method")
+        dev = self.device
+        Md = self.M_device
+        t0 = time.time()
+        owns = not (isinstance(u_data, torch.Tensor) and u_data.is_cuda)
+        Xt = _as_device_rows(u_data, dev)
+        if shifted:
+            # u_shift = mean over ALL samples (np.mean(u_data, axis=0), PODProjector.py:733), then X - shift
+            u_shift_d = K.colsum(Xt, 1.0 / n_data)
+            collective.allReduce(u_shift_d, 'avg')
+            if not owns:
+                Xc = K.padded_empty(n_data, dim_u, dev)
+                Xc.copy_(Xt)
+                Xt = Xc
+            K.subtract_row_(Xt, u_shift_d)
+        else:
+            u_shift_d = torch.zeros(dim_u, dtype=torch.float64, device=dev)
+        self.timings['upload_shift'] = time.time() - t0
+
+        t1 = time.time()
+        if method == 'randomized':
+            d, phi_d, Mphi_d = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful)
+        else:
+            if collective.size() != 1:
+                raise NotImplementedError("method='%s' is serial like the reference (PODProjector.py:683); "
+                                          "use method='randomized' with a collective" % method)
+            d, phi_d, Mphi_d = self._snapshot_eig(Xt, Md, u_rank, method)
+        torch.cuda.synchronize(dev)
+        self.timings['eigensolve'] = time.time() - t1
+
+        if verify:
+            r = u_rank - 1 if shifted else u_rank
+            G = K.dgemm(K.HFB_TN, phi_d[:, :r], Mphi_d[:, :r]).cpu().numpy()
+            print(f"Basis-Projector Orthogonality error: {np.linalg.norm(G - np.eye(r))}")
+            coef = K.dgemm(K.HFB_NN, Xt, Mphi_d[:, :r])                       # (N, r)
+            rec = K.dgemm(K.HFB_NT, coef, phi_d[:, :r])                       # (N, n)
+            K.axpby_(1.0, Xt, -1.0, rec)
+            err = torch.sqrt(K.coldot(Md.matmat_rows(rec).t().contiguous(), rec.t().contiguous())) \
+                if n_data <= 512 else None
+            if err is not None:
+                nrm = torch.sqrt(K.coldot(Md.matmat_rows(Xt).t().contiguous(), Xt.t().contiguous()))
+                rel = (err / nrm).cpu().numpy()
+                print(f"Mean reconstruction error: {np.mean(rel):.3e}")
+                print(f"Max reconstruction error: {np.max(rel):.3e}")
+        if return_device:
+            return d, phi_d, Mphi_d, u_shift_d
+        return d, phi_d.cpu().numpy().copy(), Mphi_d.cpu().numpy().copy(), u_shift_d.cpu().numpy()
+
+    # ---------------------------------------------------------------- randomized GHEP (north star (a))
+    def _randomized(self, Xt, Md, u_rank, oversampling, Omega, collective, faithful):
+        n = Xt.shape[1]
+        m = u_rank + oversampling
+        if Omega is None:
+            Omega = gaussian_omega(n, m, 1, self.device)
+        elif not isinstance(Omega, DeviceMultiVector):
+            Omega = DeviceMultiVector.from_dense(Omega, self.device)
+        assert Omega.nvec() >= u_rank
+        C = SampleCovarianceOperator(SampleCovariance(Xt), collective, 'avg')
+        A = SandwichedCovarianceOperator(C, Md)
+        self.info = {}
+        d, U = doublePassG(A, Md, None, Omega, u_rank, s=1, faithful=faithful, info=self.info)
+        Mphi = Md.matmat(U.tensor())
+        return d, U.tensor(), Mphi
+
+    # ---------------------------------------------------------------- method of snapshots ('hep' :812-833)
+    def _snapshot_eig(self, Xt, Md, u_rank, method):
+        n_data, n = Xt.shape
+        Zt = Md.matmat_rows(Xt)                                   # (M X)^T, sample-major
+        G = K.dgemm(K.HFB_NT, Xt, Zt)                             # X^T M X  (N x N)
+        del Zt
+        Gs = 0.5 * (G + G.t())
+        if n_data <= 1024:
+            s, Uh = np.linalg.eigh(Gs.cpu().numpy())
+            Uh = torch.as_tensor(Uh, device=self.device)
+        else:
+            s, Uh = torch.linalg.eigh(Gs.contiguous())
+            s = s.cpu().numpy()
+        d = s[::-1][:u_rank] / n_data
+        Usel = K.to_padded(torch.flip(Uh, dims=[1])[:, :u_rank], self.device)
+        phi = K.dgemm(K.HFB_TN, Xt, Usel)                         # X U  (n x r)
+        nrm = weighted_l2_norm_vector(phi, Md)
+        K.colscale_(phi, 1.0 / nrm)
+        Mphi = Md.matmat(phi)
+        return np.ascontiguousarray(d), phi, Mphi
+
+
+class StoredSnapshots:
+    """Stand-in for the ``observable`` argument of PODProjector when the snapshots q_i = B u(m_i) are already
+    stored: ``snapshots`` is the local (N_loc, n) array (host or device)."""
+
+    def __init__(self, snapshots):
+        self.snapshots = snapshots
+
+
+class PODProjector:
+    """Collective double-pass POD of stored snapshots (PODProjector.py:52-390, eigensolve part :359-384)."""
+
+    def __init__(self, observable, prior=None, control_distribution=None, mesh_constructor_comm=None,
+                 collective=None, parameters=None, device=None):
+        self.observable = observable
+        self.prior = prior
+        self.control_distribution = control_distribution
+        self.mesh_constructor_comm = mesh_constructor_comm
+        self.collective = collective if collective is not None else NullCollective()
+        self.parameters = parameters if parameters is not None else PODParameterList()
+        self.device = device if device is not None else _default_device()
+        self.d = None
+        self.U_MV = None
+        self.Omega = None
+
+    def construct_subspace(self, Omega=None):
+        t0 = time.time()
+        snaps = self.observable.snapshots
+        Xt = _as_device_rows(snaps, self.device)
+        n = Xt.shape[1]
+        # LocalPODOperator = LowRankOperator(ones/N_loc, LocalObservables); Global = CollectiveOperator(.., 'avg')
+        A = SampleCovarianceOperator(SampleCovariance(Xt), self.collective, 'avg')
+        m = self.parameters['rank'] + self.parameters['oversampling']
+        if Omega is None:
+            # rank 0 draws, everybody else zero, then bcast (PODProjector.py:367-374)
+            if self.collective.rank() == 0:
+                Omega = gaussian_omega(n, m, self.parameters['omega_seed'], self.device)
+            else:
+                Omega = DeviceMultiVector(n, m, device=self.device)
+            self.collective.bcast(Omega, root=0)
+        elif not isinstance(Omega, DeviceMultiVector):
+            Omega = DeviceMultiVector.from_dense(Omega, self.device)
+        self.Omega = Omega
+        self.d, self.U_MV = doublePass(A, Omega, self.parameters['rank'], s=1)
+        torch.cuda.synchronize(self.device)
+        self._subspace_construction_time = time.time() - t0
+        if self.parameters['verbose'] and self.collective.rank() == 0:
+            print('Construction of POD subspace took ', self._subspace_construction_time, 's')
+        if self.parameters['save_and_plot'] and self.collective.rank() == 0 and self.parameters['output_directory'] is not None:
+            np.save(self.parameters['output_directory'] + 'POD_projector', mv_to_dense(self.U_MV))
+            np.save(self.parameters['output_directory'] + 'POD_d', self.d)
+        return self.d, self.U_MV

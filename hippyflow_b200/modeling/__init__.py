@@ -1,0 +1,6 @@
+from .PODProjector import PODParameterList, PODProjector, PODProjectorFromData, StoredSnapshots, weighted_l2_norm_vector
+from .KLEProjector import KLEParameterList, KLEProjector, MassPreconditionedCovarianceOperator, SampleCovariancePrior
+from .activeSubspaceProjector import (ActiveSubspaceParameterList, ActiveSubspaceProjector, SparsePrior,
+                                      StoredJacobians)
+from .operators import MeanJTJfromDataOperator, SampleCovarianceOperator, SandwichedCovarianceOperator
+from .projection import jacobian_action, jacobian_transpose_action, project_data, reduced_jacobians

@@ -1,0 +1,170 @@
+"""Active-subspace input/output bases from STORED Jacobians on the device: counterpart of
+hippyflow/modeling/activeSubspaceProjector.py:252-673 (eigensolve call sites :447-463, :553-577, :654).
+Generating the Jacobians (adjoint PDE solves, :690-1044) is upstream; here ``observable`` carries the local
+(N_loc, dQ, dM) array, as the user of ``MeanJTJfromDataOperator`` (operatorWrappers.py:55-121) would hold it."""
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib as K
+from ..collectives import NullCollective
+from ..linalg import CsrMatrix, CsrCGSolver, SampleCovariance
+from ..multivector import DeviceMultiVector, mv_to_dense
+from ..parameterList import ParameterList
+from ..randomized import doublePass, doublePassG
+from .operators import MeanJTJfromDataOperator, SampleCovarianceOperator
+from .PODProjector import _default_device, _to_scipy_csr, gaussian_omega
+
+
+def ActiveSubspaceParameterList():
+    """activeSubspaceProjector.py:33-66 (keys that concern the stored-data path keep their defaults)."""
+    parameters = {}
+    parameters['samples_per_process'] = [64, 'Number of samples per process']
+    parameters['jacobian_data_per_process'] = [512, 'Number of samples per process']
+    parameters['error_test_samples'] = [50, 'Number of samples for error test']
+    parameters['rank'] = [128, 'Rank of subspace']
+    parameters['jacobian_rank'] = [128, 'Rank of Jacobians generated']
+    parameters['control_jacobian_rank'] = [None, 'Rank of control Jacobians generated']
+    parameters['oversampling'] = [10, 'Oversampling parameter for randomized algorithms']
+    parameters['double_loop_samples'] = [20, 'Number of samples used in double loop MC approximation']
+    parameters['verbose'] = [True, 'Boolean for printing']
+    parameters['input_decoder_name'] = ['_input_decoder', 'string for naming']
+    parameters['output_decoder_name'] = ['_output_decoder', 'string for naming']
+    parameters['initialize_samples'] = [False, 'Boolean for the initialization of samples']
+    parameters['serialized_sampling'] = [True, 'Boolean for the serialization of sampling on a process']
+    parameters['observable_constructor'] = [None, 'observable constructor function']
+    parameters['observable_kwargs'] = [{}, 'kwargs used when instantiating observables']
+    parameters['output_directory'] = [None, 'output directory for saving arrays and plots']
+    parameters['plot_label_suffix'] = ['', 'suffix for plot label']
+    parameters['save_and_plot'] = [True, 'Boolean for saving data and plots (only False for unit testing)']
+    parameters['store_Omega'] = [False, 'Boolean for storing Gaussian random matrix (only True for unit testing)']
+    parameters['ms_given'] = [False, 'Boolean for passing ms into serialized AS construction']
+    parameters['omega_seed'] = [1, 'seed of the Gaussian test matrix when none is supplied']
+    return ParameterList(parameters)
+
+
+class StoredJacobians:
+    """``observable`` stand-in: local stored Jacobians J (N_loc, dQ, dM), optional noise precision (dQ, dQ)."""
+
+    def __init__(self, J, noise_cov_inv=None):
+        assert len(J.shape) == 3
+        self.J = J
+        self.noise_cov_inv = noise_cov_inv
+
+
+class SparsePrior:
+    """``prior`` stand-in exposing ``R`` (CSR precision-like SPD matrix on the device) and ``Rsolver`` (block CG),
+    the two objects doublePassG receives at activeSubspaceProjector.py:449-450."""
+
+    def __init__(self, R, device=None, rel_tol=1e-13):
+        self.device = device if device is not None else _default_device()
+        self.R_csr = _to_scipy_csr(R)
+        self.R = CsrMatrix(self.R_csr, self.device)
+        self.Rsolver = CsrCGSolver(self.R, rel_tol=rel_tol)
+
+
+class ActiveSubspaceProjector:
+    def __init__(self, observable, prior=None, control_distribution=None, mesh_constructor_comm=None,
+                 collective=NullCollective(), parameters=None, device=None):
+        self.observable = observable
+        self.prior = prior
+        self.control_distribution = control_distribution
+        self.mesh_constructor_comm = mesh_constructor_comm
+        self.collective = collective
+        self.parameters = parameters if parameters is not None else ActiveSubspaceParameterList()
+        self.device = device if device is not None else (prior.device if prior is not None else _default_device())
+        self.d_GN = None
+        self.V_GN = None
+        self.d_NG = None
+        self.U_NG = None
+        self.Omega_GN = None
+        self.Omega_NG = None
+        self.prior_preconditioned = None
+        self._JTJ = None
+
+    def _operator(self):
+        if self._JTJ is None:
+            # Average_GN_Hessian = CollectiveOperator(SummedListOperator([JTJ(J_i)]), collective, 'avg') (:427-431)
+            self._JTJ = MeanJTJfromDataOperator(self.observable.J, self.prior, self.observable.noise_cov_inv,
+                                                device=self.device, collective=self.collective, mpi_op='avg')
+        return self._JTJ
+
+    def _omega(self, stored, n):
+        m = self.parameters['rank'] + self.parameters['oversampling']
+        if stored is not None:
+            return stored if isinstance(stored, DeviceMultiVector) else DeviceMultiVector.from_dense(stored, self.device)
+        if self.collective.rank() == 0:
+            Omega = gaussian_omega(n, m, self.parameters['omega_seed'], self.device)
+        else:
+            Omega = DeviceMultiVector(n, m, device=self.device)
+        self.collective.bcast(Omega, root=0)
+        return Omega
+
+    def construct_input_subspace(self, prior_preconditioned=True, name_suffix=None, faithful=False):
+        t0 = time.time()
+        A = self._operator()
+        Omega = self._omega(self.Omega_GN, A.dM)
+        if self.parameters['store_Omega']:
+            self.Omega_GN = Omega
+        rank = self.parameters['rank']
+        if prior_preconditioned:
+            if self.prior is None or not hasattr(self.prior, "R"):
+                raise ValueError("prior_preconditioned=True needs a prior exposing R and Rsolver")
+            self.d_GN, self.V_GN = doublePassG(A, self.prior.R, self.prior.Rsolver, Omega, rank, s=1, faithful=faithful)
+            as_decoder = self.V_GN
+            as_encoder = DeviceMultiVector(self.prior.R.matmat(as_decoder.tensor()))   # hp.MatMvMult(prior.R, ...) :452-453
+        else:
+            self.d_GN, self.V_GN = doublePass(A, Omega, rank, s=1, faithful=faithful)
+            as_decoder = self.V_GN
+            as_encoder = DeviceMultiVector(as_decoder)
+        torch.cuda.synchronize(self.device)
+        self.prior_preconditioned = prior_preconditioned
+        self._input_subspace_construction_time = time.time() - t0
+        if self.parameters['verbose'] and self.collective.rank() == 0:
+            print(('Input subspace construction took ' + str(self._input_subspace_construction_time)[:5] + ' s').center(80))
+        if self.parameters['save_and_plot'] and self.collective.rank() == 0:
+            name = 'AS_' + str(int(self.parameters['samples_per_process'] * self.collective.size()))
+            if name_suffix is not None:
+                assert type(name_suffix) is str
+                name += name_suffix
+            np.save(self.parameters['output_directory'] + name + self.parameters['input_decoder_name'], mv_to_dense(self.V_GN))
+            np.save(self.parameters['output_directory'] + name + '_d_GN', self.d_GN)
+        return self.d_GN, as_decoder, as_encoder
+
+    def construct_output_subspace(self, name_suffix=None):
+        """E[J J^T] (activeSubspaceProjector.py:618-673): a (dQ x dQ) problem.  J J^T averaged over samples is
+        accumulated as one NT GEMM per sample block and handed to doublePass through a dense operator."""
+        t0 = time.time()
+        J = self.observable.J
+        N, dQ, dM = J.shape
+        Jd = self._operator()._cov.Xt                                        # (N*dQ, dM) on the device
+        C = torch.zeros((dQ, dQ), dtype=torch.float64, device=self.device)
+        tmp = K.padded_empty(dQ, dQ, self.device)
+        for i in range(N):
+            Ji = Jd[i * dQ:(i + 1) * dQ]
+            K.dgemm(K.HFB_NT, Ji, Ji, out=tmp)
+            C += tmp
+        C /= N
+        self.collective.allReduce(C, 'avg')
+        Cd = K.to_padded(C, self.device)
+
+        class _Dense:
+            def matMvMult(self_, X, Y):
+                K.dgemm(K.HFB_NN, Cd, X.tensor(), out=Y.tensor())
+
+        Omega = self._omega(self.Omega_NG, dQ)
+        if self.parameters['store_Omega']:
+            self.Omega_NG = Omega
+        self.d_NG, self.U_NG = doublePass(_Dense(), Omega, min(self.parameters['rank'], dQ), s=1)
+        output_decoder = self.U_NG
+        output_encoder = DeviceMultiVector(output_decoder)
+        torch.cuda.synchronize(self.device)
+        self._output_subspace_construction_time = time.time() - t0
+        if self.parameters['save_and_plot'] and self.collective.rank() == 0:
+            name = 'AS_' + str(int(self.parameters['samples_per_process'] * self.collective.size()))
+            if name_suffix is not None:
+                name += name_suffix
+            np.save(self.parameters['output_directory'] + name + self.parameters['output_decoder_name'], mv_to_dense(self.U_NG))
+            np.save(self.parameters['output_directory'] + name + '_d_NG', self.d_NG)
+        return self.d_NG, output_decoder, output_encoder

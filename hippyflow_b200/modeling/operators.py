@@ -1,0 +1,148 @@
+"""Sample-averaged operators on the device (layer L3 of SURVEY.md section 1): the duck-typed hIPPYlib
+operator protocol -- ``mult(x, y)``, ``transpmult(x, y)``, ``init_vector(x, dim)``, ``matMvMult(X, Y)`` --
+implemented with the two-GEMM block apply of ``linalg.SampleCovariance``."""
+import numpy as np
+import torch
+
+from .. import _lib as K
+from ..collectives import NullCollective
+from ..linalg import CsrMatrix, SampleCovariance
+from ..multivector import DeviceMultiVector, DeviceVector
+
+
+def _as_device_rows(data, device):
+    """(rows, n) float64 array -> padded row-major device block (zero-copy if already conforming)."""
+    if isinstance(data, torch.Tensor) and data.is_cuda and data.dtype == torch.float64 and data.dim() == 2 \
+            and data.stride(1) == 1 and K._ld(data) % 2 == 0 and data.data_ptr() % 16 == 0:
+        return data
+    return K.to_padded(data, device)
+
+
+class SampleCovarianceOperator:
+    """A = avg over ranks of (1/N_loc) sum_i X_i G X_i^T.
+
+    Equivalent of ``CollectiveOperator(hp.LowRankOperator(ones/N_loc, U_loc), collective, 'avg')``
+    (PODProjector.py:360-363) and of ``CollectiveOperator(SummedListOperator([JTJ(J_i)]), collective,
+    'avg')`` (activeSubspaceProjector.py:427-431): local mean, then allReduce with mpi_op.  The averaging
+    assumes every rank holds the same number of samples (comment at activeSubspaceProjector.py:429-430)."""
+
+    def __init__(self, cov, collective=None, mpi_op="avg"):
+        self.cov = cov
+        self.collective = collective if collective is not None else NullCollective()
+        self.mpi_op = mpi_op
+        self.n = cov.n
+        self.device = cov.Xt.device
+
+    def init_vector(self, x, dim):
+        x.init(self.n)
+
+    def matMvMult(self, X, Y):
+        self.cov.apply(X.tensor(), out=Y.tensor())
+        self.collective.allReduce(Y, self.mpi_op)
+
+    matMvTranspmult = matMvMult
+
+    def mult(self, x, y):
+        self.cov.apply(x.storage_tensor(), out=y.storage_tensor())
+        self.collective.allReduce(y, self.mpi_op)
+
+    transpmult = mult
+
+    def rayleigh(self, Q, BQ):
+        """T = BQ^T A BQ (m x m, host) from projected samples; only an (m x m) allreduce."""
+        T = self.cov.gram_T(BQ.tensor())
+        self.collective.allReduce(T, self.mpi_op)
+        return T.cpu().numpy()
+
+
+class SandwichedCovarianceOperator:
+    """A = B C B with C a SampleCovarianceOperator and B a sparse SPD matrix on the device:
+    ``MassPreconditionedCovarianceOperator`` (KLEProjector.py:47-69, M C M) and ``H_matvec`` of the
+    weighted POD (PODProjector.py:750-754, MX (MX)^T / N)."""
+
+    def __init__(self, C, B):
+        self.C = C
+        self.B = B
+        self.n = C.n
+
+    def init_vector(self, x, dim):
+        x.init(self.n)
+
+    def matMvMult(self, X, Y):
+        BX = DeviceMultiVector(self.B.matmat(X.tensor()))
+        CBX = DeviceMultiVector(self.n, X.nvec(), device=X.tensor().device)
+        self.C.matMvMult(BX, CBX)
+        self.B.matmat(CBX.tensor(), out=Y.tensor())
+
+    def mult(self, x, y):
+        X = DeviceMultiVector(x.storage_tensor())
+        Y = DeviceMultiVector(y.storage_tensor())
+        self.matMvMult(X, Y)
+
+    transpmult = mult
+
+    def solveB_matMvMult(self, X, Y):
+        """Y = B^-1 A X = C (B X): the generalized range finder needs no solve with B."""
+        BX = DeviceMultiVector(self.B.matmat(X.tensor()))
+        self.C.matMvMult(BX, Y)
+
+    def rayleigh(self, Q, BQ):
+        return self.C.rayleigh(BQ, BQ)
+
+
+class MeanJTJfromDataOperator:
+    """Drop-in for hippyflow/modeling/operatorWrappers.py:55-121: y = mean_i J_i^T [Gamma^-1] J_i x from a
+    stored (ndata, r, dM) array.  The reference reads all of J twice per column through two einsums; here
+    the array sits in HBM as the (ndata*r, dM) row-major matrix and a block of columns costs two GEMMs."""
+
+    def __init__(self, J, prior=None, noise_cov_inv=None, device=None, collective=None, mpi_op="avg"):
+        assert len(J.shape) == 3
+        self._J = J
+        self.ndata, self.r, self.dM = J.shape
+        self._prior = prior
+        if noise_cov_inv is not None:
+            assert hasattr(noise_cov_inv, "__matmul__")
+        self._noise_cov_inv = noise_cov_inv
+        if device is None:
+            device = J.device if isinstance(J, torch.Tensor) and J.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        J2 = J.reshape(self.ndata * self.r, self.dM)
+        self._cov = SampleCovariance(_as_device_rows(J2, device), block=self.r,
+                                     noise_cov_inv=None if noise_cov_inv is None else np.asarray(noise_cov_inv))
+        self._op = SampleCovarianceOperator(self._cov, collective, mpi_op)
+        self.device = device
+
+    @property
+    def J(self):
+        return self._J
+
+    @property
+    def prior(self):
+        return self._prior
+
+    @property
+    def noise_cov_inv(self):
+        return self._noise_cov_inv
+
+    def init_vector(self, x, dim):
+        # the reference delegates to prior.R / prior.Hlr and trips over an undefined name
+        # (operatorWrappers.py:92); domain and range both have dimension dM
+        x.init(self.dM)
+
+    def mult(self, x, y):
+        if isinstance(x, DeviceVector):
+            self._op.mult(x, y)
+        else:  # host vectors with get_local / set_local, as in the reference
+            xd = DeviceVector(self.dM, self.device)
+            yd = DeviceVector(self.dM, self.device)
+            xd.set_local(x.get_local())
+            self._op.mult(xd, yd)
+            y.set_local(yd.get_local())
+
+    def transpmult(self, x, y):
+        return self.mult(x, y)
+
+    def matMvMult(self, X, Y):
+        self._op.matMvMult(X, Y)
+
+    def rayleigh(self, Q, BQ):
+        return self._op.rayleigh(Q, BQ)

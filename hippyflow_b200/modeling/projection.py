@@ -1,0 +1,62 @@
+"""Projection of stored training data onto the bases (north star (c)): reduced inputs
+(M V)^T m_i, reduced outputs, J_i^T (M Phi), J_i Psi and Phi^T J_i V for all samples at once.  In the
+reference these are per-sample column loops of PDE solves (dataGenerator.py:170,177,339); on stored data
+they are GEMMs over the stacked sample axis."""
+import numpy as np
+import torch
+
+from .. import _lib as K
+from .operators import _as_device_rows
+
+
+def _dev(a, device):
+    if hasattr(a, "tensor"):
+        return a.tensor()
+    if isinstance(a, torch.Tensor) and a.is_cuda:
+        return a if (a.dim() == 2 and a.stride(1) == 1 and K._ld(a) % 2 == 0 and a.data_ptr() % 16 == 0) else K.to_padded(a, device)
+    return K.to_padded(np.asarray(a, dtype=np.float64), device)
+
+
+def project_data(data, encoder, device=None, out=None):
+    """(N, r) reduced coordinates: row i = encoder^T data_i, with encoder = M decoder
+    (KLEProjector.py:167-168, PODProjector.py:769,830).  ``data`` (N, n) host array or device block."""
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    X = _as_device_rows(data, device)
+    E = _dev(encoder, device)
+    return K.dgemm(K.HFB_NN, X, E, out=out)
+
+
+def jacobian_action(J, Psi, device=None):
+    """JPsi (N, dQ, rM): JPsi_i = J_i Psi (dataGenerator.py:177, stacked as at :585)."""
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    N, dQ, dM = J.shape
+    Jd = _as_device_rows(J.reshape(N * dQ, dM), device)
+    P = _dev(Psi, device)
+    out = K.dgemm(K.HFB_NN, Jd, P)                                  # (N*dQ, rM)
+    rM = P.shape[1]
+    return out.as_strided((N, dQ, rM), (dQ * out.stride(0), out.stride(0), 1))
+
+
+def jacobian_transpose_action(J, MPhi, device=None):
+    """JstarPhi (N, dM, rQ): JstarPhi_i = J_i^T (M Phi) (dataGenerator.py:170,339, stacked as at :582)."""
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    N, dQ, dM = J.shape
+    Jd = _as_device_rows(J.reshape(N * dQ, dM), device)
+    E = _dev(MPhi, device)
+    rQ = E.shape[1]
+    out = torch.empty((N, dM, ((rQ + 15) // 16) * 16), dtype=torch.float64, device=device)[:, :, :rQ]
+    for i in range(N):                                              # one TN GEMM (K = dQ) per sample
+        K.dgemm(K.HFB_TN, Jd[i * dQ:(i + 1) * dQ], E, out=out[i])
+    return out
+
+
+def reduced_jacobians(J, PhiEnc, V, device=None):
+    """(N, rQ, rM): Phi_enc^T J_i V for every sample: one stacked GEMM J_all V, then a batched small GEMM."""
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    N, dQ, dM = J.shape
+    JV = jacobian_action(J, V, device)                              # (N, dQ, rM)
+    Phi = _dev(PhiEnc, device)                                      # (dQ, rQ)
+    rQ, rM = Phi.shape[1], JV.shape[2]
+    out = torch.empty((N, rQ, rM), dtype=torch.float64, device=device)
+    K.dgemm_batched_small(K.HFB_TN, Phi.unsqueeze(0), JV, out)
+    return out

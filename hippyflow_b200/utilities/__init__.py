@@ -1,0 +1,1 @@
+from ..multivector import dense_to_mv_local, mv_to_dense, mv_to_dense_local

@@ -113,6 +113,14 @@ int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, const double*
 int hfb_axpby(int64_t n, int64_t m, double a, const double* X, int64_t ldx, double b, double* Y, int64_t ldy,
               void* stream);
 
+/* Y[:,j] = a[j]*X[:,j] + b[j]*Y[:,j]  (a or b may be NULL = 1): per-column axpy of block CG, the device form of
+ * the Rsolver / Msolver applies inside doublePassG (activeSubspaceProjector.py:449, KLEProjector.py:163). */
+int hfb_axpby_cols(int64_t n, int64_t m, const double* a, const double* X, int64_t ldx, const double* b, double* Y,
+                   int64_t ldy, void* stream);
+/* Y[i,:] = s[i] * X[i,:]  (Jacobi preconditioner of the block CG). */
+int hfb_rowscale(int64_t n, int64_t m, const double* s, const double* X, int64_t ldx, double* Y, int64_t ldy,
+                 void* stream);
+
 /* Counter-based Gaussian/uniform fill keyed by (seed, global row, column): data generated on device is
  * independent of how samples are sharded. kind 0 = N(0,1), 1 = U(0,1). */
 int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64_t seed, int64_t row_offset,

@@ -1,0 +1,136 @@
+"""CPU: the collective layer (hippyflow/collectives API) with world_size-2 gloo process groups."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hippyflow_b200.collectives import (CollectiveOperator, MultipleSamePartitioningPDEsCollective,
+                                                MultipleSerialPDEsCollective)
+        c = MultipleSerialPDEsCollective()
+        res = {}
+        assert c.size() == world and c.rank() == rank
+        res["sum_f"] = c.allReduce(float(rank + 1), "sum")
+        res["avg_f"] = c.allReduce(float(rank + 1), "AVG")                 # case-insensitive (collective.py:82)
+        res["sum_i"] = int(c.allReduce(int(rank + 1), "sum"))
+        a = np.arange(6, dtype=np.float64).reshape(2, 3) * (rank + 1)
+        out = c.allReduce(a, "avg")
+        assert out is a                                                     # in place AND returned
+        res["arr"] = a.copy()
+        t = torch.full((4, 3), float(rank + 1), dtype=torch.float64)
+        c.allReduce(t, "sum")
+        res["ten"] = t.numpy().copy()
+        nc = torch.zeros(4, 6, dtype=torch.float64)[:, :3]                  # non-contiguous view (padded block)
+        nc += rank + 1
+        c.allReduce(nc, "avg")
+        res["nc"] = nc.clone().numpy()
+        b = np.full(3, float(rank))
+        c.bcast(b, root=1)
+        res["bcast"] = b.copy()
+        res["bcast_scalar"] = float(c.bcast(float(rank) + 0.5, root=0))
+        try:
+            c.allReduce(np.ones(2), "max")
+            res["bad_op"] = False
+        except NotImplementedError:
+            res["bad_op"] = True
+        try:
+            c.allReduce("a string", "sum")
+            res["bad_type"] = False
+        except NotImplementedError:
+            res["bad_type"] = True
+
+        # CollectiveOperator: local apply then allReduce (collectiveOperator.py:31-38) on host vectors
+        from oracle.hippylib_np import Vector
+
+        class LocalOp:
+            def init_vector(self, x, dim):
+                x.init(3)
+
+            def mult(self, x, y):
+                y.set_local((rank + 1) * x.get_local())
+
+            transpmult = mult
+
+        op = CollectiveOperator(LocalOp(), c, "avg")
+        x, y = Vector(np.array([1.0, 2.0, 3.0])), Vector(np.zeros(3))
+        op.mult(x, y)
+        res["op"] = y.get_local()
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_torch_collective_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        r = results[rank]
+        assert r["sum_f"] == 3.0 and r["avg_f"] == 1.5 and r["sum_i"] == 3
+        np.testing.assert_allclose(r["arr"], np.arange(6).reshape(2, 3) * 1.5)
+        np.testing.assert_allclose(r["ten"], 3.0)
+        np.testing.assert_allclose(r["nc"], 1.5)
+        np.testing.assert_allclose(r["bcast"], 1.0)
+        assert r["bcast_scalar"] == 0.5
+        assert r["bad_op"] and r["bad_type"]
+        np.testing.assert_allclose(r["op"], 1.5 * np.array([1.0, 2.0, 3.0]))
+
+
+def test_null_collective_and_operator_protocol():
+    from hippyflow_b200.collectives import CollectiveOperator, MatrixMultCollectiveOperator, NullCollective
+    c = NullCollective()
+    assert c.size() == 1 and c.rank() == 0 and c.bcast(5) == 5
+    assert c.allReduce(2.0, "Sum") == 2.0
+    with pytest.raises(NotImplementedError):
+        c.allReduce(2.0, "prod")
+
+    class NoMult:
+        pass
+
+    with pytest.raises(AssertionError):
+        CollectiveOperator(NoMult(), c)
+    with pytest.raises(AssertionError):
+        MatrixMultCollectiveOperator(NoMult(), c)
+
+
+def test_parameter_lists_have_reference_keys():
+    import hippyflow_b200 as hf
+    p = hf.PODParameterList()
+    assert p["rank"] == 20 and p["oversampling"] == 10 and p["sample_per_process"] == 100
+    a = hf.ActiveSubspaceParameterList()
+    assert a["rank"] == 128 and a["oversampling"] == 10 and a["samples_per_process"] == 64 and a["serialized_sampling"]
+    k = hf.KLEParameterList()
+    assert k["rank"] == 128 and k["input_decoder_name"] == "KLE_decoder"
+    p["rank"] = 7
+    assert p["rank"] == 7
+    with pytest.raises(ValueError):
+        p["no_such_key"]

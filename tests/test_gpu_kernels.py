@@ -1,0 +1,146 @@
+"""GPU: each C-ABI kernel against a plain torch fp64 reference of the same op (bit-level agreement is not
+expected for floating-point sums; tolerances are stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def K(cuda_device):
+    from hippyflow_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+SHAPES = [(100, 25, 289), (289, 25, 100), (513, 266, 1000), (130, 138, 77), (64, 74, 6400), (1000, 210, 333),
+          (257, 4, 50), (300, 300, 300), (1, 1, 1), (16, 8, 16), (129, 137, 17)]
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("splits", [0, 1, 3])
+def test_dgemm_matches_torch(K, cuda_device, layout, shape, splits):
+    M, N, Kd = shape
+    g = torch.Generator(device="cpu").manual_seed(M * 1000003 + N * 1009 + Kd)
+    A = torch.randn(M, Kd, dtype=torch.float64, generator=g).to(cuda_device)
+    B = torch.randn(Kd, N, dtype=torch.float64, generator=g).to(cuda_device)
+    ref = 0.5 * (A @ B)
+    Ad = K.to_padded(A.t().contiguous() if layout == K.HFB_TN else A, cuda_device)
+    Bd = K.to_padded(B.t().contiguous() if layout == K.HFB_NT else B, cuda_device)
+    C = K.dgemm(layout, Ad, Bd, alpha=0.5, splits=splits)
+    assert rel(C, ref) < 1e-13          # fp64 GEMM, K <= 6400: a few ulp * sqrt(K)
+
+
+def test_dgemm_split_k_is_bitwise_reproducible(K, cuda_device):
+    A = K.padded_empty(256, 50000, cuda_device).normal_()
+    B = K.padded_empty(50000, 74, cuda_device).normal_()
+    C1 = K.dgemm(K.HFB_NN, A, B).clone()
+    C2 = K.dgemm(K.HFB_NN, A, B).clone()
+    assert torch.equal(C1, C2)
+    assert K.lib().hfb_dgemm_auto_splits(0, 256, 74, 50000) > 1
+
+
+def test_dgemm_linearity_at_config2_width(K, cuda_device):
+    """Size-independent property at the benchmark width m = 266: (A)(B1 + B2) = A B1 + A B2 to round-off."""
+    n, R, m = 40000, 512, 266
+    A = K.padded_empty(R, n, cuda_device).normal_()
+    B1 = K.padded_empty(n, m, cuda_device).normal_()
+    B2 = K.padded_empty(n, m, cuda_device).normal_()
+    Bs = K.padded_empty(n, m, cuda_device)
+    Bs.copy_(B1 + B2)
+    lhs = K.dgemm(K.HFB_NN, A, Bs).clone()
+    rhs = K.dgemm(K.HFB_NN, A, B1).clone() + K.dgemm(K.HFB_NN, A, B2)
+    assert rel(lhs, rhs) < 1e-13
+    Y = K.dgemm(K.HFB_TN, A, lhs)                      # (n x m) = A^T W
+    assert rel(Y, A.t() @ lhs) < 1e-13
+
+
+def test_dgemm_rejects_bad_operands(K, cuda_device):
+    A = torch.randn(8, 9, dtype=torch.float64, device=cuda_device)     # odd leading dimension
+    B = K.padded_empty(9, 4, cuda_device).normal_()
+    with pytest.raises(K.HfbError):
+        K.dgemm(K.HFB_NN, A, B)
+    with pytest.raises(K.HfbError):
+        K.dgemm(K.HFB_NN, K.padded_empty(8, 10, cuda_device), B)         # inner dimensions differ
+
+
+@pytest.mark.parametrize("m", [1, 25, 64, 138, 266, 300])
+def test_csr_spmm(K, cuda_device, m):
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    M = syn.p1_mass_matrix(23, 17)
+    n = M.shape[0]
+    Md = CsrMatrix(M, cuda_device)
+    B = np.random.default_rng(m).standard_normal((n, m))
+    out = Md.matmat(K.to_padded(B, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(out, M @ B, rtol=1e-13, atol=1e-16)
+    X = np.random.default_rng(m + 1).standard_normal((37, n))
+    outr = Md.matmat_rows(K.to_padded(X, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
+
+
+def test_column_kernels(K, cuda_device):
+    rng = np.random.default_rng(0)
+    X, Y = rng.standard_normal((1000, 37)), rng.standard_normal((1000, 37))
+    Xd, Yd = K.to_padded(X, cuda_device), K.to_padded(Y, cuda_device)
+    np.testing.assert_allclose(K.coldot(Xd, Yd).cpu().numpy(), np.einsum("ij,ij->j", X, Y), rtol=1e-13)
+    np.testing.assert_allclose(K.colsum(Xd, 0.25).cpu().numpy(), 0.25 * X.sum(0), rtol=1e-12, atol=1e-14)
+    s = rng.standard_normal(37)
+    sd = torch.as_tensor(s, device=cuda_device)
+    Z = Xd.clone()
+    K.colscale_(Z, sd)
+    np.testing.assert_allclose(Z.cpu().numpy(), X * s, rtol=1e-15)
+    Z = Xd.clone()
+    K.subtract_row_(Z, sd)
+    np.testing.assert_allclose(Z.cpu().numpy(), X - s, rtol=1e-15)
+    Z = Yd.clone()
+    K.axpby_(2.0, Xd, -0.5, Z)
+    np.testing.assert_allclose(Z.cpu().numpy(), 2 * X - 0.5 * Y, rtol=1e-15, atol=1e-15)
+    Z = Yd.clone()
+    K.axpby_cols_(sd, Xd, None, Z)
+    np.testing.assert_allclose(Z.cpu().numpy(), X * s + Y, rtol=1e-14, atol=1e-15)
+    r = rng.standard_normal(1000)
+    out = K.rowscale(torch.as_tensor(r, device=cuda_device), Xd)
+    np.testing.assert_allclose(out.cpu().numpy(), X * r[:, None], rtol=1e-15)
+
+
+def test_batched_small_gemm(K, cuda_device):
+    rng = np.random.default_rng(1)
+    G = rng.standard_normal((10, 10))
+    W = rng.standard_normal((7, 10, 33))
+    out = torch.empty((7, 10, 33), dtype=torch.float64, device=cuda_device)
+    K.dgemm_batched_small(K.HFB_NN, torch.as_tensor(G, device=cuda_device).unsqueeze(0),
+                          torch.as_tensor(W, device=cuda_device), out)
+    np.testing.assert_allclose(out.cpu().numpy(), np.einsum("ab,ibc->iac", G, W), rtol=1e-13, atol=1e-14)
+    Phi = rng.standard_normal((10, 6))
+    out2 = torch.empty((7, 6, 33), dtype=torch.float64, device=cuda_device)
+    K.dgemm_batched_small(K.HFB_TN, torch.as_tensor(Phi, device=cuda_device).unsqueeze(0),
+                          torch.as_tensor(W, device=cuda_device), out2)
+    np.testing.assert_allclose(out2.cpu().numpy(), np.einsum("qa,iqc->iac", Phi, W), rtol=1e-13, atol=1e-14)
+
+
+def test_fill_random_is_sharding_independent(K, cuda_device):
+    full = K.padded_empty(64, 101, cuda_device)
+    K.fill_random_(full, seed=11)
+    part = K.padded_empty(16, 101, cuda_device)
+    K.fill_random_(part, seed=11, row_offset=32)
+    assert torch.equal(part, full[32:48])
+    big = K.padded_empty(4096, 256, cuda_device)
+    K.fill_random_(big, seed=3)
+    assert abs(float(big.mean())) < 5e-3 and abs(float(big.std()) - 1.0) < 5e-3
+
+
+def test_block_cg(K, cuda_device):
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrCGSolver, CsrMatrix
+    M = syn.p1_mass_matrix(20)
+    Md = CsrMatrix(M, cuda_device)
+    Y = np.random.default_rng(5).standard_normal((M.shape[0], 9))
+    X = CsrCGSolver(Md).solve_block(K.to_padded(Y, cuda_device)).cpu().numpy()
+    assert np.linalg.norm(M @ X - Y) / np.linalg.norm(Y) < 1e-12

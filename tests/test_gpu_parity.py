@@ -1,0 +1,262 @@
+"""GPU parity tests proper: the CUDA path (through the public projector API and the C ABI) against the CPU
+oracle on the same seeded inputs and the same Omega, against the committed golden vectors, and through
+size-independent properties at benchmark widths.
+
+Tolerances (BASELINE.json north_star, fp64): eigenvalues relative 1e-10; largest principal angle between the
+leading subspaces < 1e-8 (in the M inner product where weighted); projected data relative Frobenius 1e-12.
+"""
+import numpy as np
+import pytest
+import torch
+
+from hippyflow_b200 import synthetic as syn
+from oracle import projectors_np as P
+from conftest import subspace_angle
+
+pytestmark = pytest.mark.gpu
+
+EIG_RTOL = 1e-10
+ANGLE_TOL = 1e-8
+PROJ_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def hf(cuda_device):
+    import hippyflow_b200 as hf
+    from hippyflow_b200 import _lib
+    _lib.lib()
+    return hf
+
+
+def leading(d, floor=1e-6):
+    """Number of leading modes whose eigenvalue ratio to the first is above `floor`: the subspace-angle
+    criterion is only meaningful away from round-off-level eigenvalues."""
+    return int(np.sum(d / d[0] > floor))
+
+
+# ------------------------------------------------------------------ POD, M-weighted randomized (config 1)
+@pytest.mark.parametrize("shifted", [True, False])
+def test_pod_randomized_weighted_vs_oracle(hf, cuda_device, golden_pod, golden_dp, shifted):
+    M = syn.p1_mass_matrix(int(golden_pod["nx"]))
+    u, Om = golden_pod["u_data"], golden_dp["Omega"]
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    d, phi, Mphi, shift = proj.construct_subspace(u.copy(), 15, shifted=shifted, method="randomized", Omega=Om)
+    d0, U0, E0, s0 = P.pod_randomized_weighted(u, M, 15, Om, shifted=shifted)
+    np.testing.assert_allclose(d, d0, rtol=EIG_RTOL)
+    k = leading(d0)
+    assert subspace_angle(phi[:, :k], U0[:, :k], M) < ANGLE_TOL
+    np.testing.assert_allclose(shift, s0, rtol=0, atol=1e-14)
+    assert phi.shape == (289, 15) and Mphi.shape == (289, 15) and shift.shape == (289,) and d.shape == (15,)
+    # reference property tests (test_PODProjector.py:161-174)
+    I = np.eye(15)
+    assert np.linalg.norm(I - phi.T @ Mphi) / np.linalg.norm(I) < 1e-8
+    assert np.linalg.norm(M @ phi - Mphi) / np.linalg.norm(Mphi) < 1e-8
+    if not shifted:   # golden: reference CollectiveOperator(NullCollective) + doublePassG
+        np.testing.assert_allclose(d, golden_dp["d_w"], rtol=EIG_RTOL)
+        assert subspace_angle(phi[:, :k], golden_dp["U_w"][:, :k], M) < ANGLE_TOL
+
+
+def test_pod_randomized_faithful_equals_shortcut(hf, cuda_device, golden_pod, golden_dp):
+    """T = (AQ)^T Q (hIPPYlib's form) and T = W^T W / N give the same eigenpairs."""
+    M = syn.p1_mass_matrix(int(golden_pod["nx"]))
+    u, Om = golden_pod["u_data"], golden_dp["Omega"]
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    d1, phi1, _, _ = proj.construct_subspace(u.copy(), 15, shifted=False, method="randomized", Omega=Om)
+    d2, phi2, _, _ = proj.construct_subspace(u.copy(), 15, shifted=False, method="randomized", Omega=Om, faithful=True)
+    np.testing.assert_allclose(d1, d2, rtol=EIG_RTOL)
+    k = leading(d1)
+    assert subspace_angle(phi1[:, :k], phi2[:, :k], M) < ANGLE_TOL
+
+
+# ------------------------------------------------------------------ POD, deterministic 'hep' vs reference verbatim
+@pytest.mark.parametrize("shifted", [True, False])
+def test_pod_hep_vs_reference_golden(hf, cuda_device, golden_pod, shifted):
+    g = golden_pod
+    M = syn.p1_mass_matrix(int(g["nx"]))
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    d, phi, Mphi, shift = proj.construct_subspace(g["u_data"].copy(), 15, shifted=shifted, method="hep")
+    key = f"hep_{int(shifted)}"
+    np.testing.assert_allclose(d, g[key + "_d"], rtol=1e-9)
+    np.testing.assert_allclose(shift, g[key + "_shift"], rtol=0, atol=1e-14)
+    assert subspace_angle(phi[:, :10], g[key + "_phi"][:, :10], M) < 1e-7
+    rv = 14 if shifted else 15
+    I = np.eye(rv)
+    assert np.linalg.norm(I - phi[:, :rv].T @ Mphi[:, :rv]) / np.linalg.norm(I) < 1e-8
+    assert np.linalg.norm(M @ phi - Mphi) / np.linalg.norm(Mphi) < 1e-8
+    # eigen-relation C M phi_i = d_i phi_i (test_PODProjector.py:188-208, tolerance 1e-2)
+    X = g["u_data"] - (shift if shifted else 0.0)
+    C = X.T @ X / X.shape[0]
+    for i in range(rv):
+        lhs = C @ (M @ phi[:, i])
+        assert np.linalg.norm(lhs - d[i] * phi[:, i]) / np.linalg.norm(d[i] * phi[:, i]) < 1e-2
+
+
+def test_pod_unavailable_method_and_rank_check(hf, cuda_device, golden_pod):
+    M = syn.p1_mass_matrix(int(golden_pod["nx"]))
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    with pytest.raises(ValueError, match="Unavailable method"):
+        proj.construct_subspace(golden_pod["u_data"], 15, method="nope")
+    with pytest.raises(AssertionError):
+        proj.construct_subspace(golden_pod["u_data"][:10], 15, method="randomized")
+
+
+# ------------------------------------------------------------------ PODProjector (doublePass, collective 'avg')
+def test_pod_doublepass_vs_golden(hf, cuda_device, golden_pod, golden_dp):
+    u, Om = golden_pod["u_data"], golden_dp["Omega"]
+    params = hf.PODParameterList()
+    params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = 15, 10, False, False
+    proj = hf.PODProjector(hf.StoredSnapshots(u), collective=hf.NullCollective(), parameters=params, device=cuda_device)
+    d, U = proj.construct_subspace(Omega=Om)
+    np.testing.assert_allclose(d, golden_dp["d_pod"], rtol=EIG_RTOL)
+    Ud = hf.mv_to_dense(U)
+    k = leading(golden_dp["d_pod"])
+    assert subspace_angle(Ud[:, :k], golden_dp["U_pod"][:, :k]) < ANGLE_TOL
+    np.testing.assert_allclose(Ud.T @ Ud, np.eye(15), atol=1e-12)
+
+
+# ------------------------------------------------------------------ active subspace from stored Jacobians
+def test_meanjtj_operator_vs_reference_golden(hf, cuda_device, golden_jtj):
+    from oracle.hippylib_np import Vector
+    g = golden_jtj
+    for G, ys in ((None, g["ys"]), (g["noise_cov_inv"], g["ysG"])):
+        op = hf.MeanJTJfromDataOperator(g["J"], None, G, device=cuda_device)
+        assert (op.ndata, op.r, op.dM) == (64, 100, 121)
+        for x, yref in zip(g["xs"], ys):
+            y = Vector(np.zeros(121))
+            op.mult(Vector(x.copy()), y)
+            assert np.linalg.norm(y.get_local() - yref) / np.linalg.norm(yref) < PROJ_RTOL
+            y2 = Vector(np.zeros(121))
+            op.transpmult(Vector(x.copy()), y2)
+            np.testing.assert_array_equal(y.get_local(), y2.get_local())
+
+
+@pytest.mark.parametrize("preconditioned", [False, True])
+def test_active_subspace_vs_golden(hf, cuda_device, golden_jtj, golden_dp, preconditioned):
+    J, Om = golden_jtj["J"], golden_dp["Omega_as"]
+    params = hf.ActiveSubspaceParameterList()
+    params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = 64, 10, False, False
+    Mp = syn.p1_mass_matrix(10)
+    prior = hf.SparsePrior(Mp, device=cuda_device) if preconditioned else None
+    proj = hf.ActiveSubspaceProjector(hf.StoredJacobians(J), prior, collective=hf.NullCollective(), parameters=params,
+                                      device=cuda_device)
+    proj.Omega_GN = Om
+    d, dec, enc = proj.construct_input_subspace(prior_preconditioned=preconditioned)
+    dref = golden_dp["d_asg"] if preconditioned else golden_dp["d_as"]
+    Vref = golden_dp["V_asg"] if preconditioned else golden_dp["V_as"]
+    k = leading(dref, 1e-5)
+    np.testing.assert_allclose(d[:k], dref[:k], rtol=EIG_RTOL)
+    np.testing.assert_allclose(d, dref, rtol=1e-7, atol=1e-14 * dref[0])
+    V, E = hf.mv_to_dense(dec), hf.mv_to_dense(enc)
+    assert subspace_angle(V[:, :k], Vref[:, :k], Mp if preconditioned else None) < ANGLE_TOL
+    if preconditioned:
+        np.testing.assert_allclose(E, Mp @ V, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(V.T @ E, np.eye(64), atol=1e-10)
+    else:
+        np.testing.assert_array_equal(V, E)
+    assert proj.prior_preconditioned == preconditioned and proj.d_GN is d
+
+
+def test_active_subspace_noise_weighted_vs_oracle(hf, cuda_device, golden_jtj, golden_dp):
+    J, G, Om = golden_jtj["J"], golden_jtj["noise_cov_inv"], golden_dp["Omega_as"]
+    params = hf.ActiveSubspaceParameterList()
+    params["rank"], params["verbose"], params["save_and_plot"] = 32, False, False
+    proj = hf.ActiveSubspaceProjector(hf.StoredJacobians(J, G), None, parameters=params, device=cuda_device)
+    proj.Omega_GN = Om[:, :42]
+    d, dec, _ = proj.construct_input_subspace(prior_preconditioned=False)
+    d0, V0, _ = P.as_input_from_jacobians(J, 32, Om[:, :42], noise_cov_inv=G)
+    k = leading(d0, 1e-5)
+    np.testing.assert_allclose(d[:k], d0[:k], rtol=EIG_RTOL)
+    assert subspace_angle(hf.mv_to_dense(dec)[:, :k], V0[:, :k]) < ANGLE_TOL
+
+
+def test_active_output_subspace_vs_oracle(hf, cuda_device, golden_jtj):
+    J = golden_jtj["J"][:16]
+    Om = syn.gaussian_omega(100, 30, seed=9)
+    params = hf.ActiveSubspaceParameterList()
+    params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = 20, 10, False, False
+    proj = hf.ActiveSubspaceProjector(hf.StoredJacobians(J), None, parameters=params, device=cuda_device)
+    proj.Omega_NG = Om
+    d, dec, _ = proj.construct_output_subspace()
+    d0, U0 = P.as_output_from_jacobians(J, 20, Om)
+    k = leading(d0, 1e-5)
+    np.testing.assert_allclose(d[:k], d0[:k], rtol=EIG_RTOL)
+    assert subspace_angle(hf.mv_to_dense(dec)[:, :k], U0[:, :k]) < ANGLE_TOL
+
+
+# ------------------------------------------------------------------ KLE from stored parameter draws
+def test_kle_mass_vs_golden(hf, cuda_device, golden_pod, golden_dp):
+    M = syn.p1_mass_matrix(int(golden_pod["nx"]))
+    n = M.shape[0]
+    m_data = syn.snapshots(n, 512, r0=200, decay=2.0, eps=1e-9, seed=int(golden_dp["m_data_seed"]))
+    params = hf.KLEParameterList()
+    params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = 128, 10, False, False
+    proj = hf.KLEProjector(hf.SampleCovariancePrior(m_data, M, device=cuda_device), parameters=params)
+    d, dec, enc = proj.construct_input_subspace("mass", Omega=golden_dp["Omega_kle"])
+    dref = golden_dp["d_kle"]
+    k = leading(dref, 1e-6)
+    np.testing.assert_allclose(d[:k], dref[:k], rtol=EIG_RTOL)
+    V, E = hf.mv_to_dense(dec), hf.mv_to_dense(enc)
+    assert subspace_angle(V[:, :k], golden_dp["V_kle"][:, :k], M) < ANGLE_TOL
+    r = 128
+    assert np.linalg.norm(V.T @ E - np.eye(r)) / np.sqrt(r) < 1e-10            # test_KLEProjector.py:97-99
+    assert np.linalg.norm(M @ V - E) / np.linalg.norm(E) < 1e-10                 # :102-108
+    assert proj.M_orthogonal is True
+    d2, dec2, enc2 = proj.construct_input_subspace("identity", Omega=golden_dp["Omega_kle"])
+    d0, V0, _ = P.kle_from_samples(m_data, M, 128, golden_dp["Omega_kle"], "identity")
+    k2 = leading(d0, 1e-6)
+    np.testing.assert_allclose(d2[:k2], d0[:k2], rtol=EIG_RTOL)
+    assert subspace_angle(hf.mv_to_dense(dec2)[:, :k2], V0[:, :k2]) < ANGLE_TOL
+    np.testing.assert_array_equal(hf.mv_to_dense(dec2), hf.mv_to_dense(enc2))
+    with pytest.raises(NotImplementedError):
+        proj.construct_input_subspace("prior")
+
+
+# ------------------------------------------------------------------ projection of stored data
+def test_projection_of_stored_data_vs_oracle(hf, cuda_device, golden_jtj):
+    rng = np.random.default_rng(0)
+    M = syn.p1_mass_matrix(10)                       # 121 parameter dofs
+    m_data = rng.standard_normal((300, 121))
+    V = np.linalg.qr(rng.standard_normal((121, 20)))[0]
+    enc = M @ V
+    red = hf.project_data(m_data, enc, cuda_device).cpu().numpy()
+    ref = P.project_data(m_data, enc)
+    assert np.linalg.norm(red - ref) / np.linalg.norm(ref) < PROJ_RTOL
+    J = golden_jtj["J"][:24]                         # (24, 100, 121)
+    Phi = np.linalg.qr(rng.standard_normal((100, 12)))[0]
+    a = hf.jacobian_action(J, V, cuda_device).cpu().numpy()
+    assert np.linalg.norm(a - P.j_psi(J, V)) / np.linalg.norm(P.j_psi(J, V)) < PROJ_RTOL
+    b = hf.jacobian_transpose_action(J, Phi, cuda_device).cpu().numpy()
+    assert np.linalg.norm(b - P.jstar_phi(J, Phi)) / np.linalg.norm(P.jstar_phi(J, Phi)) < PROJ_RTOL
+    c = hf.reduced_jacobians(J, Phi, V, cuda_device).cpu().numpy()
+    refc = P.reduced_jacobians(J, Phi, V)
+    assert np.linalg.norm(c - refc) / np.linalg.norm(refc) < PROJ_RTOL
+
+
+# ------------------------------------------------------------------ mid-size parity (oracle finishes in seconds)
+def test_pod_randomized_midsize_vs_blocked_oracle(hf, cuda_device):
+    """n = 66049 (257^2 P1), N = 512, rank 64 + 10: eigenvalues against a blocked NumPy evaluation of the same
+    double-pass algorithm (d and span(U) do not depend on the choice of M-orthonormal basis of span(Y))."""
+    nx = 256
+    M = syn.p1_mass_matrix(nx)
+    n = M.shape[0]
+    u = syn.snapshots(n, 512, r0=128, decay=1.0, eps=1e-6, seed=2)
+    Om = syn.gaussian_omega(n, 74, seed=3)
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    d, phi, Mphi, shift = proj.construct_subspace(u, 64, shifted=True, method="randomized", Omega=Om)
+    X = u - u.mean(0)
+    Y = X.T @ (X @ (M @ Om)) / X.shape[0]
+    G = Y.T @ (M @ Y)
+    w, V = np.linalg.eigh((G + G.T) / 2)
+    Q = Y @ (V / np.sqrt(w))
+    G2 = Q.T @ (M @ Q)
+    w2, V2 = np.linalg.eigh((G2 + G2.T) / 2)
+    Q = Q @ (V2 / np.sqrt(w2))
+    W = X @ (M @ Q)
+    T = W.T @ W / X.shape[0]
+    dd, VV = np.linalg.eigh(T)
+    d0 = dd[::-1][:64]
+    U0 = Q @ VV[:, ::-1][:, :64]
+    np.testing.assert_allclose(d, d0, rtol=EIG_RTOL)
+    k = leading(d0)
+    assert subspace_angle(phi[:, :k], U0[:, :k], M) < ANGLE_TOL
+    assert np.linalg.norm(phi.T @ Mphi - np.eye(64)) < 1e-10
