@@ -116,57 +116,60 @@ def _sym(G):
     return 0.5 * (G + G.T)
 
 
-def b_orthonormalize(Y, Bmat=None, max_passes=4, return_BQ=True):
+def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
     """Orthonormalise the columns of the sketch Y (n, m) in the inner product of the sparse SPD matrix
     ``Bmat`` (None = Euclidean): the role of MultiVector.Borthogonalize / orthogonalize inside hIPPYlib's
     doublePassG / doublePass.
 
     hIPPYlib does column-by-column modified Gram-Schmidt (level-1 BLAS, one B-apply per column).  Here the
-    same subspace is orthonormalised with GEMM-shaped passes: Z = B Y (SpMM), G = Y^T Z (DMMA, split-K),
-    host factorisation of the column-scaled (m x m) Gram matrix, Y <- Y S (DMMA).  Cholesky is used when
-    the scaled Gram matrix is numerically positive definite; otherwise an eigen-decomposition with
-    truncation, which -- like hIPPYlib's MGS -- returns ZERO columns for numerically dependent directions.
-    Eigenvalues d and span(U) of the eigensolve do not depend on which B-orthonormal basis of span(Y) is
-    used.  Returns (Q, BQ, info); Q overwrites Y's storage when possible."""
+    same subspace is orthonormalised with GEMM-shaped passes (shifted Cholesky-QR, repeated): Z = B Y (SpMM),
+    G = Y^T Z (DMMA, split-K), host Cholesky of the column-scaled (m x m) Gram matrix, Y <- Y R^-1 (DMMA).
+    When the scaled Gram matrix is too ill-conditioned for a plain Cholesky factorisation a diagonal shift is
+    added (the first pass then only pre-conditions the sketch; no direction is discarded) and passes repeat
+    until the Gram matrix is the identity to round-off -- three passes for cond(Y) up to ~1e15, two for a
+    well-conditioned sketch.  Columns that are exactly zero stay zero, as in hIPPYlib's MGS.  Eigenvalues d and
+    span(U) of the eigensolve do not depend on which B-orthonormal basis of span(Y) is used.
+    Returns (Q, BQ, info); Q overwrites Y's storage."""
     n, m = Y.shape
     eps = np.finfo(np.float64).eps
-    info = {"passes": 0, "truncated": 0, "cond": []}
+    info = {"passes": 0, "shifted": 0, "cond": []}
     Z = None
+    eye = np.eye(m)
     for it in range(max_passes):
         Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
-        G = K.dgemm(K.HFB_TN, Y, Z).cpu().numpy()
-        G = _sym(G)
+        G = _sym(K.dgemm(K.HFB_TN, Y, Z).cpu().numpy())
         d = np.sqrt(np.maximum(np.diag(G), 0.0))
         dead = d <= 0.0
         dinv = np.where(dead, 0.0, 1.0 / np.where(dead, 1.0, d))
         Gs = G * np.outer(dinv, dinv)
-        off = np.abs(Gs - np.diag(np.diag(Gs))).max() if m > 1 else 0.0
-        if it > 0 and off < 64 * eps and np.abs(d[~dead] - 1.0).max(initial=0.0) < 64 * eps:
-            break  # already B-orthonormal to round-off: nothing to apply
-        S = None
-        if not dead.any():
+        Gs[dead, dead] = 1.0
+        dev_from_I = np.abs(Gs - eye).max() if not dead.all() else 0.0
+        if it > 0 and dev_from_I < 32 * eps and np.abs(d[~dead] - 1.0).max(initial=0.0) < 32 * eps:
+            break  # B-orthonormal to round-off: nothing left to apply
+        R = None
+        shift = 0.0
+        for attempt in range(8):
             try:
-                R = sla.cholesky(Gs, lower=False, check_finite=False)
-                rd = np.abs(np.diag(R))
+                Rt = sla.cholesky(Gs + shift * eye, lower=False, check_finite=False)
+                rd = np.abs(np.diag(Rt))
                 cond = (rd.max() / rd.min()) ** 2
-                if np.isfinite(cond) and cond < 1e14:
-                    S = sla.solve_triangular(R, np.eye(m), lower=False, check_finite=False) * dinv[:, None]
-                    info["cond"].append(float(cond))
+                if np.isfinite(cond) and (cond < 1e13 or shift > 0.0):
+                    R = Rt
+                    break
             except (np.linalg.LinAlgError, sla.LinAlgError):
-                S = None
-        if S is None:
-            w, V = np.linalg.eigh(Gs)
-            keep = w > max(m * eps * w.max(), 0.0) * 10.0
-            S = np.zeros((m, m))
-            S[:, : keep.sum()] = (V[:, keep] / np.sqrt(w[keep])) * dinv[:, None]
-            info["truncated"] = int(m - keep.sum())
-            info["cond"].append(float(w.max() / max(w[keep].min(), 1e-300)))
-        Sd = K.to_padded(S, Y.device)
-        Qn = K.dgemm(K.HFB_NN, Y, Sd)
+                pass
+            shift = 100.0 * m * eps if shift == 0.0 else shift * 100.0
+        if R is None:
+            raise K.HfbError("b_orthonormalize: Gram matrix could not be factorised")
+        if shift > 0.0:
+            info["shifted"] += 1
+        info["cond"].append(float(cond))
+        S = sla.solve_triangular(R, eye, lower=False, check_finite=False) * dinv[:, None]
+        Qn = K.dgemm(K.HFB_NN, Y, K.to_padded(S, Y.device))
         Y.copy_(Qn)
         info["passes"] += 1
-        if info["cond"][-1] * eps * m < 1e-3 and it >= 1:
-            # previous pass left cond(G) ~ 1: this pass is accurate to round-off
+        if shift == 0.0 and it >= 1 and cond < 4.0:
+            # the previous pass already left cond(G) ~ 1, so this pass is accurate to round-off
             Z = None
             break
     Q = Y

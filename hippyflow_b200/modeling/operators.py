@@ -49,8 +49,9 @@ class SampleCovarianceOperator:
     transpmult = mult
 
     def rayleigh(self, Q, BQ):
-        """T = BQ^T A BQ (m x m, host) from projected samples; only an (m x m) allreduce."""
-        T = self.cov.gram_T(BQ.tensor())
+        """T = Q^T A Q (m x m, host) as a Gram matrix of the projected samples; only an (m x m) allreduce.
+        (BQ is unused: A = C does not involve B.)"""
+        T = self.cov.gram_T(Q.tensor())
         self.collective.allReduce(T, self.mpi_op)
         return T.cpu().numpy()
 
@@ -87,7 +88,7 @@ class SandwichedCovarianceOperator:
         self.C.matMvMult(BX, Y)
 
     def rayleigh(self, Q, BQ):
-        return self.C.rayleigh(BQ, BQ)
+        return self.C.rayleigh(BQ, None)   # Q^T (B C B) Q = (BQ)^T C (BQ)
 
 
 class MeanJTJfromDataOperator:

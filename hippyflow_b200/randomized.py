@@ -58,7 +58,7 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None):
     assert k <= nvec
     Q = DeviceMultiVector(Omega)
     for _ in range(s):
-        if hasattr(A, "solveB_matMvMult") and getattr(A, "B", None) is B and not faithful:
+        if hasattr(A, "solveB_matMvMult") and getattr(A, "B", None) is B and (Binv is None or not faithful):
             Y = DeviceMultiVector(Q.tensor().shape[0], nvec, device=Q.tensor().device)
             A.solveB_matMvMult(Q, Y)
             Q = Y
