@@ -60,6 +60,7 @@ def lib():
         "hfb_axpby": (i32, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
         "hfb_axpby_cols": (i32, [i64, i64, vp, vp, i64, vp, vp, i64, vp]),
         "hfb_rowscale": (i32, [i64, i64, vp, vp, i64, vp, i64, vp]),
+        "hfb_measure_dmma_peak": (i32, [vp, sz, ctypes.POINTER(ctypes.c_double), vp]),
         "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -73,7 +74,8 @@ def lib():
 EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
-            "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random"]
+            "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
+            "hfb_measure_dmma_peak"]
 
 
 def _check(rc, what):
@@ -157,9 +159,16 @@ def dgemm(layout, A, B, out=None, alpha=1.0, splits=0):
         raise HfbError("dgemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
     nbytes = L.hfb_dgemm_workspace_bytes(layout, M, N, K, splits)
     ws = workspace(nbytes, A.device) if nbytes else None
+    if TIMING is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = L.hfb_dgemm(layout, M, N, K, float(alpha), A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
                      ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, int(splits),
                      _stream())
+    if TIMING is not None:
+        e1.record()
+        TIMING.append(((layout, M, N, K), e0, e1))
     _check(rc, "hfb_dgemm")
     return out
 
@@ -288,6 +297,37 @@ def fill_random_(X, seed, row_offset=0, kind="normal"):
                            0 if kind == "normal" else 1, _stream())
     _check(rc, "hfb_fill_random")
     return X
+
+
+def measure_dmma_peak(device):
+    """FP64 DMMA ceiling of this GPU in TFLOP/s (hfb_measure_dmma_peak)."""
+    L = lib()
+    ws = workspace(1 << 20, device)
+    out = ctypes.c_double(0.0)
+    rc = L.hfb_measure_dmma_peak(ws.data_ptr(), ws.numel(), ctypes.byref(out), _stream())
+    _check(rc, "hfb_measure_dmma_peak")
+    return out.value
+
+
+# optional per-call CUDA-event timing of the GEMM launches (bench.py's roofline leg)
+TIMING = None
+
+
+def start_timing():
+    global TIMING
+    TIMING = []
+
+
+def stop_timing():
+    """Returns {tag: (calls, total_ms)}; tags are (layout, M, N, K)."""
+    global TIMING
+    rec, TIMING = TIMING, None
+    torch.cuda.synchronize()
+    out = {}
+    for tag, e0, e1 in rec or []:
+        c, t = out.get(tag, (0, 0.0))
+        out[tag] = (c + 1, t + e0.elapsed_time(e1))
+    return out
 
 
 def launch_count():

@@ -153,14 +153,34 @@ __global__ void __launch_bounds__(256) colscale_kernel(long long n, long long m,
         X[r * ldx + c] *= s[c];
     }
 }
+// X[r, c] -= shift[c].  2-D mapping (no 64-bit division): a thread owns one 16-byte column pair for RB consecutive
+// rows, so the shift is loaded once and every warp access is a contiguous 512-byte segment.
+template <int RB>
 __global__ void __launch_bounds__(256) subtract_row_kernel(long long N, long long n, double* __restrict__ X,
-                                                           long long ldx, const double* __restrict__ shift) {
-    const long long total = N * n;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / n;
-        const long long c = idx - r * n;
-        X[r * ldx + c] -= shift[c];
+                                                           long long ldx, const double* __restrict__ shift, int vec_ok) {
+    const long long c = 2 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (c >= n) return;
+    const long long r0 = (long long)blockIdx.y * RB;
+    const bool pair = (c + 1 < n);
+    const double s0 = shift[c], s1 = pair ? shift[c + 1] : 0.0;
+    if (vec_ok && pair) {
+#pragma unroll 8
+        for (int i = 0; i < RB; ++i) {
+            const long long r = r0 + i;
+            if (r >= N) break;
+            double2* ptr = reinterpret_cast<double2*>(X + r * ldx + c);
+            double2 v = *ptr;
+            v.x -= s0;
+            v.y -= s1;
+            *ptr = v;
+        }
+    } else {
+        for (int i = 0; i < RB; ++i) {
+            const long long r = r0 + i;
+            if (r >= N) break;
+            X[r * ldx + c] -= s0;
+            if (pair) X[r * ldx + c + 1] -= s1;
+        }
     }
 }
 __global__ void __launch_bounds__(256) axpby_kernel(long long n, long long m, double a, const double* __restrict__ X,
@@ -302,6 +322,24 @@ __global__ void __launch_bounds__(256) dgemm_batched_small_kernel(int M, int N, 
         }
 }
 
+// ------------------------------------------------------------------------------------------ DMMA peak probe
+// Register-resident DMMA.8x8x4 issue loop (no memory traffic): the FP64 tensor-pipe ceiling of this GPU at its
+// current clocks -- the denominator of the GEMM roofline (same loop as tools/microbench_fp64.cu).
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double av, double bv) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = av + threadIdx.x, b = bv;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 static inline unsigned grid_1d(long long total, int per_block = 256) {
     long long blocks = (total + per_block - 1) / per_block;
     const long long cap = 32LL * num_sms();
@@ -408,7 +446,12 @@ extern "C" int hfb_colscale(int64_t n, int64_t m, double* X, int64_t ldx, const 
 }
 extern "C" int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, const double* shift, void* stream_) {
     if (N <= 0 || n <= 0 || !X || !shift || ldx < n) return HFB_E_BADARG;
-    subtract_row_kernel<<<grid_1d(N * n), 256, 0, (cudaStream_t)stream_>>>(N, n, X, ldx, shift);
+    constexpr int RB = 32;
+    const long long by = (N + RB - 1) / RB;
+    if (by > 65535) return HFB_E_UNSUPPORTED;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldx & 1) == 0) ? 1 : 0;
+    dim3 grid((unsigned)(((n + 1) / 2 + 255) / 256), (unsigned)by);
+    subtract_row_kernel<RB><<<grid, 256, 0, (cudaStream_t)stream_>>>(N, n, X, ldx, shift, vec_ok);
     HFB_LAUNCHED();
     return (int)cudaGetLastError();
 }
@@ -433,6 +476,34 @@ extern "C" int hfb_rowscale(int64_t n, int64_t m, const double* s, const double*
     HFB_LAUNCHED();
     return (int)cudaGetLastError();
 }
+extern "C" int hfb_measure_dmma_peak(double* scratch, size_t scratch_bytes, double* tflops_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int sms = num_sms();
+    if (!scratch || !tflops_out || scratch_bytes < (size_t)sms * 256 * 8) return HFB_E_WORKSPACE;
+    cudaEvent_t e0, e1;
+    cudaError_t err;
+    if ((err = cudaEventCreate(&e0)) != cudaSuccess) return (int)err;
+    if ((err = cudaEventCreate(&e1)) != cudaSuccess) return (int)err;
+    const int iters = 20000;
+    dmma_peak_kernel<<<sms, 256, 0, stream>>>(scratch, iters, 1.0, 1.0);  // warm-up
+    HFB_LAUNCHED();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, stream);
+        dmma_peak_kernel<<<sms, 256, 0, stream>>>(scratch, iters, 1.0, 1.0);
+        HFB_LAUNCHED();
+        cudaEventRecord(e1, stream);
+        if ((err = cudaEventSynchronize(e1)) != cudaSuccess) return (int)err;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = 2.0 * 256.0 * 16.0 * (double)iters * 8.0 * sms / ((double)best * 1e-3) * 1e-12;
+    return 0;
+}
+
 extern "C" int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64_t seed, int64_t row_offset,
                                int kind, void* stream_) {
     if (nrows <= 0 || ncols <= 0 || !X || ldx < ncols || kind < 0 || kind > 1) return HFB_E_BADARG;

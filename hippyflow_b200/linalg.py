@@ -12,6 +12,7 @@ Layouts ("operand layouts are fixed by the reference"):
 """
 import numpy as np
 import scipy.linalg as sla
+from scipy.linalg import lapack as _lapack
 import torch
 
 from . import _lib as K
@@ -129,8 +130,9 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
     until the Gram matrix is the identity to round-off -- three passes for cond(Y) up to ~1e15, two for a
     well-conditioned sketch.  Columns that are exactly zero stay zero, as in hIPPYlib's MGS.  Eigenvalues d and
     span(U) of the eigensolve do not depend on which B-orthonormal basis of span(Y) is used.
-    Returns (Q, BQ, info); Q overwrites Y's storage."""
+    Returns (Q, BQ, info); Y's storage may be reused as scratch."""
     n, m = Y.shape
+    spare = None
     eps = np.finfo(np.float64).eps
     info = {"passes": 0, "shifted": 0, "cond": []}
     Z = None
@@ -149,24 +151,25 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
         R = None
         shift = 0.0
         for attempt in range(8):
-            try:
-                Rt = sla.cholesky(Gs + shift * eye, lower=False, check_finite=False)
+            Rt, fail = _lapack.dpotrf(Gs + shift * eye if shift else Gs, lower=0, clean=1, overwrite_a=0)
+            if fail == 0:
                 rd = np.abs(np.diag(Rt))
                 cond = (rd.max() / rd.min()) ** 2
                 if np.isfinite(cond) and (cond < 1e13 or shift > 0.0):
                     R = Rt
                     break
-            except (np.linalg.LinAlgError, sla.LinAlgError):
-                pass
             shift = 100.0 * m * eps if shift == 0.0 else shift * 100.0
         if R is None:
             raise K.HfbError("b_orthonormalize: Gram matrix could not be factorised")
         if shift > 0.0:
             info["shifted"] += 1
         info["cond"].append(float(cond))
-        S = sla.solve_triangular(R, eye, lower=False, check_finite=False) * dinv[:, None]
-        Qn = K.dgemm(K.HFB_NN, Y, K.to_padded(S, Y.device))
-        Y.copy_(Qn)
+        S, fail = _lapack.dtrtri(R, lower=0)                     # R^-1 (upper triangular), then undo the column scaling
+        if fail != 0:
+            raise K.HfbError("b_orthonormalize: singular triangular factor")
+        S *= dinv[:, None]
+        spare = K.dgemm(K.HFB_NN, Y, K.to_padded(S, Y.device), out=spare)
+        Y, spare = spare, Y                                      # ping-pong instead of copying the (n x m) block back
         info["passes"] += 1
         if shift == 0.0 and it >= 1 and cond < 4.0:
             # the previous pass already left cond(G) ~ 1, so this pass is accurate to round-off
@@ -183,7 +186,9 @@ def top_k_eig(T, k):
     """eigh of the small symmetric matrix T on the host, top-k descending
     (hIPPYlib doublePass: np.linalg.eigh(T), sort descending, keep k)."""
     T = _sym(np.asarray(T))
-    d, V = np.linalg.eigh(T)
+    d, V, fail = _lapack.dsyevd(T, compute_v=1, lower=1)
+    if fail != 0:
+        d, V = np.linalg.eigh(T)
     perm = np.argsort(d)[::-1][:k]
     return d[perm], np.ascontiguousarray(V[:, perm])
 

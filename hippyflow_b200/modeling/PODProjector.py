@@ -56,10 +56,21 @@ def _to_scipy_csr(M):
 
 
 def gaussian_omega(n, m, seed, device):
-    """Host-generated Gaussian test matrix (role of hp.parRandom.normal(1., Omega), PODProjector.py:367-372)
-    uploaded as a device multivector; the same (seed, n, m) gives the same Omega on every rank."""
-    Om = np.random.default_rng(seed).standard_normal((n, m))
-    return DeviceMultiVector.from_dense(Om, device)
+    """Gaussian test matrix (role of hp.parRandom.normal(1., Omega), PODProjector.py:367-372) generated on the
+    device by the counter-based generator of hfb_fill_random: the same (seed, n, m) gives the same Omega on
+    every rank.  Parity runs pass an explicit Omega instead so that oracle and GPU see identical values."""
+    Om = DeviceMultiVector(n, m, device=device)
+    K.fill_random_(Om.tensor(), seed)
+    return Om
+
+
+def to_host(t):
+    """Device block -> NumPy array through a pinned staging tensor (torch's caching host allocator reuses the
+    pinned blocks once earlier results are garbage-collected)."""
+    h = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
 
 
 def weighted_l2_norm_vector(x, W):
@@ -90,11 +101,13 @@ class PODProjectorFromData:
         return self._Md
 
     def construct_subspace(self, u_data, u_rank, shifted=True, method='hep', verify=False,
-                           oversampling=10, Omega=None, collective=None, return_device=False, faithful=False):
+                           oversampling=10, Omega=None, collective=None, return_device=False, faithful=False,
+                           overwrite_data=False):
         """Same contract as PODProjector.py:699-852: returns (d, phi, Mphi, u_shift) as NumPy arrays of shape
         (r,), (n, r), (n, r), (n,).  ``u_data`` may be a NumPy array or a float64 CUDA tensor (rows = samples;
         with a collective, the local shard).  Extra keywords (randomized method only): ``oversampling``,
-        ``Omega`` ((n, r+p) array or DeviceMultiVector fed to the solver), ``collective`` (sample-parallel)."""
+        ``Omega`` ((n, r+p) array or DeviceMultiVector fed to the solver), ``collective`` (sample-parallel),
+        ``overwrite_data`` (allow the mean shift to be applied in place to a device-resident ``u_data``)."""
         n_data, dim_u = u_data.shape
         collective = collective if collective is not None else NullCollective()
         n_total = n_data * collective.size()
@@ -110,7 +123,7 @@ class PODProjectorFromData:
             # u_shift = mean over ALL samples (np.mean(u_data, axis=0), PODProjector.py:733), then X - shift
             u_shift_d = K.colsum(Xt, 1.0 / n_data)
             collective.allReduce(u_shift_d, 'avg')
-            if not owns:
+            if not owns and not overwrite_data:
                 Xc = K.padded_empty(n_data, dim_u, dev)
                 Xc.copy_(Xt)
                 Xt = Xc
@@ -146,7 +159,7 @@ class PODProjectorFromData:
                 print(f"Max reconstruction error: {np.max(rel):.3e}")
         if return_device:
             return d, phi_d, Mphi_d, u_shift_d
-        return d, phi_d.cpu().numpy().copy(), Mphi_d.cpu().numpy().copy(), u_shift_d.cpu().numpy()
+        return d, to_host(phi_d), to_host(Mphi_d), u_shift_d.cpu().numpy()
 
     # ---------------------------------------------------------------- randomized GHEP (north star (a))
     def _randomized(self, Xt, Md, u_rank, oversampling, Omega, collective, faithful):

@@ -85,3 +85,47 @@ def gaussian_omega(n, m, seed=1):
     """Gaussian test matrix (n, m), the role of hp.parRandom.normal(1., Omega)
     (PODProjector.py:367-372).  Generated on the host so the SAME Omega feeds oracle and GPU."""
     return np.random.default_rng(seed).standard_normal((n, m))
+
+
+# --------------------------------------------------------------------------- device-side generators (benchmark sizes)
+def p1_mass_matrix_for(n):
+    """Mass matrix with exactly n = (nx+1)^2 dofs (n must be a perfect square)."""
+    side = int(round(np.sqrt(n)))
+    assert side * side == n, "n must be a perfect square"
+    return p1_mass_matrix(side - 1)
+
+
+def snapshots_device(n, N, device, r0=512, decay=1.0, eps=1e-6, seed=0, row_offset=0):
+    """(N, n) snapshot shard generated in HBM: X = G diag(j^-decay) Phi0^T + eps * noise with G and the noise from
+    the counter-based generator keyed by (seed, GLOBAL sample index), so that the data does not depend on how
+    the samples are sharded over GPUs (``row_offset`` = first global sample of this shard).  Same construction as
+    ``snapshots`` (different random stream).  Uses the library's own GEMM for G Phi0^T."""
+    import torch
+    from . import _lib as K
+    side = int(round(np.sqrt(n)))
+    r0 = min(r0, n)
+    if side * side == n:
+        x = torch.linspace(0.0, 1.0, side, dtype=torch.float64, device=device)
+        ab = torch.as_tensor(_mode_table(r0), device=device)
+        Sx = torch.sin(np.pi * x[:, None] * torch.arange(1, int(ab.max()) + 1, device=device, dtype=torch.float64)[None, :])
+        Phi = K.padded_empty(n, r0, device)
+        Phi.copy_((Sx[:, None, ab[:, 0] - 1] * Sx[None, :, ab[:, 1] - 1]).reshape(n, r0))
+    else:
+        x = torch.linspace(0.0, 1.0, n, dtype=torch.float64, device=device)
+        Phi = K.padded_empty(n, r0, device)
+        Phi.copy_(torch.sin(np.pi * x[:, None] * torch.arange(1, r0 + 1, device=device, dtype=torch.float64)[None, :]))
+    G = K.padded_empty(N, r0, device)
+    K.fill_random_(G, seed, row_offset=row_offset)
+    sig = torch.arange(1, r0 + 1, dtype=torch.float64, device=device) ** (-decay)
+    K.colscale_(G, sig)
+    X = K.padded_empty(N, n, device)
+    K.dgemm(K.HFB_NT, G, Phi, out=X)                       # (N x r0) (n x r0)^T
+    del Phi, G
+    chunk = max(1, min(N, (1 << 28) // max(n, 1)))         # noise in chunks of <= 2 GiB
+    for i0 in range(0, N, chunk):
+        i1 = min(N, i0 + chunk)
+        noise = K.padded_empty(i1 - i0, n, device)
+        K.fill_random_(noise, seed + 0x9E3779B9, row_offset=row_offset + i0)
+        K.axpby_(eps, noise, 1.0, X[i0:i1])
+        del noise
+    return X

@@ -126,6 +126,11 @@ int hfb_rowscale(int64_t n, int64_t m, const double* s, const double* X, int64_t
 int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64_t seed, int64_t row_offset,
                     int kind, void* stream);
 
+/* Measure the FP64 tensor-pipe ceiling of the current device (register-resident DMMA.8x8x4 loop, 8 warps/SM,
+ * best of 5): the roofline denominator bench.py reports the GEMM against.  Synchronises the stream.
+ * scratch: >= SMs*256*8 bytes of device memory; *tflops_out is a HOST double. */
+int hfb_measure_dmma_peak(double* scratch, size_t scratch_bytes, double* tflops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
