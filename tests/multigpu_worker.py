@@ -1,0 +1,84 @@
+"""Worker for the multi-GPU parity test (launched by torch.distributed.run, one rank per GPU):
+sample-sharded randomized POD / KLE / AS over NCCL must reproduce the single-rank oracle with the same Omega."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import hippyflow_b200 as hf
+    from hippyflow_b200 import synthetic as syn
+    from oracle import projectors_np as P
+    coll = hf.MultipleSerialPDEsCollective()
+    assert coll.size() == world and coll.rank() == rank
+
+    nx = 24
+    M = syn.p1_mass_matrix(nx)
+    n = M.shape[0]
+    N = 64 * world
+    u = syn.snapshots(n, N, r0=48, seed=11) + 0.2 * np.cos(np.linspace(0, 2, n))[None, :]
+    Om = syn.gaussian_omega(n, 30, seed=12)
+    shard = u[rank * 64:(rank + 1) * 64]
+
+    # weighted randomized POD, shifted (global mean needs an allreduce)
+    proj = hf.PODProjectorFromData(None, M_output=M, device=dev)
+    d, phi, Mphi, shift = proj.construct_subspace(shard.copy(), 20, shifted=True, method="randomized", Omega=Om, collective=coll)
+    d0, U0, E0, s0 = P.pod_randomized_weighted(u, M, 20, Om, shifted=True, ranks=world)
+    k = int(np.sum(d0 / d0[0] > 1e-5))
+    assert np.abs(d[:k] - d0[:k]).max() / 1.0 < 1e-10 * d0[0] or np.allclose(d[:k], d0[:k], rtol=1e-10), (d, d0)
+    np.testing.assert_allclose(d[:k], d0[:k], rtol=1e-10)
+    assert P.principal_angle(phi[:, :k], U0[:, :k], M) < 1e-8
+    np.testing.assert_allclose(shift, s0, atol=1e-14)
+
+    # PODProjector: Omega drawn on rank 0 and broadcast (PODProjector.py:367-374) -> identical on all ranks
+    params = hf.PODParameterList()
+    params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = 20, 10, False, False
+    pp = hf.PODProjector(hf.StoredSnapshots(shard.copy()), collective=coll, parameters=params, device=dev)
+    d2, U2 = pp.construct_subspace()
+    Om_used = pp.Omega.to_dense()
+    gathered = [torch.zeros_like(pp.Omega.tensor().contiguous()) for _ in range(world)]
+    dist.all_gather(gathered, pp.Omega.tensor().contiguous())
+    for g in gathered:
+        assert torch.equal(g, gathered[0])
+    d3, U3 = P.pod_randomized(u, 20, Om_used, ranks=world)
+    k = int(np.sum(d3 / d3[0] > 1e-5))
+    np.testing.assert_allclose(d2[:k], d3[:k], rtol=1e-10)
+    assert P.principal_angle(hf.mv_to_dense(U2)[:, :k], U3[:, :k]) < 1e-8
+
+    # active subspace from sharded stored Jacobians
+    J = syn.jacobians(8 * world, 30, 121, r0=16, seed=13)
+    OmJ = syn.gaussian_omega(121, 26, seed=14)
+    pa = hf.ActiveSubspaceParameterList()
+    pa["rank"], pa["oversampling"], pa["verbose"], pa["save_and_plot"] = 16, 10, False, False
+    asp = hf.ActiveSubspaceProjector(hf.StoredJacobians(J[rank * 8:(rank + 1) * 8]), None, collective=coll, parameters=pa, device=dev)
+    asp.Omega_GN = OmJ
+    dj, Vj, _ = asp.construct_input_subspace(prior_preconditioned=False)
+    dj0, Vj0, _ = P.as_input_from_jacobians(J, 16, OmJ, ranks=world)
+    k = int(np.sum(dj0 / dj0[0] > 1e-5))
+    np.testing.assert_allclose(dj[:k], dj0[:k], rtol=1e-10)
+    assert P.principal_angle(hf.mv_to_dense(Vj)[:, :k], Vj0[:, :k]) < 1e-8
+
+    # collective on device blocks: one NCCL call for the whole padded block, 'avg' = sum / size
+    mv = hf.DeviceMultiVector(50, 7, device=dev)
+    mv.tensor().fill_(float(rank + 1))
+    coll.allReduce(mv, "avg")
+    assert torch.allclose(mv.tensor(), torch.full_like(mv.tensor(), (world + 1) / 2.0))
+    assert coll.allReduce(float(rank), "sum") == sum(range(world))
+    dist.barrier()
+    if rank == 0:
+        print("MULTIGPU_OK world=%d" % world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

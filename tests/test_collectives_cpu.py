@@ -76,6 +76,23 @@ def _worker(rank, world, port, q):
         x, y = Vector(np.array([1.0, 2.0, 3.0])), Vector(np.zeros(3))
         op.mult(x, y)
         res["op"] = y.get_local()
+
+        # the N > 1 eigensolve path on CPU: each rank holds a sample shard, the repo's CollectiveOperator('avg')
+        # over gloo wraps the local operator, Omega is drawn on rank 0 and broadcast (PODProjector.py:360-376)
+        from oracle import hippylib_np as hnp
+        from oracle import projectors_np as P
+        from hippyflow_b200 import synthetic as syn
+        M = syn.p1_mass_matrix(8)
+        n = M.shape[0]
+        u = syn.snapshots(n, 16 * world, r0=20, seed=3)
+        shard = u[rank * 16:(rank + 1) * 16]
+        local = hnp.LowRankOperator(np.ones(16) / 16, hnp.MultiVector.from_dense(shard.T))
+        A = CollectiveOperator(local, c, "avg")
+        Om = syn.gaussian_omega(n, 14, seed=4) if rank == 0 else np.zeros((n, 14))
+        c.bcast(Om, root=0)
+        d, U = hnp.doublePass(A, hnp.MultiVector.from_dense(Om), 8, s=1)
+        res["d"], res["Omega00"] = d, float(Om[0, 0])
+        res["d_serial"] = P.pod_randomized(u, 8, syn.gaussian_omega(n, 14, seed=4), ranks=1)[0]
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -103,6 +120,8 @@ def test_torch_collective_gloo_world2():
         assert r["bcast_scalar"] == 0.5
         assert r["bad_op"] and r["bad_type"]
         np.testing.assert_allclose(r["op"], 1.5 * np.array([1.0, 2.0, 3.0]))
+        np.testing.assert_allclose(r["d"], r["d_serial"], rtol=1e-12)
+        assert r["Omega00"] == results[0]["Omega00"]
 
 
 def test_null_collective_and_operator_protocol():
