@@ -4,6 +4,7 @@
 // with a fixed summation order (bitwise reproducible), no atomics.
 #include "../../include/hfb200.h"
 #include "hfb_common.cuh"
+#include <cstdlib>
 
 namespace hfb {
 
@@ -60,6 +61,60 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(long long nrows, int m, c
                 if (c < m) crow[c] = acc[i].x;
                 if (c + 1 < m) crow[c + 1] = acc[i].y;
             }
+        }
+    }
+}
+
+// v2: (row block) x (64-column panel) decomposition.  A CTA of 16 warps walks 64 consecutive rows (16 at a time) of one
+// 64-column panel, so the B-row segments shared by neighbouring rows (FEM stencils) are re-used out of L1 instead of
+// being re-fetched from L2; the CSR entries of a row are fetched by one coalesced load and broadcast by shuffles,
+// which leaves three dependent memory latencies per row instead of 2*nnz.
+constexpr int SPMM_WARPS = 16;
+constexpr int SPMM_ROWS_PER_CTA = 64;
+__global__ void __launch_bounds__(SPMM_WARPS * 32) csr_spmm_panel_kernel(long long nrows, int m, const int* __restrict__ rowptr,
+                                                                        const int* __restrict__ colind,
+                                                                        const double* __restrict__ val,
+                                                                        const double* __restrict__ B, long long ldb,
+                                                                        double* __restrict__ C, long long ldc, int vec_ok) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.y * 64 + 2 * lane;
+    const bool in0 = c < m, in1 = c + 1 < m;
+    const long long row_base = (long long)blockIdx.x * SPMM_ROWS_PER_CTA;
+#pragma unroll 1
+    for (int i = 0; i < SPMM_ROWS_PER_CTA / SPMM_WARPS; ++i) {
+        const long long row = row_base + i * SPMM_WARPS + warp;
+        if (row >= nrows) break;
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        double2 acc = make_double2(0.0, 0.0);
+        for (int base = beg; base < end; base += 32) {
+            const int cnt = min(32, end - base);
+            int my_col = 0;
+            double my_val = 0.0;
+            if (lane < cnt) {
+                my_col = __ldg(colind + base + lane);
+                my_val = __ldg(val + base + lane);
+            }
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const int col = __shfl_sync(0xffffffffu, my_col, j);
+                const double v = __shfl_sync(0xffffffffu, my_val, j);
+                const double* bp = B + (long long)col * ldb + c;
+                if (vec_ok && in1) {
+                    const double2 b = *reinterpret_cast<const double2*>(bp);
+                    acc.x = fma(v, b.x, acc.x);
+                    acc.y = fma(v, b.y, acc.y);
+                } else {
+                    if (in0) acc.x = fma(v, bp[0], acc.x);
+                    if (in1) acc.y = fma(v, bp[1], acc.y);
+                }
+            }
+        }
+        double* cp = C + row * ldc + c;
+        if (vec_ok && in1) {
+            *reinterpret_cast<double2*>(cp) = acc;
+        } else {
+            if (in0) cp[0] = acc.x;
+            if (in1) cp[1] = acc.y;
         }
     }
 }
@@ -361,12 +416,20 @@ extern "C" int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, con
                             const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nrows <= 0 || m <= 0 || !rowptr || !colind || !val || !B || !C || ldb < m || ldc < m) return HFB_E_BADARG;
-    if (m > 512) return HFB_E_UNSUPPORTED;
     if (B == C) return HFB_E_BADARG;
     const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
                         (ldb & 1) == 0 && (ldc & 1) == 0)
                            ? 1
                            : 0;
+    static const bool use_v1 = (getenv("HFB_SPMM_V1") != nullptr);
+    if (!use_v1) {
+        const long long bx = (nrows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA;
+        if (bx > 0x7fffffffLL) return HFB_E_UNSUPPORTED;
+        dim3 grid((unsigned)bx, (unsigned)((m + 63) / 64));
+        csr_spmm_panel_kernel<<<grid, SPMM_WARPS * 32, 0, stream>>>(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok);
+        HFB_LAUNCHED();
+        return (int)cudaGetLastError();
+    }
     const int ch = (int)((m + 63) / 64);
     long long blocks = (nrows + 7) / 8;  // 8 warps (rows) per CTA
     const long long cap = 16LL * num_sms();
