@@ -179,7 +179,14 @@ class PODProjectorFromData:
 
     # ---------------------------------------------------------------- method of snapshots ('hep' :812-833)
     def _snapshot_eig(self, Xt, Md, u_rank, method):
+        """'hep' is the reference's method of snapshots.  'ghep' (:743-773) and 'inverse_ghep' (:775-810) pose the
+        SAME eigenproblem, (1/N) X X^T M phi = d phi with phi^T M phi = I, to ARPACK in generalized mode; their
+        eigenpairs coincide with 'hep' (the reference's three outputs agree to ~1e-12 on the golden fixture).
+        Here they are solved to machine precision by a dense factorisation instead of Lanczos: through the
+        (N x N) snapshot Gram matrix when n_data <= dim_u, through the dense (n x n) pencil (H, M) otherwise."""
         n_data, n = Xt.shape
+        if method != 'hep' and n_data > n:
+            return self._dense_pencil_eig(Xt, Md, u_rank)
         Zt = Md.matmat_rows(Xt)                                   # (M X)^T, sample-major
         G = K.dgemm(K.HFB_NT, Xt, Zt)                             # X^T M X  (N x N)
         del Zt
@@ -197,6 +204,19 @@ class PODProjectorFromData:
         K.colscale_(phi, 1.0 / nrm)
         Mphi = Md.matmat(phi)
         return np.ascontiguousarray(d), phi, Mphi
+
+
+    def _dense_pencil_eig(self, Xt, Md, u_rank):
+        import scipy.linalg as sla
+        n_data, n = Xt.shape
+        if n > 4096:
+            raise NotImplementedError("ghep / inverse_ghep with n_data > dim_u > 4096: use method='randomized'")
+        Zt = Md.matmat_rows(Xt)                                   # (M X)^T
+        H = K.dgemm(K.HFB_TN, Zt, Zt, alpha=1.0 / n_data).cpu().numpy()   # M X X^T M / N  (n x n)
+        w, V = sla.eigh(0.5 * (H + H.T), self.M_csr.toarray())    # V^T M V = I
+        d = np.ascontiguousarray(w[::-1][:u_rank])
+        phi = K.to_padded(np.ascontiguousarray(V[:, ::-1][:, :u_rank]), self.device)
+        return d, phi, Md.matmat(phi)
 
 
 class StoredSnapshots:

@@ -69,13 +69,14 @@ def test_pod_randomized_faithful_equals_shortcut(hf, cuda_device, golden_pod, go
 
 
 # ------------------------------------------------------------------ POD, deterministic 'hep' vs reference verbatim
+@pytest.mark.parametrize("method", ["hep", "ghep", "inverse_ghep"])
 @pytest.mark.parametrize("shifted", [True, False])
-def test_pod_hep_vs_reference_golden(hf, cuda_device, golden_pod, shifted):
+def test_pod_hep_vs_reference_golden(hf, cuda_device, golden_pod, shifted, method):
     g = golden_pod
     M = syn.p1_mass_matrix(int(g["nx"]))
     proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
-    d, phi, Mphi, shift = proj.construct_subspace(g["u_data"].copy(), 15, shifted=shifted, method="hep")
-    key = f"hep_{int(shifted)}"
+    d, phi, Mphi, shift = proj.construct_subspace(g["u_data"].copy(), 15, shifted=shifted, method=method)
+    key = f"{method}_{int(shifted)}"
     np.testing.assert_allclose(d, g[key + "_d"], rtol=1e-9)
     np.testing.assert_allclose(shift, g[key + "_shift"], rtol=0, atol=1e-14)
     assert subspace_angle(phi[:, :10], g[key + "_phi"][:, :10], M) < 1e-7
@@ -89,6 +90,18 @@ def test_pod_hep_vs_reference_golden(hf, cuda_device, golden_pod, shifted):
     for i in range(rv):
         lhs = C @ (M @ phi[:, i])
         assert np.linalg.norm(lhs - d[i] * phi[:, i]) / np.linalg.norm(d[i] * phi[:, i]) < 1e-2
+
+
+def test_pod_ghep_dense_pencil_when_more_samples_than_dofs(hf, cuda_device):
+    """n_data > dim_u: the (n x n) pencil route; checked against the restated reference (ARPACK 'ghep')."""
+    M = syn.p1_mass_matrix(6)                                     # 49 dofs
+    u = syn.snapshots(49, 200, r0=30, seed=4)
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    d, phi, Mphi, shift = proj.construct_subspace(u.copy(), 8, shifted=True, method="ghep")
+    d0, phi0, Mphi0, s0 = P.pod_from_data(u.copy(), M, 8, shifted=True, method="ghep")
+    np.testing.assert_allclose(d, d0, rtol=1e-9)
+    assert subspace_angle(phi[:, :6], phi0[:, :6], M) < 1e-7
+    np.testing.assert_allclose(phi.T @ Mphi, np.eye(8), atol=1e-10)
 
 
 def test_pod_unavailable_method_and_rank_check(hf, cuda_device, golden_pod):
@@ -260,3 +273,43 @@ def test_pod_randomized_midsize_vs_blocked_oracle(hf, cuda_device):
     k = leading(d0)
     assert subspace_angle(phi[:, :k], U0[:, :k], M) < ANGLE_TOL
     assert np.linalg.norm(phi.T @ Mphi - np.eye(64)) < 1e-10
+
+
+# ------------------------------------------------------------------ on-disk data contract
+def test_data_contract_roundtrip(hf, cuda_device, tmp_path, golden_jtj):
+    from hippyflow_b200 import dataIO
+    rng = np.random.default_rng(3)
+    N, dM, dQ, r = 24, 121, 30, 6
+    m_data, q_data = rng.standard_normal((N, dM)), rng.standard_normal((N, dQ))
+    np.savez_compressed(tmp_path / "mq_data.npz", m_data=m_data, q_data=q_data)
+    m0, q0 = dataIO.load_mq_data(str(tmp_path), cuda_device, rank=1, world=2)
+    np.testing.assert_array_equal(m0.cpu().numpy(), m_data[12:24])
+    np.testing.assert_array_equal(q0.cpu().numpy(), q_data[12:24])
+    # low-rank stored Jacobians: the SVD factor reproduces mean(J^T J) exactly
+    U = np.linalg.qr(rng.standard_normal((N, dQ, r)))[0]
+    V = np.linalg.qr(rng.standard_normal((N, dM, r)))[0]
+    s = np.abs(rng.standard_normal((N, r))) + 0.1
+    np.savez_compressed(tmp_path / "Jsvd_data.npz", U_data=U, sigma_data=s, V_data=V)
+    J = np.einsum("iqr,ir,imr->iqm", U, s, V)
+    Xt, blk = dataIO.load_jacobian_svd_factor(str(tmp_path), cuda_device)
+    assert blk == r and tuple(Xt.shape) == (N * r, dM)
+    from hippyflow_b200.linalg import SampleCovariance
+    Om = syn.gaussian_omega(dM, 9, seed=1)
+    from hippyflow_b200 import _lib as K
+    Y = SampleCovariance(Xt, block=r).apply(K.to_padded(Om, cuda_device)).cpu().numpy()
+    ref = np.einsum("iqm,iqk->mk", J, J @ Om) / N
+    assert np.linalg.norm(Y - ref) / np.linalg.norm(ref) < PROJ_RTOL
+    # reduced data set + projector file names
+    enc_in = np.linalg.qr(rng.standard_normal((dM, 5)))[0]
+    enc_out = np.linalg.qr(rng.standard_normal((dQ, 4)))[0]
+    shift = q_data.mean(0)
+    m_r, q_r = dataIO.reduce_dataset(str(tmp_path), enc_in, enc_out, cuda_device, q_shift=shift, out_name="mq_reduced.npz")
+    np.testing.assert_allclose(m_r.cpu().numpy(), m_data @ enc_in, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(q_r.cpu().numpy(), (q_data - shift) @ enc_out, rtol=1e-12, atol=1e-14)
+    z = np.load(tmp_path / "mq_reduced.npz")
+    assert z["m_data"].shape == (N, 5) and z["q_data"].shape == (N, 4)
+    dataIO.save_pod(str(tmp_path), enc_out, np.arange(4.0))
+    dataIO.save_kle(str(tmp_path), enc_in, np.arange(5.0))
+    dataIO.save_active_subspace(str(tmp_path), enc_in, np.arange(5.0), 128)
+    for f in ("POD_projector.npy", "POD_d.npy", "KLE_decoder.npy", "KLE_d.npy", "AS_128_input_decoder.npy", "AS_128_d_GN.npy"):
+        assert (tmp_path / f).exists(), f
