@@ -2,5 +2,6 @@ from .PODProjector import PODParameterList, PODProjector, PODProjectorFromData, 
 from .KLEProjector import KLEParameterList, KLEProjector, MassPreconditionedCovarianceOperator, SampleCovariancePrior
 from .activeSubspaceProjector import (ActiveSubspaceParameterList, ActiveSubspaceProjector, SparsePrior,
                                       StoredJacobians)
-from .operators import MeanJTJfromDataOperator, SampleCovarianceOperator, SandwichedCovarianceOperator
+from .operators import (JTJ, MeanJTJfromDataOperator, SampleCovarianceOperator, SandwichedCovarianceOperator,
+                        SummedListOperator)
 from .projection import jacobian_action, jacobian_transpose_action, project_data, reduced_jacobians

@@ -147,3 +147,53 @@ class MeanJTJfromDataOperator:
 
     def rayleigh(self, Q, BQ):
         return self._op.rayleigh(Q, BQ)
+
+
+class JTJ:
+    """Gauss-Newton Hessian J^T J of ONE stored Jacobian (dQ, dM): the stored-data form of
+    hippyflow/modeling/jacobian.py:142-166 (there every apply is an incremental forward and adjoint PDE solve)."""
+
+    def __init__(self, J, device=None):
+        if device is None:
+            device = J.device if isinstance(J, torch.Tensor) and J.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        self._cov = SampleCovariance(_as_device_rows(J, device), block=J.shape[0])
+        self.dM = J.shape[1]
+
+    def init_vector(self, x, dim=0):
+        x.init(self.dM)
+
+    def matMvMult(self, X, Y):
+        self._cov.apply(X.tensor(), out=Y.tensor(), scale=1.0)
+
+    def mult(self, x, y):
+        self._cov.apply(x.storage_tensor(), out=y.storage_tensor(), scale=1.0)
+
+    transpmult = mult
+
+
+class SummedListOperator:
+    """hippyflow/modeling/activeSubspaceProjector.py:69-95: sum (or average) of a list of operators of equal
+    dimension.  Works on device vectors and, block-wise, on device multivectors."""
+
+    def __init__(self, operators, communicator=None, average=True):
+        assert type(operators) is list
+        self.operators = operators
+        self.average = average
+
+    def init_vector(self, x, dim=0):
+        self.operators[0].init_vector(x, dim)
+
+    def _accumulate(self, apply, x, y, make_tmp):
+        acc = make_tmp()
+        for op in self.operators:
+            apply(op, x, y)
+            acc.axpy(1.0, y)
+        y.zero()
+        y.axpy(1.0 / float(len(self.operators)) if self.average else 1.0, acc)
+
+    def mult(self, x, y):
+        self._accumulate(lambda op, a, b: op.mult(a, b), x, y, lambda: DeviceVector(y.size(), y.storage_tensor().device))
+
+    def matMvMult(self, X, Y):
+        self._accumulate(lambda op, a, b: op.matMvMult(a, b), X, Y,
+                         lambda: DeviceMultiVector(Y.tensor().shape[0], Y.nvec(), device=Y.tensor().device))

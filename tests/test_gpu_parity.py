@@ -313,3 +313,65 @@ def test_data_contract_roundtrip(hf, cuda_device, tmp_path, golden_jtj):
     dataIO.save_active_subspace(str(tmp_path), enc_in, np.arange(5.0), 128)
     for f in ("POD_projector.npy", "POD_d.npy", "KLE_decoder.npy", "KLE_d.npy", "AS_128_input_decoder.npy", "AS_128_d_GN.npy"):
         assert (tmp_path / f).exists(), f
+
+
+# ------------------------------------------------------------------ batched vs stacked operator forms, edge cases
+def test_batched_list_and_stacked_operator_give_equal_eigenvalues(hf, cuda_device, golden_jtj, golden_dp):
+    """The invariant of test_derivativeSubspace.py:83-102: two ways of applying the sample-averaged operator
+    (a SummedListOperator of per-sample J^T J wrapped in CollectiveOperator vs the stacked one-GEMM-pair form in
+    MatrixMultCollectiveOperator) give the same eigenvalues with the same Omega, ||d1 - d2||_2 < 1e-12."""
+    J = golden_jtj["J"][:16]
+    Om = hf.DeviceMultiVector.from_dense(golden_dp["Omega_as"][:, :30], cuda_device)
+    coll = hf.NullCollective()
+    batched = hf.CollectiveOperator(hf.SummedListOperator([hf.JTJ(J[i], cuda_device) for i in range(16)], average=True), coll, "avg")
+    stacked = hf.MatrixMultCollectiveOperator(hf.MeanJTJfromDataOperator(J, None, None, device=cuda_device), coll, "avg")
+    d1, U1 = hf.doublePass(batched, Om, 20, s=1)
+    d2, U2 = hf.doublePass(stacked, Om, 20, s=1, faithful=True)
+    d3, U3 = hf.doublePass(stacked.local_op, Om, 20, s=1)
+    assert np.linalg.norm(d1 - d2) < 1e-12 * max(1.0, d1[0])
+    assert np.linalg.norm(d1 - d3) < 1e-12 * max(1.0, d1[0])
+
+
+def test_rank_deficient_snapshots_and_extreme_ranks(hf, cuda_device):
+    """Edge cases: fewer independent snapshots than requested modes (trailing eigenvalues are round-off, nothing is
+    NaN), u_rank == n_data, no oversampling, a single snapshot."""
+    M = syn.p1_mass_matrix(9)                        # 100 dofs
+    n = M.shape[0]
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((5, n))
+    u = rng.standard_normal((30, 5)) @ base            # 30 snapshots of rank 5
+    Om = syn.gaussian_omega(n, 22, seed=2)
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    d, phi, Mphi, shift = proj.construct_subspace(u.copy(), 12, shifted=False, method="randomized", Omega=Om)
+    d0, U0, _, _ = P.pod_randomized_weighted(u, M, 12, Om, shifted=False)
+    assert np.all(np.isfinite(d)) and np.all(np.isfinite(phi))
+    np.testing.assert_allclose(d[:5], d0[:5], rtol=EIG_RTOL)
+    assert np.all(np.abs(d[5:]) < 1e-12 * d[0])
+    assert subspace_angle(phi[:, :5], U0[:, :5], M) < ANGLE_TOL
+    # u_rank == n_data with zero oversampling
+    u2 = syn.snapshots(n, 8, r0=8, seed=5)
+    d2, phi2, _, _ = proj.construct_subspace(u2.copy(), 8, shifted=False, method="randomized", oversampling=0,
+                                             Omega=Om[:, :8])
+    d20, U20, _, _ = P.pod_randomized_weighted(u2, M, 8, Om[:, :8], shifted=False)
+    k = leading(d20)
+    np.testing.assert_allclose(d2[:k], d20[:k], rtol=EIG_RTOL)
+    # deterministic route with u_rank == n_data
+    d3, phi3, Mphi3, _ = proj.construct_subspace(u2.copy(), 8, shifted=False, method="hep")
+    d30, _, _, _ = P.pod_from_data(u2.copy(), M, 8, shifted=False, method="hep")
+    np.testing.assert_allclose(d3, d30, rtol=1e-9)
+    # one snapshot, rank 1
+    d4, phi4, Mphi4, _ = proj.construct_subspace(u2[:1].copy(), 1, shifted=False, method="randomized", oversampling=2,
+                                                 Omega=Om[:, :3])
+    x = u2[0]
+    np.testing.assert_allclose(d4[0], x @ (M @ x), rtol=1e-10)
+
+
+def test_projector_files_written_with_reference_names(hf, cuda_device, tmp_path, golden_pod, golden_dp):
+    out = str(tmp_path) + "/"
+    params = hf.PODParameterList()
+    params["rank"], params["oversampling"], params["verbose"], params["output_directory"] = 15, 10, False, out
+    proj = hf.PODProjector(hf.StoredSnapshots(golden_pod["u_data"]), parameters=params, device=cuda_device)
+    proj.construct_subspace(Omega=golden_dp["Omega"])
+    U = np.load(out + "POD_projector.npy")
+    np.testing.assert_allclose(np.load(out + "POD_d.npy"), golden_dp["d_pod"], rtol=EIG_RTOL)   # PODProjector.py:383-384
+    assert U.shape == (289, 15)
