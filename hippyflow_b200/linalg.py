@@ -81,6 +81,8 @@ class SampleCovariance:
         where GW = blockdiag(Gamma^-1) W (or W itself)."""
         m = B.shape[1]
         W = self._wbuf(m)
+        if B.data_ptr() % 16 or K._ld(B) % 2:
+            B = K.to_padded(B, B.device)      # e.g. one column of a multivector block: stage into a TMA-aligned buffer
         K.dgemm(K.HFB_NN, self.Xt, B, out=W)
         if self.noise_cov_inv is None:
             return W, W
