@@ -119,7 +119,7 @@ def _sym(G):
     return 0.5 * (G + G.T)
 
 
-def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
+def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=False):
     """Orthonormalise the columns of the sketch Y (n, m) in the inner product of the sparse SPD matrix
     ``Bmat`` (None = Euclidean): the role of MultiVector.Borthogonalize / orthogonalize inside hIPPYlib's
     doublePassG / doublePass.
@@ -132,7 +132,14 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
     until the Gram matrix is the identity to round-off -- three passes for cond(Y) up to ~1e15, two for a
     well-conditioned sketch.  Columns that are exactly zero stay zero, as in hIPPYlib's MGS.  Eigenvalues d and
     span(U) of the eigensolve do not depend on which B-orthonormal basis of span(Y) is used.
-    Returns (Q, BQ, info); Y's storage may be reused as scratch."""
+    Returns (Q, BQ, info); Y's storage may be reused as scratch.
+
+    ``defer_last=True`` (used by the double-pass drivers): when the first pass was well conditioned
+    (cond(G) * eps * m < 1e-4, so Q1 is B-orthonormal to ~1e-7 or better) the clean-up pass is not applied to the
+    (n x m) block.  Q1, Z1 = B Q1 and the device matrix G1 = Q1^T Z1 (``info["gram"]``) are returned instead; the
+    caller folds the clean-up factor S2 = chol(G1)^-1 into the small matrices (T = S2^T T1 S2, U = Q1 (S2 V)),
+    which is the same algebra as Q = Q1 S2 without the (n x m) update GEMM, one SpMM and one host round trip on
+    the critical path."""
     n, m = Y.shape
     spare = None
     eps = np.finfo(np.float64).eps
@@ -173,6 +180,10 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
         spare = K.dgemm(K.HFB_NN, Y, K.to_padded(S, Y.device), out=spare)
         Y, spare = spare, Y                                      # ping-pong instead of copying the (n x m) block back
         info["passes"] += 1
+        if defer_last and it == 0 and shift == 0.0 and cond * eps * m < 1e-4:
+            Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
+            info["gram"] = K.dgemm(K.HFB_TN, Y, Z)                 # device (m x m); fetched by the caller, asynchronously
+            return Y, (Z if return_BQ else None), info
         if shift == 0.0 and it >= 1 and cond < 4.0:
             # the previous pass already left cond(G) ~ 1, so this pass is accurate to round-off
             Z = None
@@ -182,6 +193,18 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True):
     if return_BQ:
         BQ = Bmat.matmat(Q) if Bmat is not None else Q
     return Q, BQ, info
+
+
+def cleanup_factor(G1):
+    """S2 = chol(G1)^-1 (upper triangular) for the Gram matrix G1 ~ I of a nearly B-orthonormal basis:
+    Q = Q1 S2 is B-orthonormal to round-off."""
+    R, fail = _lapack.dpotrf(_sym(np.asarray(G1)), lower=0, clean=1, overwrite_a=0)
+    if fail != 0:
+        raise K.HfbError("cleanup_factor: Gram matrix of the pre-orthonormalised basis is not positive definite")
+    S, fail = _lapack.dtrtri(R, lower=0)
+    if fail != 0:
+        raise K.HfbError("cleanup_factor: singular triangular factor")
+    return S
 
 
 def top_k_eig(T, k):

@@ -51,9 +51,13 @@ class SampleCovarianceOperator:
     def rayleigh(self, Q, BQ):
         """T = Q^T A Q (m x m, host) as a Gram matrix of the projected samples; only an (m x m) allreduce.
         (BQ is unused: A = C does not involve B.)"""
+        return self.rayleigh_device(Q, BQ).cpu().numpy()
+
+    def rayleigh_device(self, Q, BQ):
+        """Same, left on the device (asynchronous)."""
         T = self.cov.gram_T(Q.tensor())
         self.collective.allReduce(T, self.mpi_op)
-        return T.cpu().numpy()
+        return T
 
 
 class SandwichedCovarianceOperator:
@@ -89,6 +93,9 @@ class SandwichedCovarianceOperator:
 
     def rayleigh(self, Q, BQ):
         return self.C.rayleigh(BQ, None)   # Q^T (B C B) Q = (BQ)^T C (BQ)
+
+    def rayleigh_device(self, Q, BQ):
+        return self.C.rayleigh_device(BQ, None)
 
 
 class MeanJTJfromDataOperator:
@@ -147,6 +154,9 @@ class MeanJTJfromDataOperator:
 
     def rayleigh(self, Q, BQ):
         return self._op.rayleigh(Q, BQ)
+
+    def rayleigh_device(self, Q, BQ):
+        return self._op.rayleigh_device(Q, BQ)
 
 
 class JTJ:

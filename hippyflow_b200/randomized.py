@@ -7,14 +7,19 @@ Algorithm (s = 1 at every reference call site):
     doublePassG(A, B, Binv, Omega, k): Q = B-orth(Binv A Omega);      T = Q^T A Q; eigh; U = Q V, U^T B U = I
 Differences from the column-by-column hIPPYlib code, none of which changes d or span(U):
   * A is applied to all m = k + p columns at once (two DMMA GEMMs + one NCCL allreduce per pass);
-  * (B-)orthonormalisation is Cholesky-QR / eig-QR on the Gram matrix instead of MGS (linalg.b_orthonormalize);
+  * (B-)orthonormalisation is (shifted) Cholesky-QR on the Gram matrix instead of MGS (linalg.b_orthonormalize);
+    when the first pass is well conditioned its clean-up pass is folded into the small matrices
+    (T = S2^T T1 S2, U = Q1 (S2 V)) and the host factorisation overlaps with the pass-2 GEMM;
   * when the operator exposes ``rayleigh`` the small matrix T = Q^T A Q is formed as a Gram matrix of the
     projected samples (one GEMM less, only an (m x m) allreduce); ``faithful=True`` forces T = (A Q)^T Q.
 """
 import numpy as np
 
 from . import _lib as K
-from .linalg import b_orthonormalize, top_k_eig
+import torch
+from scipy.linalg import blas as _blas
+
+from .linalg import b_orthonormalize, cleanup_factor, top_k_eig
 from .multivector import DeviceMultiVector
 
 
@@ -28,6 +33,61 @@ def _block_apply(A, X):
     return Y
 
 
+_side_streams = {}
+
+
+def _fetch_async(t):
+    """Start a device -> pinned-host copy of the small matrix ``t`` on a side stream; returns (host tensor, event).
+    The copy waits only for the work queued so far, so kernels launched afterwards overlap with it."""
+    dev = t.device
+    side = _side_streams.get(dev.index)
+    if side is None:
+        side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    ready = torch.cuda.Event()
+    ready.record()
+    host = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+    done = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        host.copy_(t, non_blocking=True)
+        done.record(side)
+    t.record_stream(side)
+    return host, done
+
+
+def _rayleigh_ritz(A, Q, BQ, k, gram, faithful):
+    """T = Q^T A Q, top-k eigenpairs, and the (m x k) coefficient matrix C with U = Q C.  ``gram`` is the device
+    Gram matrix of a basis whose clean-up pass was deferred (see linalg.b_orthonormalize)."""
+    if gram is not None:
+        G1h, done = _fetch_async(gram)
+    if hasattr(A, "rayleigh_device") and not faithful:
+        Td = A.rayleigh_device(Q, BQ)                          # big GEMM(s) queued: overlaps with the host work below
+        S2 = None
+        if gram is not None:
+            done.synchronize()
+            S2 = cleanup_factor(G1h.numpy())
+        T = Td.cpu().numpy()
+    elif hasattr(A, "rayleigh") and not faithful:
+        S2 = None
+        if gram is not None:
+            done.synchronize()
+            S2 = cleanup_factor(G1h.numpy())
+        T = A.rayleigh(Q, BQ)
+    else:
+        AQ = _block_apply(A, Q)
+        S2 = None
+        if gram is not None:
+            done.synchronize()
+            S2 = cleanup_factor(G1h.numpy())
+        T = AQ.dot_mv(Q)
+    if S2 is not None:
+        # small host products through SciPy's BLAS (the same OpenBLAS instance as the LAPACK calls: mixing in NumPy's
+        # own BLAS thread pool for 266 x 266 operands was measured to cost > 200 ms per product on these hosts)
+        T = _blas.dgemm(1.0, S2, _blas.dgemm(1.0, np.asarray(T), S2), trans_a=1)
+    d, V = top_k_eig(T, k)
+    return d, (V if S2 is None else _blas.dgemm(1.0, S2, V))
+
+
 def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     """d (k,) descending, U DeviceMultiVector (n, k) with U^T U = I."""
     nvec = Omega.nvec()
@@ -35,15 +95,10 @@ def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     Q = DeviceMultiVector(Omega)
     for _ in range(s):
         Q = _block_apply(A, Q)
-    Qt, _, oinfo = b_orthonormalize(Q.tensor(), None, return_BQ=False)
+    Qt, _, oinfo = b_orthonormalize(Q.tensor(), None, return_BQ=False, defer_last=True)
     Q = DeviceMultiVector(Qt)
-    if hasattr(A, "rayleigh") and not faithful:
-        T = A.rayleigh(Q, Q)
-    else:
-        AQ = _block_apply(A, Q)
-        T = AQ.dot_mv(Q)
-    d, V = top_k_eig(T, k)
-    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), K.to_padded(V, Q.tensor().device)))
+    d, C = _rayleigh_ritz(A, Q, Q, k, oinfo.pop("gram", None), faithful)
+    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), K.to_padded(C, Q.tensor().device)))
     if info is not None:
         info.update(oinfo)
     return d, U
@@ -65,15 +120,10 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None):
         else:
             Ybar = _block_apply(A, Q)
             Q = DeviceMultiVector(Binv.solve_block(Ybar.tensor()))
-    Qt, BQt, oinfo = b_orthonormalize(Q.tensor(), B, return_BQ=True)
+    Qt, BQt, oinfo = b_orthonormalize(Q.tensor(), B, return_BQ=True, defer_last=True)
     Q, BQ = DeviceMultiVector(Qt), DeviceMultiVector(BQt)
-    if hasattr(A, "rayleigh") and not faithful:
-        T = A.rayleigh(Q, BQ)
-    else:
-        AQ = _block_apply(A, Q)
-        T = AQ.dot_mv(Q)
-    d, V = top_k_eig(T, k)
-    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), K.to_padded(V, Q.tensor().device)))
+    d, C = _rayleigh_ritz(A, Q, BQ, k, oinfo.pop("gram", None), faithful)
+    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), K.to_padded(C, Q.tensor().device)))
     if info is not None:
         info.update(oinfo)
     return d, U
