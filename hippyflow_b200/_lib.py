@@ -50,6 +50,8 @@ def lib():
         "hfb_dgemm": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, vp, i64, vp, sz, i32, vp]),
         "hfb_dgemm_batched_small": (i32, [i32, i64, i64, i64, dbl, vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, vp]),
         "hfb_csr_spmm": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
+        "hfb_csr_spmm_ordered": (i32, [i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp]),
+        "hfb_csr_cluster_rows": (i32, [i64, vp, vp, i32, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -72,7 +74,8 @@ def lib():
 
 
 EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm",
-            "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
+            "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
+            "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
             "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
             "hfb_measure_dmma_peak"]
@@ -195,17 +198,34 @@ def dgemm_batched_small(layout, A, B, out, alpha=1.0):
     return out
 
 
-def csr_spmm(rowptr, colind, val, B, out=None):
+def csr_spmm(rowptr, colind, val, B, out=None, order=None):
     L = lib()
     _req(B, "B")
     n, m = B.shape
     if out is None:
         out = padded_empty(n, m, B.device)
     nrows = rowptr.numel() - 1
-    rc = L.hfb_csr_spmm(nrows, m, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), _ld(B),
-                        out.data_ptr(), _ld(out), _stream())
+    if order is not None:
+        rc = L.hfb_csr_spmm_ordered(nrows, m, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), order.data_ptr(),
+                                    B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    else:
+        rc = L.hfb_csr_spmm(nrows, m, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), _ld(B),
+                            out.data_ptr(), _ld(out), _stream())
     _check(rc, "hfb_csr_spmm")
     return out
+
+
+def csr_cluster_rows(indptr, indices, cluster=64):
+    """Host preprocessing: NumPy int32 CSR arrays -> int32 permutation grouping neighbouring rows (hfb_csr_cluster_rows)."""
+    import numpy as np
+    L = lib()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    n = indptr.size - 1
+    order = np.empty(n, dtype=np.int32)
+    rc = L.hfb_csr_cluster_rows(n, indptr.ctypes.data, indices.ctypes.data, int(cluster), order.ctypes.data)
+    _check(rc, "hfb_csr_cluster_rows")
+    return order
 
 
 def csr_spmm_rows(rowptr, colind, val, X, out=None):

@@ -71,21 +71,26 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(long long nrows, int m, c
 // which leaves three dependent memory latencies per row instead of 2*nnz.
 constexpr int SPMM_WARPS = 16;
 constexpr int SPMM_ROWS_PER_CTA = 64;
+template <int CH>
 __global__ void __launch_bounds__(SPMM_WARPS * 32) csr_spmm_panel_kernel(long long nrows, int m, const int* __restrict__ rowptr,
                                                                         const int* __restrict__ colind,
                                                                         const double* __restrict__ val,
                                                                         const double* __restrict__ B, long long ldb,
-                                                                        double* __restrict__ C, long long ldc, int vec_ok) {
+                                                                        double* __restrict__ C, long long ldc, int vec_ok,
+                                                                        const int* __restrict__ order) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.y * 64 + 2 * lane;
-    const bool in0 = c < m, in1 = c + 1 < m;
+    const int c0 = blockIdx.y * (64 * CH) + 2 * lane;  // this lane's columns: c0 + 64*i + {0, 1}
     const long long row_base = (long long)blockIdx.x * SPMM_ROWS_PER_CTA;
 #pragma unroll 1
     for (int i = 0; i < SPMM_ROWS_PER_CTA / SPMM_WARPS; ++i) {
-        const long long row = row_base + i * SPMM_WARPS + warp;
-        if (row >= nrows) break;
+        const long long slot = row_base + i * SPMM_WARPS + warp;
+        if (slot >= nrows) break;
+        // `order` groups mesh-neighbouring rows into one CTA (hfb_csr_cluster_rows) so their B rows overlap in L1
+        const long long row = order ? (long long)__ldg(order + slot) : slot;
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        double2 acc = make_double2(0.0, 0.0);
+        double2 acc[CH];
+#pragma unroll
+        for (int h = 0; h < CH; ++h) acc[h] = make_double2(0.0, 0.0);
         for (int base = beg; base < end; base += 32) {
             const int cnt = min(32, end - base);
             int my_col = 0;
@@ -98,25 +103,53 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) csr_spmm_panel_kernel(long lo
             for (int j = 0; j < cnt; ++j) {
                 const int col = __shfl_sync(0xffffffffu, my_col, j);
                 const double v = __shfl_sync(0xffffffffu, my_val, j);
-                const double* bp = B + (long long)col * ldb + c;
-                if (vec_ok && in1) {
-                    const double2 b = *reinterpret_cast<const double2*>(bp);
-                    acc.x = fma(v, b.x, acc.x);
-                    acc.y = fma(v, b.y, acc.y);
-                } else {
-                    if (in0) acc.x = fma(v, bp[0], acc.x);
-                    if (in1) acc.y = fma(v, bp[1], acc.y);
+                const double* bp = B + (long long)col * ldb + c0;
+#pragma unroll
+                for (int h = 0; h < CH; ++h) {
+                    const int c = c0 + 64 * h;
+                    if (vec_ok && c + 1 < m) {
+                        const double2 b = *reinterpret_cast<const double2*>(bp + 64 * h);
+                        acc[h].x = fma(v, b.x, acc[h].x);
+                        acc[h].y = fma(v, b.y, acc[h].y);
+                    } else {
+                        if (c < m) acc[h].x = fma(v, bp[64 * h], acc[h].x);
+                        if (c + 1 < m) acc[h].y = fma(v, bp[64 * h + 1], acc[h].y);
+                    }
                 }
             }
         }
-        double* cp = C + row * ldc + c;
-        if (vec_ok && in1) {
-            *reinterpret_cast<double2*>(cp) = acc;
-        } else {
-            if (in0) cp[0] = acc.x;
-            if (in1) cp[1] = acc.y;
+        double* cp = C + row * ldc + c0;
+#pragma unroll
+        for (int h = 0; h < CH; ++h) {
+            const int c = c0 + 64 * h;
+            if (vec_ok && c + 1 < m) {
+                *reinterpret_cast<double2*>(cp + 64 * h) = acc[h];
+            } else {
+                if (c < m) cp[64 * h] = acc[h].x;
+                if (c + 1 < m) cp[64 * h + 1] = acc[h].y;
+            }
         }
     }
+}
+
+static int launch_spmm_panel(long long nrows, int m, const int* rowptr, const int* colind, const double* val, const double* B,
+                             long long ldb, double* C, long long ldc, int vec_ok, const int* order, cudaStream_t stream) {
+    const long long bx = (nrows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA;
+    if (bx > 0x7fffffffLL) return HFB_E_UNSUPPORTED;
+    static const int ch_env = getenv("HFB_SPMM_CH") ? atoi(getenv("HFB_SPMM_CH")) : 0;
+    const int ch = ch_env ? ch_env : 1;  // measured on B200: 64-column panels win (0.49 ms vs 0.54 / 0.75 for 128 / 256)
+    if (ch == 2) {
+        dim3 grid((unsigned)bx, (unsigned)((m + 127) / 128));
+        csr_spmm_panel_kernel<2><<<grid, SPMM_WARPS * 32, 0, stream>>>(nrows, m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, order);
+    } else if (ch == 4) {
+        dim3 grid((unsigned)bx, (unsigned)((m + 255) / 256));
+        csr_spmm_panel_kernel<4><<<grid, SPMM_WARPS * 32, 0, stream>>>(nrows, m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, order);
+    } else {
+        dim3 grid((unsigned)bx, (unsigned)((m + 63) / 64));
+        csr_spmm_panel_kernel<1><<<grid, SPMM_WARPS * 32, 0, stream>>>(nrows, m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, order);
+    }
+    ++g_launch_count;
+    return (int)cudaGetLastError();
 }
 
 // Sparse matrix applied to sample-major data: C[s, r] = sum_j val[j] X[s, col[j]], j in row r.
@@ -423,12 +456,7 @@ extern "C" int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, con
                            : 0;
     static const bool use_v1 = (getenv("HFB_SPMM_V1") != nullptr);
     if (!use_v1) {
-        const long long bx = (nrows + SPMM_ROWS_PER_CTA - 1) / SPMM_ROWS_PER_CTA;
-        if (bx > 0x7fffffffLL) return HFB_E_UNSUPPORTED;
-        dim3 grid((unsigned)bx, (unsigned)((m + 63) / 64));
-        csr_spmm_panel_kernel<<<grid, SPMM_WARPS * 32, 0, stream>>>(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok);
-        HFB_LAUNCHED();
-        return (int)cudaGetLastError();
+        return launch_spmm_panel(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, nullptr, stream);
     }
     const int ch = (int)((m + 63) / 64);
     long long blocks = (nrows + 7) / 8;  // 8 warps (rows) per CTA
@@ -446,6 +474,90 @@ extern "C" int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, con
 #undef SPMM_CASE
     HFB_LAUNCHED();
     return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind,
+                                    const double* val, const int32_t* order, const double* B, int64_t ldb, double* C,
+                                    int64_t ldc, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nrows <= 0 || m <= 0 || !rowptr || !colind || !val || !order || !B || !C || ldb < m || ldc < m || B == C)
+        return HFB_E_BADARG;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(B) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                        (ldb & 1) == 0 && (ldc & 1) == 0)
+                           ? 1
+                           : 0;
+    return launch_spmm_panel(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, order, stream);
+}
+
+// Host-side preprocessing (HOST pointers): group the rows of a sparse matrix with symmetric pattern into clusters of
+// `cluster` graph-neighbouring rows by greedy breadth-first growth; order_out is a permutation of 0..n-1 whose
+// consecutive runs of `cluster` entries are the clusters.  O(nnz).
+extern "C" int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t cluster,
+                                    int32_t* order_out) {
+    if (n <= 0 || !rowptr || !colind || !order_out || cluster <= 0) return HFB_E_BADARG;
+    int32_t* queue = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    unsigned char* state = (unsigned char*)calloc((size_t)n, 1);  // 0 free, 1 queued in the current cluster, 2 assigned
+    if (!queue || !state) {
+        free(queue);
+        free(state);
+        return HFB_E_WORKSPACE;
+    }
+    int64_t out = 0, seed_scan = 0;
+    // frontier carried over between clusters so that the next cluster starts next to the previous one
+    int64_t carry_head = 0, carry_tail = 0;
+    int32_t* carry = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    if (!carry) {
+        free(queue);
+        free(state);
+        return HFB_E_WORKSPACE;
+    }
+    while (out < n) {
+        int32_t seed = -1;
+        while (carry_head < carry_tail) {
+            const int32_t cnd = carry[carry_head++];
+            if (state[cnd] != 2) {
+                seed = cnd;
+                break;
+            }
+        }
+        if (seed < 0) {
+            while (seed_scan < n && state[seed_scan] == 2) ++seed_scan;
+            if (seed_scan >= n) break;
+            seed = (int32_t)seed_scan;
+        }
+        int64_t head = 0, tail = 0, taken = 0;
+        queue[tail++] = seed;
+        state[seed] = 1;
+        while (head < tail && taken < cluster) {
+            const int32_t r = queue[head++];
+            state[r] = 2;
+            order_out[out++] = r;
+            ++taken;
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+                const int32_t c = colind[j];
+                if (c >= 0 && c < n && state[c] == 0) {
+                    state[c] = 1;
+                    queue[tail++] = c;
+                }
+            }
+        }
+        // rows queued but not taken go back to "free" and seed the following clusters
+        for (int64_t q = head; q < tail; ++q) {
+            state[queue[q]] = 0;
+            if (carry_tail < n) carry[carry_tail++] = queue[q];
+        }
+        if (carry_tail >= n - 1 && carry_head > 0) {  // compact the carry list
+            int64_t w = 0;
+            for (int64_t q = carry_head; q < carry_tail; ++q)
+                if (state[carry[q]] != 2) carry[w++] = carry[q];
+            carry_head = 0;
+            carry_tail = w;
+        }
+    }
+    free(queue);
+    free(state);
+    free(carry);
+    return out == n ? 0 : HFB_E_BADARG;
 }
 
 extern "C" int hfb_csr_spmm_rows(int64_t nsamples, int64_t n, const int32_t* rowptr, const int32_t* colind,

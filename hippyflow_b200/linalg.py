@@ -22,7 +22,7 @@ class CsrMatrix:
     """Sparse SPD weight matrix (mass matrix M, prior precision R) resident on the device as int32 CSR,
     the format the reference exports (PODProjector.py:695-697)."""
 
-    def __init__(self, M_csr, device):
+    def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
         M.sort_indices()
         self.shape = M.shape
@@ -31,10 +31,14 @@ class CsrMatrix:
         self.rowptr = torch.as_tensor(np.asarray(M.indptr, dtype=np.int32), device=device)
         self.colind = torch.as_tensor(np.asarray(M.indices, dtype=np.int32), device=device)
         self.val = torch.as_tensor(np.asarray(M.data, dtype=np.float64), device=device)
+        # row schedule: clusters of 64 mesh-neighbouring rows per CTA (L1 reuse of the dense rows they share)
+        self.order = None
+        if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
+            self.order = torch.as_tensor(K.csr_cluster_rows(M.indptr, M.indices, 64), device=device)
 
     def matmat(self, B, out=None):
         """out (n, m) = M @ B for a dense row-major (n, m) block."""
-        return K.csr_spmm(self.rowptr, self.colind, self.val, B, out)
+        return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order)
 
     def matmat_rows(self, X, out=None):
         """out (N, n): row i = M @ X[i]  (= (M X^T)^T for sample-major X)."""

@@ -84,6 +84,14 @@ int hfb_dgemm_batched_small(int layout, int64_t M, int64_t N, int64_t K, double 
 int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind,
                  const double* val, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
+/* Same product with the rows visited in the order `order` (device int32 permutation of 0..nrows-1, from
+ * hfb_csr_cluster_rows): a CTA then owns 64 mesh-neighbouring rows whose B rows overlap, so most B reads hit in L1. */
+int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind, const double* val,
+                         const int32_t* order, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+/* HOST function (host pointers, no CUDA call): greedy breadth-first clustering of the rows of a CSR matrix with
+ * symmetric pattern into groups of `cluster` neighbouring rows; writes a permutation of 0..n-1. O(nnz). */
+int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t cluster, int32_t* order_out);
+
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.
  * (M X)^T for symmetric M with X stored as u_data (N, n)  (PODProjector.py:750, 818).
