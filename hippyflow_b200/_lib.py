@@ -52,6 +52,8 @@ def lib():
         "hfb_csr_spmm": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_ordered": (i32, [i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_csr_cluster_rows": (i32, [i64, vp, vp, i32, vp]),
+        "hfb_csr_cluster_rows_capped": (i32, [i64, vp, vp, i32, i32, vp, vp, ctypes.POINTER(ctypes.c_int64)]),
+        "hfb_csr_spmm_staged": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -75,6 +77,7 @@ def lib():
 
 EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
+            "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
             "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -212,6 +215,37 @@ def csr_spmm(rowptr, colind, val, B, out=None, order=None):
         rc = L.hfb_csr_spmm(nrows, m, rowptr.data_ptr(), colind.data_ptr(), val.data_ptr(), B.data_ptr(), _ld(B),
                             out.data_ptr(), _ld(out), _stream())
     _check(rc, "hfb_csr_spmm")
+    return out
+
+
+def csr_cluster_rows_capped(indptr, indices, max_rows=64, max_cols=128):
+    """Host preprocessing for the staged SpMM: (order, cluster_ptr) as NumPy int32 arrays."""
+    import numpy as np
+    L = lib()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    n = indptr.size - 1
+    order = np.empty(n, dtype=np.int32)
+    cptr = np.empty(n + 1, dtype=np.int32)
+    ncl = ctypes.c_int64(0)
+    rc = L.hfb_csr_cluster_rows_capped(n, indptr.ctypes.data, indices.ctypes.data, int(max_rows), int(max_cols),
+                                       order.ctypes.data, cptr.ctypes.data, ctypes.byref(ncl))
+    _check(rc, "hfb_csr_cluster_rows_capped")
+    return order, cptr[:ncl.value + 1].copy()
+
+
+def csr_spmm_staged(plan, B, out=None):
+    """C = M @ B with the cluster-staged kernel; ``plan`` is the dict built by linalg.CsrMatrix._build_plan."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_staged(plan["nclusters"], m, plan["cl_rowptr"].data_ptr(), plan["order"].data_ptr(),
+                               plan["s_rowptr"].data_ptr(), plan["entries"].data_ptr(), plan["cl_colptr"].data_ptr(),
+                               plan["cl_cols"].data_ptr(), plan["max_cols"], plan["max_entries"], B.data_ptr(), _ld(B),
+                               out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_staged")
     return out
 
 

@@ -152,6 +152,89 @@ static int launch_spmm_panel(long long nrows, int m, const int* rowptr, const in
     return (int)cudaGetLastError();
 }
 
+// v3: cluster-staged SpMM.  A CTA owns one cluster of <= 64 mesh-neighbouring rows (hfb_csr_cluster_rows_capped) and one
+// 64-column panel: the <= max_cols DISTINCT rows of B the cluster touches are copied once into shared memory with
+// cp.async (512 contiguous bytes per row), then every row of the cluster is a sequence of conflict-free LDS.128 + DFMA
+// against cluster-local column indices.  B is read ~1.7x from L2 (halo overlap between clusters) instead of ~7x.
+constexpr int SPMM_STAGED_WARPS = 8;
+struct __align__(16) SpmmEntry {  // one matrix entry in cluster order: value + cluster-local column index
+    double v;
+    long long l;
+};
+__global__ void __launch_bounds__(SPMM_STAGED_WARPS * 32) csr_spmm_staged_kernel(
+    int m, int max_cols, int max_entries, const int* __restrict__ cl_rowptr, const int* __restrict__ order,
+    const int* __restrict__ s_rowptr, const SpmmEntry* __restrict__ ent, const int* __restrict__ cl_colptr,
+    const int* __restrict__ cl_cols, const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc) {
+    // shared memory: two B-panel buffers [max_cols][64] (double-buffered over the column panels), the cluster's matrix
+    // entries, its distinct-column list and the entry offsets of its rows
+    extern __shared__ __align__(16) unsigned char smem_spmm[];
+    double* sB0 = reinterpret_cast<double*>(smem_spmm);
+    double* sB1 = sB0 + (size_t)max_cols * 64;
+    SpmmEntry* sE = reinterpret_cast<SpmmEntry*>(sB1 + (size_t)max_cols * 64);
+    int* sCols = reinterpret_cast<int*>(sE + max_entries);
+    int* sRow = sCols + max_cols;  // [rows + 1] offsets relative to the cluster's first entry
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cluster = blockIdx.x;
+    const int col_beg = __ldg(cl_colptr + cluster), ncol = __ldg(cl_colptr + cluster + 1) - col_beg;
+    const int slot_beg = __ldg(cl_rowptr + cluster), nrow = __ldg(cl_rowptr + cluster + 1) - slot_beg;
+    const int e_beg = __ldg(s_rowptr + slot_beg);
+    const int nent = __ldg(s_rowptr + slot_beg + nrow) - e_beg;
+    for (int e = threadIdx.x; e < nent; e += SPMM_STAGED_WARPS * 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sE + e)), "l"(ent + e_beg + e) : "memory");
+    for (int j = threadIdx.x; j < ncol; j += SPMM_STAGED_WARPS * 32) sCols[j] = __ldg(cl_cols + col_beg + j);
+    for (int r = threadIdx.x; r <= nrow; r += SPMM_STAGED_WARPS * 32) sRow[r] = __ldg(s_rowptr + slot_beg + r) - e_beg;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    __syncthreads();  // sCols visible before the first panel is staged
+
+    const int npanel = (m + 63) / 64;
+    auto stage = [&](int panel, double* buf) {
+        const int c = panel * 64 + 2 * lane;
+#pragma unroll 4
+        for (int j = warp; j < ncol; j += SPMM_STAGED_WARPS) {
+            const double* src = B + (long long)sCols[j] * ldb + c;
+            double* dst = buf + j * 64 + 2 * lane;
+            if (c + 1 < m) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+            } else if (c < m) {
+                dst[0] = src[0];
+                dst[1] = 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, sB0);
+    for (int panel = 0; panel < npanel; ++panel) {
+        double* cur = (panel & 1) ? sB1 : sB0;
+        if (panel + 1 < npanel) {
+            stage(panel + 1, (panel & 1) ? sB0 : sB1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int c = panel * 64 + 2 * lane;
+        const double* sBl = cur + 2 * lane;
+        for (int r = warp; r < nrow; r += SPMM_STAGED_WARPS) {
+            const int beg = sRow[r], end = sRow[r + 1];
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+            for (int j = beg; j < end; ++j) {
+                const SpmmEntry en = sE[j];  // same address in all lanes: one broadcast LDS.128
+                const double2 b = *reinterpret_cast<const double2*>(sBl + en.l * 64);
+                acc.x = fma(en.v, b.x, acc.x);
+                acc.y = fma(en.v, b.y, acc.y);
+            }
+            double* cp = C + (long long)__ldg(order + slot_beg + r) * ldc + c;
+            if (c + 1 < m) {
+                *reinterpret_cast<double2*>(cp) = acc;
+            } else if (c < m) {
+                cp[0] = acc.x;
+            }
+        }
+        __syncthreads();  // everyone is done with `cur` before it is refilled two panels later
+    }
+}
+
 // Sparse matrix applied to sample-major data: C[s, r] = sum_j val[j] X[s, col[j]], j in row r.
 // Thread = matrix row r (consecutive threads -> consecutive r -> near-contiguous gathers from a sample
 // row); a CTA reuses each CSR entry for SB samples held in registers.
@@ -558,6 +641,106 @@ extern "C" int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int3
     free(state);
     free(carry);
     return out == n ? 0 : HFB_E_BADARG;
+}
+
+// Same greedy growth with a cap on the number of DISTINCT columns a cluster may touch (the shared-memory budget of
+// csr_spmm_staged_kernel).  cluster_ptr_out (n+1 entries allocated by the caller) receives the slot boundaries of
+// the clusters, *nclusters_out their number.
+extern "C" int hfb_csr_cluster_rows_capped(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t max_rows,
+                                           int32_t max_cols, int32_t* order_out, int32_t* cluster_ptr_out,
+                                           int64_t* nclusters_out) {
+    if (n <= 0 || !rowptr || !colind || !order_out || !cluster_ptr_out || !nclusters_out || max_rows <= 0 || max_cols <= 0)
+        return HFB_E_BADARG;
+    int32_t* queue = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* carry = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* stamp = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);   // cluster id that last touched a column
+    unsigned char* state = (unsigned char*)calloc((size_t)n, 1);
+    if (!queue || !carry || !stamp || !state) {
+        free(queue); free(carry); free(stamp); free(state);
+        return HFB_E_WORKSPACE;
+    }
+    for (int64_t i = 0; i < n; ++i) stamp[i] = -1;
+    int64_t out = 0, seed_scan = 0, carry_head = 0, carry_tail = 0, ncl = 0;
+    cluster_ptr_out[0] = 0;
+    int rc = 0;
+    while (out < n) {
+        int32_t seed = -1;
+        while (carry_head < carry_tail) {
+            const int32_t cnd = carry[carry_head++];
+            if (state[cnd] != 2) { seed = cnd; break; }
+        }
+        if (seed < 0) {
+            while (seed_scan < n && state[seed_scan] == 2) ++seed_scan;
+            if (seed_scan >= n) break;
+            seed = (int32_t)seed_scan;
+        }
+        int64_t head = 0, tail = 0;
+        int32_t taken = 0, ncols = 0;
+        queue[tail++] = seed;
+        state[seed] = 1;
+        while (head < tail && taken < max_rows) {
+            const int32_t r = queue[head];
+            int32_t fresh = 0;
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+                const int32_t c = colind[j];
+                if (c < 0 || c >= n) { rc = HFB_E_BADARG; goto done; }
+                if (stamp[c] != (int32_t)ncl) ++fresh;   // duplicates inside a row are counted twice: harmless upper bound
+            }
+            if (taken > 0 && ncols + fresh > max_cols) break;            // cluster full (column budget)
+            if (taken == 0 && fresh > max_cols) { rc = HFB_E_UNSUPPORTED; goto done; }  // a single row exceeds the budget
+            ++head;
+            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+                const int32_t c = colind[j];
+                if (stamp[c] != (int32_t)ncl) { stamp[c] = (int32_t)ncl; ++ncols; }
+                if (state[c] == 0) { state[c] = 1; queue[tail++] = c; }
+            }
+            state[r] = 2;
+            order_out[out++] = r;
+            ++taken;
+        }
+        for (int64_t q = head; q < tail; ++q) {
+            state[queue[q]] = 0;
+            if (carry_tail < n) carry[carry_tail++] = queue[q];
+        }
+        if (carry_tail >= n - 1 && carry_head > 0) {
+            int64_t w = 0;
+            for (int64_t q = carry_head; q < carry_tail; ++q)
+                if (state[carry[q]] != 2) carry[w++] = carry[q];
+            carry_head = 0;
+            carry_tail = w;
+        }
+        cluster_ptr_out[++ncl] = (int32_t)out;
+    }
+    *nclusters_out = ncl;
+    if (out != n) rc = HFB_E_BADARG;
+done:
+    free(queue); free(carry); free(stamp); free(state);
+    return rc;
+}
+
+extern "C" int hfb_csr_spmm_staged(int64_t nclusters, int64_t m, const int32_t* cl_rowptr, const int32_t* order,
+                                   const int32_t* s_rowptr, const void* entries, const int32_t* cl_colptr,
+                                   const int32_t* cl_cols, int32_t max_cols, int32_t max_entries, const double* B,
+                                   int64_t ldb, double* C, int64_t ldc, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nclusters <= 0 || m <= 0 || !cl_rowptr || !order || !s_rowptr || !entries || !cl_colptr || !cl_cols || !B || !C ||
+        ldb < m || ldc < m || B == C || max_cols <= 0 || max_cols > 256 || max_entries <= 0 || max_entries > 4096)
+        return HFB_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(entries) & 15) return HFB_E_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15) || (ldb & 1) || (ldc & 1)) return HFB_E_ALIGN;
+    if (nclusters > 0x7fffffffLL) return HFB_E_UNSUPPORTED;
+    const size_t smem = 2 * (size_t)max_cols * 64 * 8 + (size_t)max_entries * sizeof(SpmmEntry) + (size_t)max_cols * 4 + 65 * 4 + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(csr_spmm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    csr_spmm_staged_kernel<<<(unsigned)nclusters, SPMM_STAGED_WARPS * 32, smem, stream>>>((int)m, (int)max_cols, (int)max_entries, cl_rowptr, order, s_rowptr,
+                                                                           (const SpmmEntry*)entries, cl_colptr, cl_cols, B,
+                                                                           ldb, C, ldc);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
 }
 
 extern "C" int hfb_csr_spmm_rows(int64_t nsamples, int64_t n, const int32_t* rowptr, const int32_t* colind,

@@ -31,13 +31,57 @@ class CsrMatrix:
         self.rowptr = torch.as_tensor(np.asarray(M.indptr, dtype=np.int32), device=device)
         self.colind = torch.as_tensor(np.asarray(M.indices, dtype=np.int32), device=device)
         self.val = torch.as_tensor(np.asarray(M.data, dtype=np.float64), device=device)
-        # row schedule: clusters of 64 mesh-neighbouring rows per CTA (L1 reuse of the dense rows they share)
+        # cluster-staged SpMM plan (one-time host preprocessing): clusters of <= 64 mesh-neighbouring rows whose distinct
+        # B rows (<= 128) are staged in shared memory by the kernel
         self.order = None
+        self.plan = None
         if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
-            self.order = torch.as_tensor(K.csr_cluster_rows(M.indptr, M.indices, 64), device=device)
+            try:
+                self.plan = self._build_plan(M, device)
+                self.order = self.plan["order"]      # the L1-panel kernel (narrow blocks) walks the same clusters
+            except K.HfbError:
+                self.plan = None          # e.g. a row with more entries than the column budget: the generic kernel handles it
+
+    @staticmethod
+    def _build_plan(M, device, max_rows=None, max_cols=None):
+        import os
+        # (32, 64) measured best on B200 (cfg2: 0.39 ms; (48, 96): 0.46 ms; (64, 128): 0.73 ms): smaller clusters keep
+        # three CTAs with double-buffered panels resident per SM
+        max_rows = int(os.environ.get("HFB_SPMM_ROWS", 32)) if max_rows is None else max_rows
+        max_cols = int(os.environ.get("HFB_SPMM_COLS", 64)) if max_cols is None else max_cols
+        indptr, indices, data = np.asarray(M.indptr, dtype=np.int64), np.asarray(M.indices, dtype=np.int64), np.asarray(M.data)
+        order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, max_rows, max_cols)
+        n = M.shape[0]
+        ncl = cptr.size - 1
+        counts = (indptr[1:] - indptr[:-1])[order]                       # nnz per row, cluster order
+        s_rowptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(counts, out=s_rowptr[1:])
+        # gather the entries in cluster order
+        src = np.repeat(indptr[:-1][order], counts) + (np.arange(s_rowptr[-1]) - np.repeat(s_rowptr[:-1], counts))
+        cols, vals = indices[src], data[src]
+        cl_of_slot = np.repeat(np.arange(ncl), np.diff(cptr))            # cluster id of every slot
+        cl_of_nnz = np.repeat(cl_of_slot, counts)
+        key = cl_of_nnz * n + cols
+        ukey, inv = np.unique(key, return_inverse=True)
+        ucl = ukey // n
+        cl_colptr = np.searchsorted(ucl, np.arange(ncl + 1)).astype(np.int64)
+        lcol = inv - cl_colptr[cl_of_nnz]
+        assert lcol.max() < max_cols and np.diff(cl_colptr).max() <= max_cols
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a.astype(dt)), device=device)
+        ent = np.empty((vals.size, 2), dtype=np.float64)                 # 16-byte {double value; int64 local column}
+        ent[:, 0] = vals
+        ent[:, 1] = lcol.astype(np.int64).view(np.float64)
+        max_entries = int(np.diff(s_rowptr[cptr]).max())
+        return {"nclusters": int(ncl), "max_cols": int(np.diff(cl_colptr).max()), "max_entries": max_entries,
+                "cl_rowptr": t(cptr, np.int32), "order": t(order, np.int32), "s_rowptr": t(s_rowptr, np.int32),
+                "entries": torch.as_tensor(ent, device=device), "cl_colptr": t(cl_colptr, np.int32),
+                "cl_cols": t(ukey % n, np.int32)}
 
     def matmat(self, B, out=None):
         """out (n, m) = M @ B for a dense row-major (n, m) block."""
+        if self.plan is not None and B.shape[1] >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
+                (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
+            return K.csr_spmm_staged(self.plan, B, out)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order)
 
     def matmat_rows(self, X, out=None):

@@ -92,6 +92,18 @@ int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const 
  * symmetric pattern into groups of `cluster` neighbouring rows; writes a permutation of 0..n-1. O(nnz). */
 int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t cluster, int32_t* order_out);
 
+/* Cluster-staged SpMM (the fast path): HOST preprocessing hfb_csr_cluster_rows_capped groups the rows into clusters of
+ * <= max_rows rows touching <= max_cols distinct columns; the caller then builds, in cluster order, the row offsets
+ * s_rowptr, the 16-byte entries {value, cluster-LOCAL column index} and the per-cluster distinct-column lists
+ * (cl_colptr, cl_cols) -- see hippyflow_b200/linalg.py:CsrMatrix._build_plan.  The kernel stages each cluster's distinct
+ * B rows in shared memory once (cp.async) and reads them with LDS.128.  B, C: 16-byte aligned, even ld. */
+int hfb_csr_cluster_rows_capped(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t max_rows, int32_t max_cols,
+                                int32_t* order_out, int32_t* cluster_ptr_out, int64_t* nclusters_out);
+int hfb_csr_spmm_staged(int64_t nclusters, int64_t m, const int32_t* cl_rowptr, const int32_t* order,
+                        const int32_t* s_rowptr, const void* entries /* {double value; int64 local column} per nnz */,
+                        const int32_t* cl_colptr, const int32_t* cl_cols, int32_t max_cols, int32_t max_entries,
+                        const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.
  * (M X)^T for symmetric M with X stored as u_data (N, n)  (PODProjector.py:750, 818).
