@@ -57,6 +57,7 @@ def lib():
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
+        "hfb_rowdot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp]),
         "hfb_colscale": (i32, [i64, i64, vp, i64, vp, vp]),
         "hfb_colmean_workspace_bytes": (sz, [i64, i64]),
         "hfb_colsum": (i32, [i64, i64, vp, i64, dbl, vp, vp, sz, vp]),
@@ -79,7 +80,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
-            "hfb_coldot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
+            "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
             "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
             "hfb_measure_dmma_peak"]
 
@@ -283,6 +284,16 @@ def coldot(X, Y):
     ws = workspace(nbytes, X.device)
     rc = L.hfb_coldot(n, m, X.data_ptr(), _ld(X), Y.data_ptr(), _ld(Y), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _check(rc, "hfb_coldot")
+    return out
+
+
+def rowdot(X, Y):
+    """out[i] = <X[i, :], Y[i, :]>."""
+    L = lib()
+    _req(X, "X"), _req(Y, "Y")
+    out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+    rc = L.hfb_rowdot(X.shape[0], X.shape[1], X.data_ptr(), _ld(X), Y.data_ptr(), _ld(Y), out.data_ptr(), _stream())
+    _check(rc, "hfb_rowdot")
     return out
 
 

@@ -313,6 +313,24 @@ static int reduce_parts(long long nrows, long long ncols) {
     return (int)want;
 }
 
+// out[r] = sum_c X[r,c] * Y[r,c]: one warp per row, fixed-order lane partial sums + shuffle tree (deterministic).
+__global__ void __launch_bounds__(256) rowdot_kernel(long long nrows, long long ncols, const double* __restrict__ X,
+                                                     long long ldx, const double* __restrict__ Y, long long ldy,
+                                                     double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp0; r < nrows; r += nwarps) {
+        const double* x = X + r * ldx;
+        const double* y = Y + r * ldy;
+        double s = 0.0;
+        for (long long c = lane; c < ncols; c += 32) s = fma(x[c], y[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[r] = s;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ elementwise
 __global__ void __launch_bounds__(256) colscale_kernel(long long n, long long m, double* __restrict__ X, long long ldx,
                                                        const double* __restrict__ s) {
@@ -792,6 +810,17 @@ extern "C" int hfb_colsum(int64_t N, int64_t n, const double* X, int64_t ldx, do
     colreduce_stage1<<<grid, 256, 0, stream>>>(N, n, X, ldx, nullptr, 0, rpb, (double*)workspace);
     HFB_LAUNCHED();
     colreduce_stage2<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, parts, (const double*)workspace, scale, out);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_rowdot(int64_t nrows, int64_t ncols, const double* X, int64_t ldx, const double* Y, int64_t ldy,
+                          double* out, void* stream_) {
+    if (nrows <= 0 || ncols <= 0 || !X || !Y || !out || ldx < ncols || ldy < ncols) return HFB_E_BADARG;
+    long long blocks = (nrows + 7) / 8;
+    const long long cap = 16LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    rowdot_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(nrows, ncols, X, ldx, Y, ldy, out);
     HFB_LAUNCHED();
     return (int)cudaGetLastError();
 }

@@ -5,3 +5,4 @@ from .activeSubspaceProjector import (ActiveSubspaceParameterList, ActiveSubspac
 from .operators import (JTJ, MeanJTJfromDataOperator, SampleCovarianceOperator, SandwichedCovarianceOperator,
                         SummedListOperator)
 from .projection import jacobian_action, jacobian_transpose_action, project_data, reduced_jacobians
+from .errors import PriorPreconditionedProjector, jacobian_truncated_svd, projection_errors

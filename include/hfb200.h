@@ -117,6 +117,11 @@ size_t hfb_coldot_workspace_bytes(int64_t n, int64_t m);
 int hfb_coldot(int64_t n, int64_t m, const double* X, int64_t ldx, const double* Y, int64_t ldy,
                double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* out[i] = sum_j X[i,j] * Y[i,j]  (i < nrows): per-sample inner products / squared norms, e.g. the relative projection
+ * errors of KLEProjector.test_errors (KLEProjector.py:262-270).  Deterministic. */
+int hfb_rowdot(int64_t nrows, int64_t ncols, const double* X, int64_t ldx, const double* Y, int64_t ldy, double* out,
+               void* stream);
+
 /* X[i,j] *= s[j]  (column scaling, e.g. phi / weighted_l2_norm_vector, PODProjector.py:829). */
 int hfb_colscale(int64_t n, int64_t m, double* X, int64_t ldx, const double* s, void* stream);
 

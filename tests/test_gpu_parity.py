@@ -375,3 +375,45 @@ def test_projector_files_written_with_reference_names(hf, cuda_device, tmp_path,
     U = np.load(out + "POD_projector.npy")
     np.testing.assert_allclose(np.load(out + "POD_d.npy"), golden_dp["d_pod"], rtol=EIG_RTOL)   # PODProjector.py:383-384
     assert U.shape == (289, 15)
+
+
+# ------------------------------------------------------------------ projection-error sweep and per-sample Jacobian SVD (8(f) ranks 2, 3)
+def test_projection_error_sweep_vs_numpy(hf, cuda_device):
+    rng = np.random.default_rng(4)
+    M = syn.p1_mass_matrix(10)
+    n = M.shape[0]
+    test = syn.snapshots(n, 37, r0=30, seed=8)
+    # an M-orthonormal basis and its encoder
+    A = rng.standard_normal((n, 20))
+    L = np.linalg.cholesky(A.T @ (M @ A))
+    V = np.linalg.solve(L, A.T).T
+    E = M @ V
+    ranks = [5, 1, 20, 12]
+    avg, std = hf.projection_errors(test, V, E, ranks, device=cuda_device)
+    for i, r in enumerate(sorted(ranks)):
+        rec = (test @ E[:, :r]) @ V[:, :r].T
+        rel = np.linalg.norm(test - rec, axis=1) / np.linalg.norm(test, axis=1)      # KLEProjector.py:262-270
+        np.testing.assert_allclose(avg[i], rel.mean(), rtol=1e-10)
+        np.testing.assert_allclose(std[i], rel.std(), rtol=1e-8, atol=1e-14)
+    assert np.all(np.diff(avg) <= 1e-12)
+    # PriorPreconditionedProjector.mult: y = U U^T C^-1 x   (priorPreconditionedProjector.py:48-55)
+    from hippyflow_b200.linalg import CsrMatrix
+    Pj = hf.PriorPreconditionedProjector(hf.DeviceMultiVector.from_dense(V, cuda_device), CsrMatrix(M, cuda_device))
+    X = hf.DeviceMultiVector.from_dense(test.T.copy(), cuda_device)
+    Y = hf.DeviceMultiVector(n, 37, device=cuda_device)
+    Pj.matMvMult(X, Y)
+    ref = V @ (V.T @ (M @ test.T))
+    assert np.linalg.norm(Y.to_dense() - ref) / np.linalg.norm(ref) < PROJ_RTOL
+
+
+def test_jacobian_truncated_svd_vs_numpy(hf, cuda_device, golden_jtj):
+    J = golden_jtj["J"][:6]                                          # (6, 100, 121)
+    U, s, V = hf.jacobian_truncated_svd(J, 10, cuda_device)
+    U, s, V = U.cpu().numpy(), s.cpu().numpy(), V.cpu().numpy()
+    for i in range(6):
+        u0, s0, vt0 = np.linalg.svd(J[i], full_matrices=False)
+        np.testing.assert_allclose(s[i], s0[:10], rtol=1e-9)
+        rec = (U[i] * s[i]) @ V[i].T
+        ref = (u0[:, :10] * s0[:10]) @ vt0[:10]
+        assert np.linalg.norm(rec - ref) / np.linalg.norm(ref) < 1e-8
+        np.testing.assert_allclose(V[i].T @ V[i], np.eye(10), atol=1e-8)
