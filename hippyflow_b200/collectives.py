@@ -208,6 +208,10 @@ class MatrixMultCollectiveOperator:
         self.collective = collective
         self.mpi_op = mpi_op
 
+    @property
+    def overwrites(self):
+        return getattr(self.local_op, "overwrites", False)
+
     def matMvMult(self, x, y):
         self.local_op.matMvMult(x, y)
         self.collective.allReduce(y, self.mpi_op)

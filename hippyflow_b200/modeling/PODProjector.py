@@ -59,7 +59,7 @@ def gaussian_omega(n, m, seed, device):
     """Gaussian test matrix (role of hp.parRandom.normal(1., Omega), PODProjector.py:367-372) generated on the
     device by the counter-based generator of hfb_fill_random: the same (seed, n, m) gives the same Omega on
     every rank.  Parity runs pass an explicit Omega instead so that oracle and GPU see identical values."""
-    Om = DeviceMultiVector(n, m, device=device)
+    Om = DeviceMultiVector(K.padded_empty(n, m, device))
     K.fill_random_(Om.tensor(), seed)
     return Om
 

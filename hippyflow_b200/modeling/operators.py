@@ -26,6 +26,8 @@ class SampleCovarianceOperator:
     'avg')`` (activeSubspaceProjector.py:427-431): local mean, then allReduce with mpi_op.  The averaging
     assumes every rank holds the same number of samples (comment at activeSubspaceProjector.py:429-430)."""
 
+    overwrites = True   # matMvMult writes every entry of Y (no caller-side zeroing needed)
+
     def __init__(self, cov, collective=None, mpi_op="avg"):
         self.cov = cov
         self.collective = collective if collective is not None else NullCollective()
@@ -65,6 +67,8 @@ class SandwichedCovarianceOperator:
     ``MassPreconditionedCovarianceOperator`` (KLEProjector.py:47-69, M C M) and ``H_matvec`` of the
     weighted POD (PODProjector.py:750-754, MX (MX)^T / N)."""
 
+    overwrites = True   # matMvMult writes every entry of Y (no caller-side zeroing needed)
+
     def __init__(self, C, B):
         self.C = C
         self.B = B
@@ -102,6 +106,8 @@ class MeanJTJfromDataOperator:
     """Drop-in for hippyflow/modeling/operatorWrappers.py:55-121: y = mean_i J_i^T [Gamma^-1] J_i x from a
     stored (ndata, r, dM) array.  The reference reads all of J twice per column through two einsums; here
     the array sits in HBM as the (ndata*r, dM) row-major matrix and a block of columns costs two GEMMs."""
+
+    overwrites = True   # matMvMult writes every entry of Y (no caller-side zeroing needed)
 
     def __init__(self, J, prior=None, noise_cov_inv=None, device=None, collective=None, mpi_op="avg"):
         assert len(J.shape) == 3
@@ -162,6 +168,8 @@ class MeanJTJfromDataOperator:
 class JTJ:
     """Gauss-Newton Hessian J^T J of ONE stored Jacobian (dQ, dM): the stored-data form of
     hippyflow/modeling/jacobian.py:142-166 (there every apply is an incremental forward and adjoint PDE solve)."""
+
+    overwrites = True   # matMvMult writes every entry of Y (no caller-side zeroing needed)
 
     def __init__(self, J, device=None):
         if device is None:

@@ -24,7 +24,11 @@ from .multivector import DeviceMultiVector
 
 
 def _block_apply(A, X):
-    Y = DeviceMultiVector(X.tensor().shape[0], X.nvec(), device=X.tensor().device)
+    if hasattr(A, "matMvMult") and getattr(A, "overwrites", False):
+        Y = DeviceMultiVector(K.padded_empty(X.tensor().shape[0], X.nvec(), X.tensor().device))   # fully overwritten
+        A.matMvMult(X, Y)
+        return Y
+    Y = DeviceMultiVector(X.tensor().shape[0], X.nvec(), device=X.tensor().device)   # zeroed: operators may accumulate into Y (activeSubspaceProjector.py:214-221)
     if hasattr(A, "matMvMult"):
         A.matMvMult(X, Y)
     else:  # hippylib MatMvMult fallback: column loop over A.mult
@@ -92,7 +96,7 @@ def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     """d (k,) descending, U DeviceMultiVector (n, k) with U^T U = I."""
     nvec = Omega.nvec()
     assert k <= nvec
-    Q = DeviceMultiVector(Omega)
+    Q = Omega                                   # not modified: every apply writes a fresh block
     for _ in range(s):
         Q = _block_apply(A, Q)
     Qt, _, oinfo = b_orthonormalize(Q.tensor(), None, return_BQ=False, defer_last=True)
@@ -111,10 +115,10 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None):
     Returns d (k,), U (n, k) with U^T B U = I."""
     nvec = Omega.nvec()
     assert k <= nvec
-    Q = DeviceMultiVector(Omega)
+    Q = Omega                                   # not modified: every apply writes a fresh block
     for _ in range(s):
         if hasattr(A, "solveB_matMvMult") and getattr(A, "B", None) is B and (Binv is None or not faithful):
-            Y = DeviceMultiVector(Q.tensor().shape[0], nvec, device=Q.tensor().device)
+            Y = DeviceMultiVector(K.padded_empty(Q.tensor().shape[0], nvec, Q.tensor().device))   # fully overwritten
             A.solveB_matMvMult(Q, Y)
             Q = Y
         else:
