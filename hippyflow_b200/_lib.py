@@ -48,6 +48,8 @@ def lib():
         "hfb_dgemm_workspace_bytes": (sz, [i32, i64, i64, i64, i32]),
         "hfb_dgemm_auto_splits": (i32, [i32, i64, i64, i64]),
         "hfb_dgemm": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, vp, i64, vp, sz, i32, vp]),
+        "hfb_dgemm_ex_workspace_bytes": (sz, [i32, i64, i64, i64, i32, i32]),
+        "hfb_dgemm_ex": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, vp, i64, vp, sz, i32, i32, vp]),
         "hfb_dgemm_batched_small": (i32, [i32, i64, i64, i64, dbl, vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, vp]),
         "hfb_csr_spmm": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_ordered": (i32, [i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp]),
@@ -76,7 +78,8 @@ def lib():
     return L
 
 
-EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm",
+EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm", "hfb_dgemm_ex",
+            "hfb_dgemm_ex_workspace_bytes",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
@@ -141,9 +144,10 @@ def to_padded(a, device, pad=16):
     return out
 
 
-def dgemm(layout, A, B, out=None, alpha=1.0, splits=0):
+def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False):
     """out[M,N] = alpha * op(A) op(B) on the DMMA/TMA kernel.  layout: HFB_NN (A MxK, B KxN),
-    HFB_TN (A KxM), HFB_NT (B NxK)."""
+    HFB_TN (A KxM), HFB_NT (B NxK).  symmetric=True: the caller asserts a symmetric result (Gram matrix); only the
+    tiles on or above the diagonal are computed, the rest is mirrored."""
     L = lib()
     _req(A, "A"), _req(B, "B")
     if layout == HFB_NN:
@@ -164,15 +168,16 @@ def dgemm(layout, A, B, out=None, alpha=1.0, splits=0):
     _req(out, "out")
     if tuple(out.shape) != (M, N):
         raise HfbError("dgemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
-    nbytes = L.hfb_dgemm_workspace_bytes(layout, M, N, K, splits)
+    flags = 1 if (symmetric and M == N) else 0
+    nbytes = L.hfb_dgemm_ex_workspace_bytes(layout, M, N, K, splits, flags)
     ws = workspace(nbytes, A.device) if nbytes else None
     if TIMING is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = L.hfb_dgemm(layout, M, N, K, float(alpha), A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
-                     ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, int(splits),
-                     _stream())
+    rc = L.hfb_dgemm_ex(layout, M, N, K, float(alpha), A.data_ptr(), _ld(A), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out),
+                        ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0, int(splits),
+                        flags, _stream())
     if TIMING is not None:
         e1.record()
         TIMING.append(((layout, M, N, K), e0, e1))

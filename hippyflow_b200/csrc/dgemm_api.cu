@@ -73,9 +73,16 @@ static int sm_count() {
     return n;
 }
 
-static int auto_splits(long long M, long long N, long long K) {
+static int auto_splits(long long M, long long N, long long K, int symmetric = 0) {
     const int nt = choose_nt(N);
-    const long long tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 8 * nt - 1) / (8 * nt));
+    long long tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 8 * nt - 1) / (8 * nt));
+    if (symmetric) {  // count the tiles that are actually computed
+        const long long mt = (M + GEMM_BM - 1) / GEMM_BM, ntl = (N + 8 * nt - 1) / (8 * nt);
+        tiles = 0;
+        for (long long i = 0; i < mt; ++i)
+            for (long long j = 0; j < ntl; ++j)
+                if (!(j * 8 * nt + 8 * nt <= i * GEMM_BM)) ++tiles;
+    }
     const long long kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int sms = sm_count();
     if (tiles >= 2LL * sms || kb < 64) return 1;
@@ -112,6 +119,23 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, long long sp
     }
 }
 
+// C[j][i] = C[i][j] for i < j: completes a symmetric result whose below-diagonal tiles were skipped.
+__global__ void mirror_upper_kernel(double* __restrict__ C, long long ldc, int N) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;  // tile (bi, bj) of the upper triangle, bj >= bi
+    if (bj < bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi * 32 + r, j = bj * 32 + tx;
+        tile[r][tx] = (i < N && j < N) ? C[(long long)i * ldc + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int j = bj * 32 + r, i = bi * 32 + tx;  // write C[j][i] = tile[i - bi*32][j - bj*32]
+        if (i < N && j < N && j > i) C[(long long)j * ldc + i] = tile[tx][r];
+    }
+}
+
 // per-layout launchers: dgemm_inst.cu compiled with -DHFB_GEMM_LAYOUT={0,1,2}
 int dgemm_launch_nn(int nt, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s);
 int dgemm_launch_tn(int nt, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s);
@@ -140,7 +164,23 @@ extern "C" size_t hfb_dgemm_workspace_bytes(int layout, int64_t M, int64_t N, in
 extern "C" int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                          const double* B, int64_t ldb, double* C, int64_t ldc, void* workspace, size_t workspace_bytes,
                          int splits, void* stream_) {
+    return hfb_dgemm_ex(layout, M, N, K, alpha, A, lda, B, ldb, C, ldc, workspace, workspace_bytes, splits, 0, stream_);
+}
+
+extern "C" size_t hfb_dgemm_ex_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int splits, int flags) {
+    if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0) return 0;
+    if (splits == 0) splits = auto_splits(M, N, K, (flags & HFB_GEMM_SYMMETRIC) && M == N);
+    if (splits <= 1) return 0;
+    const long long ldw = (N + 1) & ~1LL;
+    return (size_t)splits * (size_t)M * (size_t)ldw * 8;
+}
+
+extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                            const double* B, int64_t ldb, double* C, int64_t ldc, void* workspace,
+                            size_t workspace_bytes, int splits, int flags, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    const int symmetric = ((flags & HFB_GEMM_SYMMETRIC) && M == N) ? 1 : 0;
+    if ((flags & HFB_GEMM_SYMMETRIC) && M != N) return HFB_E_BADARG;
     if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || splits < 0) return HFB_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return HFB_E_BADARG;
     const long long a_inner = (layout == HFB_TN) ? M : K, a_outer = (layout == HFB_TN) ? K : M;
@@ -152,7 +192,7 @@ extern "C" int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alp
 
     const int nt = choose_nt(N);
     const long long kb_total = (K + GEMM_BK - 1) / GEMM_BK;
-    if (splits == 0) splits = auto_splits(M, N, K);
+    if (splits == 0) splits = auto_splits(M, N, K, symmetric);
     if (splits > kb_total) splits = (int)kb_total;
     if (splits < 1) splits = 1;
 
@@ -179,6 +219,7 @@ extern "C" int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alp
         p.split_stride = 0;
     }
     p.vec_store = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 1) == 0) ? 1 : 0;
+    p.symmetric = symmetric;
     if ((long long)p.m_tiles * p.n_tiles * p.splits > 0x7fffffffLL) return HFB_E_BADARG;
 
     CUtensorMap mapA, mapB;
@@ -201,6 +242,12 @@ extern "C" int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alp
         if (blocks > 148 * 16) blocks = 148 * 16;
         splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const double*)workspace, p.split_stride, splits, ldw,
                                                                   C, ldc, (int)M, (int)N, alpha);
+        ++g_launch_count;
+        rc = (int)cudaGetLastError();
+    }
+    if (rc == 0 && symmetric) {
+        const unsigned t = (unsigned)((N + 31) / 32);
+        mirror_upper_kernel<<<dim3(t, t), 256, 0, stream>>>(C, ldc, (int)N);
         ++g_launch_count;
         rc = (int)cudaGetLastError();
     }

@@ -43,6 +43,7 @@ struct GemmParams {
     long long ldc;         // leading dimension of C / workspace
     long long split_stride;  // elements between consecutive split slabs in the workspace
     int vec_store;         // 1 if C base is 16-byte aligned and ldc even (16-byte stores allowed)
+    int symmetric;         // 1: the result is symmetric (M == N); tiles strictly below the diagonal are skipped
 };
 
 template <int LAYOUT, int NT>
@@ -88,6 +89,7 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int kb_count = kb_base + (split < kb_rem ? 1 : 0);
     const int m0 = m_tile * GEMM_BM;
     const int n0 = n_tile * Cfg::BN;
+    if (p.symmetric && n0 + Cfg::BN <= m0) return;  // whole tile below the diagonal: filled by the mirror kernel
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {

@@ -154,7 +154,7 @@ class SampleCovariance:
         W, GW = self.project(B)
         if scale is None:
             scale = 1.0 / self.nsamples
-        return K.dgemm(K.HFB_TN, W, GW, alpha=scale)
+        return K.dgemm(K.HFB_TN, W, GW, alpha=scale, symmetric=True)
 
     def flops_apply(self, m):
         return 4.0 * self.rows * self.n * m
@@ -196,7 +196,7 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=Fals
     eye = np.eye(m)
     for it in range(max_passes):
         Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
-        G = _sym(K.dgemm(K.HFB_TN, Y, Z).cpu().numpy())
+        G = _sym(K.dgemm(K.HFB_TN, Y, Z, symmetric=True).cpu().numpy())
         d = np.sqrt(np.maximum(np.diag(G), 0.0))
         dead = d <= 0.0
         dinv = np.where(dead, 0.0, 1.0 / np.where(dead, 1.0, d))
@@ -230,7 +230,7 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=Fals
         info["passes"] += 1
         if defer_last and it == 0 and shift == 0.0 and cond * eps * m < 1e-4:
             Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
-            info["gram"] = K.dgemm(K.HFB_TN, Y, Z)                 # device (m x m); fetched by the caller, asynchronously
+            info["gram"] = K.dgemm(K.HFB_TN, Y, Z, symmetric=True)                 # device (m x m); fetched by the caller, asynchronously
             return Y, (Z if return_BQ else None), info
         if shift == 0.0 and it >= 1 and cond < 4.0:
             # the previous pass already left cond(G) ~ 1, so this pass is accurate to round-off

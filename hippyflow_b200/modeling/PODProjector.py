@@ -188,7 +188,7 @@ class PODProjectorFromData:
         if method != 'hep' and n_data > n:
             return self._dense_pencil_eig(Xt, Md, u_rank)
         Zt = Md.matmat_rows(Xt)                                   # (M X)^T, sample-major
-        G = K.dgemm(K.HFB_NT, Xt, Zt)                             # X^T M X  (N x N)
+        G = K.dgemm(K.HFB_NT, Xt, Zt, symmetric=True)             # X^T M X  (N x N): upper tiles + mirror
         del Zt
         Gs = 0.5 * (G + G.t())
         if n_data <= 1024:

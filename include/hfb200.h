@@ -60,6 +60,14 @@ int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alpha,
               const double* A, int64_t lda, const double* B, int64_t ldb,
               double* C, int64_t ldc, void* workspace, size_t workspace_bytes, int splits,
               void* stream);
+/* Same with flags.  HFB_GEMM_SYMMETRIC: the caller asserts that the (M == N) result is symmetric (Gram matrices
+ * X^T M X, Y^T B Y, W^T W); tiles strictly below the diagonal are not computed and are filled by a mirror kernel. */
+#define HFB_GEMM_SYMMETRIC 1
+size_t hfb_dgemm_ex_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int splits, int flags);
+int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb,
+                 double* C, int64_t ldc, void* workspace, size_t workspace_bytes, int splits, int flags,
+                 void* stream);
 /* The split count hfb_dgemm would choose for splits=0. */
 int hfb_dgemm_auto_splits(int layout, int64_t M, int64_t N, int64_t K);
 

@@ -144,3 +144,22 @@ def test_block_cg(K, cuda_device):
     Y = np.random.default_rng(5).standard_normal((M.shape[0], 9))
     X = CsrCGSolver(Md).solve_block(K.to_padded(Y, cuda_device)).cpu().numpy()
     assert np.linalg.norm(M @ X - Y) / np.linalg.norm(Y) < 1e-12
+
+
+@pytest.mark.parametrize("layout,n,kd", [(2, 300, 777), (1, 266, 5000), (2, 129, 64), (1, 138, 20000), (0, 256, 256)])
+def test_dgemm_symmetric_result_flag(K, cuda_device, layout, n, kd):
+    """HFB_GEMM_SYMMETRIC: only tiles on/above the diagonal are computed, the rest is mirrored."""
+    g = torch.Generator(device="cpu").manual_seed(n + kd)
+    X = torch.randn(n, kd, dtype=torch.float64, generator=g).to(cuda_device)
+    if layout == 2:        # X X^T
+        A, B, ref = K.to_padded(X, cuda_device), K.to_padded(X, cuda_device), X @ X.t()
+    elif layout == 1:      # (X^T)^T X^T = X X^T with A = B = X^T stored (kd, n)
+        Xt = K.to_padded(X.t().contiguous(), cuda_device)
+        A, B, ref = Xt, Xt, X @ X.t()
+    else:                  # NN with a symmetric product: S S (S symmetric)
+        S = X[:, :n] + X[:, :n].t()
+        A, B, ref = K.to_padded(S, cuda_device), K.to_padded(S, cuda_device), S @ S
+    for splits in (0, 1, 4):
+        C = K.dgemm(layout, A, B, symmetric=True, splits=splits)
+        assert float((C - ref).norm() / ref.norm()) < 1e-13
+        assert torch.equal(C, C.t())
