@@ -148,6 +148,20 @@ class SampleCovariance:
             scale = 1.0 / self.nsamples
         return K.dgemm(K.HFB_TN, self.Xt, GW, out=out, alpha=scale)
 
+    def lift(self, W, out=None, scale=None):
+        """out (n, m) = scale * Xt^T [G] W for an already computed projection W = Xt B (second half of ``apply``)."""
+        GW = W
+        if self.noise_cov_inv is not None:
+            q, m = self.block, W.shape[1]
+            GWb = K.padded_empty(self.rows, m, self.Xt.device)
+            K.dgemm_batched_small(K.HFB_NN, self.noise_cov_inv.unsqueeze(0),
+                                  W.as_strided((self.nsamples, q, m), (q * W.stride(0), W.stride(0), 1)),
+                                  GWb.as_strided((self.nsamples, q, m), (q * GWb.stride(0), GWb.stride(0), 1)))
+            GW = GWb
+        if scale is None:
+            scale = 1.0 / self.nsamples
+        return K.dgemm(K.HFB_TN, self.Xt, GW, out=out, alpha=scale)
+
     def gram_T(self, B, scale=None):
         """T_local (m, m) = scale * (Xt B)^T G (Xt B): the Rayleigh quotient B^T C B without forming C B
         (SURVEY.md 7 'T = Q^T A Q shortcut')."""

@@ -64,6 +64,16 @@ def gaussian_omega(n, m, seed, device):
     return Om
 
 
+_copy_streams = {}
+
+
+def _copy_stream(dev):
+    st = _copy_streams.get(dev.index)
+    if st is None:
+        st = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def to_host(t):
     """Device block -> NumPy array through a pinned staging tensor (torch's caching host allocator reuses the
     pinned blocks once earlier results are garbage-collected)."""
@@ -102,7 +112,7 @@ class PODProjectorFromData:
 
     def construct_subspace(self, u_data, u_rank, shifted=True, method='hep', verify=False,
                            oversampling=10, Omega=None, collective=None, return_device=False, faithful=False,
-                           overwrite_data=False):
+                           overwrite_data=False, pipelined_upload=True):
         """Same contract as PODProjector.py:699-852: returns (d, phi, Mphi, u_shift) as NumPy arrays of shape
         (r,), (n, r), (n, r), (n,).  ``u_data`` may be a NumPy array or a float64 CUDA tensor (rows = samples;
         with a collective, the local shard).  Extra keywords (randomized method only): ``oversampling``,
@@ -118,8 +128,17 @@ class PODProjectorFromData:
         Md = self.M_device
         t0 = time.time()
         owns = not (isinstance(u_data, torch.Tensor) and u_data.is_cuda)
-        Xt = _as_device_rows(u_data, dev)
-        if shifted:
+        first_W = None
+        if owns and method == 'randomized' and pipelined_upload:
+            # host input: stream the snapshots to the device in row chunks and overlap the upload with the sample mean
+            # and the first projection W = X (M Omega)
+            Omega = self._resolve_omega(Omega, dim_u, u_rank + oversampling)
+            Xt, first_W, u_shift_d = self._upload_pipelined(u_data, Md, Omega, shifted, collective)
+        else:
+            Xt = _as_device_rows(u_data, dev)
+        if first_W is not None:
+            pass
+        elif shifted:
             # u_shift = mean over ALL samples (np.mean(u_data, axis=0), PODProjector.py:733), then X - shift
             u_shift_d = K.colsum(Xt, 1.0 / n_data)
             collective.allReduce(u_shift_d, 'avg')
@@ -134,7 +153,7 @@ class PODProjectorFromData:
 
         t1 = time.time()
         if method == 'randomized':
-            d, phi_d, Mphi_d = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful)
+            d, phi_d, Mphi_d = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, first_W)
         else:
             if collective.size() != 1:
                 raise NotImplementedError("method='%s' is serial like the reference (PODProjector.py:683); "
@@ -162,18 +181,71 @@ class PODProjectorFromData:
         return d, to_host(phi_d), to_host(Mphi_d), u_shift_d.cpu().numpy()
 
     # ---------------------------------------------------------------- randomized GHEP (north star (a))
-    def _randomized(self, Xt, Md, u_rank, oversampling, Omega, collective, faithful):
+    def _resolve_omega(self, Omega, n, m):
+        if Omega is None:
+            return gaussian_omega(n, m, 1, self.device)
+        if not isinstance(Omega, DeviceMultiVector):
+            return DeviceMultiVector.from_dense(Omega, self.device)
+        return Omega
+
+    def _upload_pipelined(self, u_host, Md, Omega, shifted, collective, max_chunks=8):
+        """Host snapshots -> device in row chunks on a copy stream; as each chunk lands the main stream adds its column
+        sums to the sample mean and computes its rows of the first projection W = X (M Omega) (DMMA GEMM), so that the
+        PCIe transfer hides that work.  The mean shift is then applied to W as the rank-one correction
+        (X - 1 u^T) B = X B - 1 (u^T B) and to X in place (so every later product sees the shifted data exactly as in
+        the resident path).  Returns (Xt shifted, W, u_shift)."""
+        dev = self.device
+        src = u_host if isinstance(u_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(u_host, dtype=np.float64))
+        N, n = src.shape
+        m = Omega.nvec()
+        Xt = K.padded_empty(N, n, dev)
+        B = Md.matmat(Omega.tensor())                                        # M Omega, ready before the data arrives
+        W = K.padded_empty(N, m, dev)
+        nchunk = int(max(1, min(max_chunks, N // 256)))
+        bounds = [(i * N // nchunk, (i + 1) * N // nchunk) for i in range(nchunk)]
+        main = torch.cuda.current_stream(dev)
+        copy_stream = _copy_stream(dev)
+        copy_stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for lo, hi in bounds:
+                Xt[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+        colsum = None
+        for (lo, hi), ev in zip(bounds, events):
+            main.wait_event(ev)
+            if shifted:
+                part = K.colsum(Xt[lo:hi], 1.0)
+                colsum = part if colsum is None else colsum.add_(part)
+            K.dgemm(K.HFB_NN, Xt[lo:hi], B, out=W[lo:hi])
+        Xt.record_stream(copy_stream)
+        if shifted:
+            u_shift = colsum.mul_(1.0 / N)
+            collective.allReduce(u_shift, 'avg')
+            sb = K.dgemm(K.HFB_TN, K.to_padded(u_shift.unsqueeze(1), dev, pad=2), B)     # (1, m) = u^T B
+            K.subtract_row_(W, sb.reshape(-1).contiguous())
+            K.subtract_row_(Xt, u_shift)
+        else:
+            u_shift = torch.zeros(n, dtype=torch.float64, device=dev)
+        return Xt, W, u_shift
+
+    def _randomized(self, Xt, Md, u_rank, oversampling, Omega, collective, faithful, first_W=None):
         n = Xt.shape[1]
         m = u_rank + oversampling
-        if Omega is None:
-            Omega = gaussian_omega(n, m, 1, self.device)
-        elif not isinstance(Omega, DeviceMultiVector):
-            Omega = DeviceMultiVector.from_dense(Omega, self.device)
+        Omega = self._resolve_omega(Omega, n, m)
         assert Omega.nvec() >= u_rank
-        C = SampleCovarianceOperator(SampleCovariance(Xt), collective, 'avg')
+        cov = SampleCovariance(Xt)
+        C = SampleCovarianceOperator(cov, collective, 'avg')
         A = SandwichedCovarianceOperator(C, Md)
         self.info = {}
-        d, U = doublePassG(A, Md, None, Omega, u_rank, s=1, faithful=faithful, info=self.info)
+        Q0 = None
+        if first_W is not None:
+            # range finder from the pre-computed projection: Q0 = avg_g (1/N_loc) X_g^T W_g  (= C M Omega)
+            Q0 = DeviceMultiVector(cov.lift(first_W))
+            collective.allReduce(Q0, 'avg')
+        d, U = doublePassG(A, Md, None, Omega, u_rank, s=1, faithful=faithful, info=self.info, Q0=Q0)
         Mphi = Md.matmat(U.tensor())
         return d, U.tensor(), Mphi
 

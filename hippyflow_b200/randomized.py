@@ -108,15 +108,16 @@ def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     return d, U
 
 
-def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None):
+def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None, Q0=None):
     """Generalised problem A u = lambda B u.  ``B`` is a linalg.CsrMatrix (or any object with
     ``matmat``); ``Binv`` an object with ``solve_block(Y) -> B^-1 Y``; it is not needed when A exposes
     ``solveB_matMvMult`` (A = B C B, so B^-1 A X = C B X without a solve).
+    ``Q0``: the block B^-1 A Omega when the caller has already formed it (s = 1 only).
     Returns d (k,), U (n, k) with U^T B U = I."""
     nvec = Omega.nvec()
     assert k <= nvec
     Q = Omega                                   # not modified: every apply writes a fresh block
-    for _ in range(s):
+    for _ in range(s if Q0 is None else 0):
         if hasattr(A, "solveB_matMvMult") and getattr(A, "B", None) is B and (Binv is None or not faithful):
             Y = DeviceMultiVector(K.padded_empty(Q.tensor().shape[0], nvec, Q.tensor().device))   # fully overwritten
             A.solveB_matMvMult(Q, Y)
@@ -124,6 +125,8 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None):
         else:
             Ybar = _block_apply(A, Q)
             Q = DeviceMultiVector(Binv.solve_block(Ybar.tensor()))
+    if Q0 is not None:
+        Q = Q0                                  # range-finder block B^-1 A Omega supplied by the caller (pipelined upload)
     Qt, BQt, oinfo = b_orthonormalize(Q.tensor(), B, return_BQ=True, defer_last=True)
     Q, BQ = DeviceMultiVector(Qt), DeviceMultiVector(BQt)
     d, C = _rayleigh_ritz(A, Q, BQ, k, oinfo.pop("gram", None), faithful)
