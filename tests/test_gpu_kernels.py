@@ -163,3 +163,25 @@ def test_dgemm_symmetric_result_flag(K, cuda_device, layout, n, kd):
         C = K.dgemm(layout, A, B, symmetric=True, splits=splits)
         assert float((C - ref).norm() / ref.norm()) < 1e-13
         assert torch.equal(C, C.t())
+
+
+def test_dgemm_random_shape_fuzz(K, cuda_device):
+    """Random ragged shapes / leading dimensions / split counts across all layouts (fixed seed)."""
+    rng = np.random.default_rng(1234)
+    for trial in range(60):
+        layout = int(rng.integers(0, 3))
+        M = int(rng.integers(1, 700))
+        N = int(rng.choice([1, 2, 7, 15, 25, 64, 74, 137, 138, 210, 266, 300, 511]))
+        Kd = int(rng.integers(1, 3000))
+        splits = int(rng.choice([0, 0, 1, 2, 5]))
+        A = torch.as_tensor(rng.standard_normal((M, Kd)), device=cuda_device)
+        B = torch.as_tensor(rng.standard_normal((Kd, N)), device=cuda_device)
+        ref = A @ B
+        pad_a, pad_b = int(rng.choice([2, 16])), int(rng.choice([2, 16]))
+        Ad = K.to_padded(A.t().contiguous() if layout == K.HFB_TN else A, cuda_device, pad=pad_a)
+        Bd = K.to_padded(B.t().contiguous() if layout == K.HFB_NT else B, cuda_device, pad=pad_b)
+        out = K.padded_empty(M, N, cuda_device, pad=int(rng.choice([1, 2, 16])))
+        out.fill_(float("nan"))
+        K.dgemm(layout, Ad, Bd, out=out, splits=splits)
+        err = float((out - ref).norm() / ref.norm())
+        assert err < 1e-13, (trial, layout, M, N, Kd, splits, err)
