@@ -69,6 +69,13 @@ class TorchCollective:
             t.mul_(1.0 / float(self.size()))
         return t
 
+    def allReduce_async(self, t, op="sum"):
+        """Asynchronous SUM allreduce of a contiguous device tensor; returns a work handle whose ``wait()`` orders the
+        current stream after the reduction (used to overlap the exchange of sketch row blocks with the next GEMM)."""
+        if op.lower() != "sum":
+            raise NotImplementedError("allReduce_async supports 'sum' (fold the 'avg' factor into the producer)")
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def _allReduce_array(self, v, op):
         if op not in ("sum", "avg"):
             raise NotImplementedError("Unknown operation *{0}* in TorchCollective.allReduce".format(op))

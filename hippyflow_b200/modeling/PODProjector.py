@@ -243,8 +243,8 @@ class PODProjectorFromData:
         Q0 = None
         if first_W is not None:
             # range finder from the pre-computed projection: Q0 = avg_g (1/N_loc) X_g^T W_g  (= C M Omega)
-            Q0 = DeviceMultiVector(cov.lift(first_W))
-            collective.allReduce(Q0, 'avg')
+            Q0 = DeviceMultiVector(K.padded_empty(n, m, self.device))
+            C.lift_reduced(first_W, Q0)
         d, U = doublePassG(A, Md, None, Omega, u_rank, s=1, faithful=faithful, info=self.info, Q0=Q0)
         Mphi = Md.matmat(U.tensor())
         return d, U.tensor(), Mphi

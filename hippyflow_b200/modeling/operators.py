@@ -39,10 +39,36 @@ class SampleCovarianceOperator:
         x.init(self.n)
 
     def matMvMult(self, X, Y):
-        self.cov.apply(X.tensor(), out=Y.tensor())
-        self.collective.allReduce(Y, self.mpi_op)
+        _, GW = self.cov.project(X.tensor())
+        self.lift_reduced(GW, Y)
 
     matMvTranspmult = matMvMult
+
+    def lift_reduced(self, GW, Y, nchunk=4):
+        """Y = allReduce_op( (1/N_loc) Xt^T GW ).  With more than one rank the lift GEMM is cut into row blocks of Y and
+        the NCCL allreduce of each block is issued asynchronously as soon as its GEMM is queued, so the exchange of
+        block i overlaps the GEMM of block i+1 (the 'avg' factor 1/size is folded into the GEMM's alpha)."""
+        Yt = Y.tensor()
+        n = Yt.shape[0]
+        scale = 1.0 / self.cov.nsamples
+        size = self.collective.size()
+        if size == 1 or not hasattr(self.collective, "allReduce_async") or n < 4096:
+            K.dgemm(K.HFB_TN, self.cov.Xt, GW, out=Yt, alpha=scale)
+            self.collective.allReduce(Y, self.mpi_op)
+            return
+        if self.mpi_op.lower() == "avg":
+            scale /= float(size)
+        elif self.mpi_op.lower() != "sum":
+            raise NotImplementedError("Unknown operation *{0}*".format(self.mpi_op))
+        step = max(128, ((n + nchunk - 1) // nchunk + 127) // 128 * 128)     # 128-row multiples keep TMA alignment
+        full = Y.storage_tensor()
+        works = []
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            K.dgemm(K.HFB_TN, self.cov.Xt[:, lo:hi], GW, out=Yt[lo:hi], alpha=scale)
+            works.append(self.collective.allReduce_async(full[lo:hi], "sum"))
+        for w in works:
+            w.wait()
 
     def mult(self, x, y):
         self.cov.apply(x.storage_tensor(), out=y.storage_tensor())

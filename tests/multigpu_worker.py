@@ -68,6 +68,23 @@ def main():
     np.testing.assert_allclose(dj[:k], dj0[:k], rtol=1e-10)
     assert P.principal_angle(hf.mv_to_dense(Vj)[:, :k], Vj0[:, :k]) < 1e-8
 
+    # n >= 4096: the lift GEMM is cut into row blocks whose NCCL allreduce overlaps the next block's GEMM
+    Mb = syn.p1_mass_matrix(70)                                   # 5041 dofs
+    nb = Mb.shape[0]
+    ub = syn.snapshots(nb, 32 * world, r0=24, seed=21)
+    Omb = syn.gaussian_omega(nb, 18, seed=22)
+    pb = hf.PODProjectorFromData(None, M_output=Mb, device=dev)
+    db, phib, _, sb = pb.construct_subspace(ub[rank * 32:(rank + 1) * 32].copy(), 8, shifted=True, method="randomized",
+                                            Omega=Omb, collective=coll)
+    db0, Ub0, _, sb0 = P.pod_randomized_weighted(ub, Mb, 8, Omb, shifted=True, ranks=world)
+    np.testing.assert_allclose(db, db0, rtol=1e-10)
+    assert P.principal_angle(phib, Ub0, Mb) < 1e-8
+    np.testing.assert_allclose(sb, sb0, atol=1e-14)
+    # same through the device-resident (non-pipelined) entry
+    Xd = hf._lib.to_padded(ub[rank * 32:(rank + 1) * 32], dev)
+    db2, _, _, _ = pb.construct_subspace(Xd, 8, shifted=True, method="randomized", Omega=Omb, collective=coll)
+    np.testing.assert_allclose(db2, db0, rtol=1e-10)
+
     # collective on device blocks: one NCCL call for the whole padded block, 'avg' = sum / size
     mv = hf.DeviceMultiVector(50, 7, device=dev)
     mv.tensor().fill_(float(rank + 1))
