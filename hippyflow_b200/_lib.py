@@ -56,6 +56,9 @@ def lib():
         "hfb_csr_cluster_rows": (i32, [i64, vp, vp, i32, vp]),
         "hfb_csr_cluster_rows_capped": (i32, [i64, vp, vp, i32, i32, vp, vp, ctypes.POINTER(ctypes.c_int64)]),
         "hfb_csr_spmm_staged": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_cluster_blob_stride": (i64, [i32, i32, i32]),
+        "hfb_csr_pack_clusters": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+        "hfb_csr_spmm_tma": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -64,6 +67,7 @@ def lib():
         "hfb_colmean_workspace_bytes": (sz, [i64, i64]),
         "hfb_colsum": (i32, [i64, i64, vp, i64, dbl, vp, vp, sz, vp]),
         "hfb_subtract_row": (i32, [i64, i64, vp, i64, vp, vp]),
+        "hfb_rank1_update": (i32, [i64, i64, dbl, vp, vp, vp, i64, vp]),
         "hfb_axpby": (i32, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
         "hfb_axpby_cols": (i32, [i64, i64, vp, vp, i64, vp, vp, i64, vp]),
         "hfb_rowscale": (i32, [i64, i64, vp, vp, i64, vp, i64, vp]),
@@ -82,9 +86,10 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_ex_workspace_bytes",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
+            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
-            "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
+            "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
             "hfb_measure_dmma_peak"]
 
 
@@ -144,7 +149,7 @@ def to_padded(a, device, pad=16):
     return out
 
 
-def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False):
+def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumulate=False):
     """out[M,N] = alpha * op(A) op(B) on the DMMA/TMA kernel.  layout: HFB_NN (A MxK, B KxN),
     HFB_TN (A KxM), HFB_NT (B NxK).  symmetric=True: the caller asserts a symmetric result (Gram matrix); only the
     tiles on or above the diagonal are computed, the rest is mirrored."""
@@ -163,12 +168,17 @@ def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False):
         raise HfbError("unknown layout")
     if K != K2:
         raise HfbError("dgemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    fresh_out = out is None
     if out is None:
         out = padded_empty(M, N, A.device)
     _req(out, "out")
     if tuple(out.shape) != (M, N):
         raise HfbError("dgemm: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
     flags = 1 if (symmetric and M == N) else 0
+    if accumulate:
+        if fresh_out or flags:
+            raise HfbError("dgemm: accumulate needs an existing out and is not combinable with symmetric")
+        flags |= 2
     nbytes = L.hfb_dgemm_ex_workspace_bytes(layout, M, N, K, splits, flags)
     ws = workspace(nbytes, A.device) if nbytes else None
     if TIMING is not None:
@@ -255,6 +265,39 @@ def csr_spmm_staged(plan, B, out=None):
     return out
 
 
+def csr_pack_clusters(indptr, indices, data, order, cptr, max_rows, max_cols, max_entries):
+    """Host preprocessing for the TMA SpMM: uint8 NumPy buffer of per-cluster blobs (hfb_csr_pack_clusters)."""
+    import numpy as np
+    L = lib()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    cptr = np.ascontiguousarray(cptr, dtype=np.int32)
+    ncl = cptr.size - 1
+    stride = int(L.hfb_csr_cluster_blob_stride(int(max_rows), int(max_cols), int(max_entries)))
+    if stride <= 0:
+        raise HfbError("hfb_csr_cluster_blob_stride: invalid caps")
+    blobs = np.empty(ncl * stride, dtype=np.uint8)
+    rc = L.hfb_csr_pack_clusters(indptr.size - 1, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, order.ctypes.data,
+                                 cptr.ctypes.data, ncl, int(max_rows), int(max_cols), int(max_entries), blobs.ctypes.data)
+    _check(rc, "hfb_csr_pack_clusters")
+    return blobs
+
+
+def csr_spmm_tma(plan, B, out=None):
+    """C = M @ B with the persistent TMA-fed kernel; ``plan`` is the dict built by linalg.CsrMatrix._build_plan."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_tma(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+                            plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_tma")
+    return out
+
+
 def csr_cluster_rows(indptr, indices, cluster=64):
     """Host preprocessing: NumPy int32 CSR arrays -> int32 permutation grouping neighbouring rows (hfb_csr_cluster_rows)."""
     import numpy as np
@@ -329,6 +372,17 @@ def subtract_row_(X, shift):
     rc = L.hfb_subtract_row(X.shape[0], X.shape[1], X.data_ptr(), _ld(X), shift.data_ptr(), _stream())
     _check(rc, "hfb_subtract_row")
     return X
+
+
+def rank1_update_(Y, a, x, y):
+    """Y += a * outer(x, y) for device vectors x (rows) and y (columns)."""
+    L = lib()
+    _req(Y, "Y")
+    if x.numel() != Y.shape[0] or y.numel() != Y.shape[1]:
+        raise HfbError("rank1_update_: vector lengths do not match Y")
+    rc = L.hfb_rank1_update(Y.shape[0], Y.shape[1], float(a), x.data_ptr(), y.data_ptr(), Y.data_ptr(), _ld(Y), _stream())
+    _check(rc, "hfb_rank1_update")
+    return Y
 
 
 def axpby_(a, X, b, Y):

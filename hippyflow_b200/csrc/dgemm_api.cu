@@ -106,7 +106,7 @@ static int auto_splits(long long M, long long N, long long K, int symmetric = 0)
 
 // Fixed-order sum of the split slabs: C = alpha * sum_s ws[s]  (bitwise reproducible).
 __global__ void splitk_reduce_kernel(const double* __restrict__ ws, long long split_stride, int splits, long long ldw,
-                                     double* __restrict__ C, long long ldc, int M, int N, double alpha) {
+                                     double* __restrict__ C, long long ldc, int M, int N, double alpha, int accumulate) {
     const long long total = (long long)M * N;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -115,7 +115,7 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, long long sp
         const double* src = ws + r * ldw + c;
         double s = 0.0;
         for (int k = 0; k < splits; ++k) s += src[(long long)k * split_stride];
-        C[r * ldc + c] = alpha * s;
+        C[r * ldc + c] = accumulate ? (C[r * ldc + c] + alpha * s) : alpha * s;
     }
 }
 
@@ -180,7 +180,9 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
                             size_t workspace_bytes, int splits, int flags, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const int symmetric = ((flags & HFB_GEMM_SYMMETRIC) && M == N) ? 1 : 0;
+    const int accumulate = (flags & HFB_GEMM_ACCUMULATE) ? 1 : 0;
     if ((flags & HFB_GEMM_SYMMETRIC) && M != N) return HFB_E_BADARG;
+    if (symmetric && accumulate) return HFB_E_UNSUPPORTED;  // the mirror pass would overwrite the accumulated half
     if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || splits < 0) return HFB_E_BADARG;
     if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return HFB_E_BADARG;
     const long long a_inner = (layout == HFB_TN) ? M : K, a_outer = (layout == HFB_TN) ? K : M;
@@ -220,6 +222,7 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
     }
     p.vec_store = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 1) == 0) ? 1 : 0;
     p.symmetric = symmetric;
+    p.accumulate = accumulate;
     if ((long long)p.m_tiles * p.n_tiles * p.splits > 0x7fffffffLL) return HFB_E_BADARG;
 
     CUtensorMap mapA, mapB;
@@ -241,7 +244,7 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const double*)workspace, p.split_stride, splits, ldw,
-                                                                  C, ldc, (int)M, (int)N, alpha);
+                                                                  C, ldc, (int)M, (int)N, alpha, accumulate);
         ++g_launch_count;
         rc = (int)cudaGetLastError();
     }

@@ -44,6 +44,7 @@ struct GemmParams {
     long long split_stride;  // elements between consecutive split slabs in the workspace
     int vec_store;         // 1 if C base is 16-byte aligned and ldc even (16-byte stores allowed)
     int symmetric;         // 1: the result is symmetric (M == N); tiles strictly below the diagonal are skipped
+    int accumulate;        // 1: C += alpha * op(A) op(B)  (applied here when splits == 1, else by the split-K reduce)
 };
 
 template <int LAYOUT, int NT>
@@ -245,6 +246,17 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // ---------------------------------------------------------------------- epilogue
     double* Cout = p.C + (long long)split * p.split_stride;
     const double alpha = (p.splits == 1) ? p.alpha : 1.0;
+    const bool accum = (p.splits == 1) && p.accumulate;
+    auto put1 = [&](double* dst, double v) { *dst = accum ? (*dst + v) : v; };
+    auto put2 = [&](double* dst, double v0, double v1) {
+        double2 o = make_double2(v0, v1);
+        if (accum) {
+            const double2 c = *reinterpret_cast<const double2*>(dst);
+            o.x += c.x;
+            o.y += c.y;
+        }
+        *reinterpret_cast<double2*>(dst) = o;
+    };
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int row = m0 + 16 * warp + (Cfg::A_KC ? (8 * j + rg) : (2 * g + j));
@@ -254,8 +266,8 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
             for (int jn = 0; jn < NT; ++jn) {
                 const int c0 = n0 + 8 * jn + t, c1 = c0 + 4;  // rho(2t) = t, rho(2t+1) = 4 + t
-                if (c0 < p.N) crow[c0] = alpha * acc[j][jn][0];
-                if (c1 < p.N) crow[c1] = alpha * acc[j][jn][1];
+                if (c0 < p.N) put1(crow + c0, alpha * acc[j][jn][0]);
+                if (c1 < p.N) put1(crow + c1, alpha * acc[j][jn][1]);
             }
         } else {
 #pragma unroll
@@ -265,23 +277,23 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const double v0 = alpha * acc[j][2 * pp][0], v1 = alpha * acc[j][2 * pp + 1][0];
                 const double v2 = alpha * acc[j][2 * pp][1], v3 = alpha * acc[j][2 * pp + 1][1];
                 if (p.vec_store && c + 3 < p.N) {
-                    *reinterpret_cast<double2*>(crow + c) = make_double2(v0, v1);
-                    *reinterpret_cast<double2*>(crow + c + 2) = make_double2(v2, v3);
+                    put2(crow + c, v0, v1);
+                    put2(crow + c + 2, v2, v3);
                 } else {
-                    if (c < p.N) crow[c] = v0;
-                    if (c + 1 < p.N) crow[c + 1] = v1;
-                    if (c + 2 < p.N) crow[c + 2] = v2;
-                    if (c + 3 < p.N) crow[c + 3] = v3;
+                    if (c < p.N) put1(crow + c, v0);
+                    if (c + 1 < p.N) put1(crow + c + 1, v1);
+                    if (c + 2 < p.N) put1(crow + c + 2, v2);
+                    if (c + 3 < p.N) put1(crow + c + 3, v3);
                 }
             }
             if (NT & 1) {
                 const int c = n0 + 8 * (NT - 1) + 2 * t;  // direct mapping: columns 2t, 2t+1 of the last tile
                 const double v0 = alpha * acc[j][NT - 1][0], v1 = alpha * acc[j][NT - 1][1];
                 if (p.vec_store && c + 1 < p.N) {
-                    *reinterpret_cast<double2*>(crow + c) = make_double2(v0, v1);
+                    put2(crow + c, v0, v1);
                 } else {
-                    if (c < p.N) crow[c] = v0;
-                    if (c + 1 < p.N) crow[c + 1] = v1;
+                    if (c < p.N) put1(crow + c, v0);
+                    if (c + 1 < p.N) put1(crow + c + 1, v1);
                 }
             }
         }

@@ -372,6 +372,34 @@ __global__ void __launch_bounds__(256) subtract_row_kernel(long long N, long lon
         }
     }
 }
+// Y[r, c] += a * x[r] * y[c]  (rank-one update).  Same 2-D mapping as subtract_row_kernel: a thread owns one 16-byte
+// column pair for RB consecutive rows.
+template <int RB>
+__global__ void __launch_bounds__(256) rank1_update_kernel(long long n, long long m, double a, const double* __restrict__ x,
+                                                           const double* __restrict__ y, double* __restrict__ Y,
+                                                           long long ldy, int vec_ok) {
+    const long long c = 2 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (c >= m) return;
+    const long long r0 = (long long)blockIdx.y * RB;
+    const bool pair = (c + 1 < m);
+    const double y0 = a * y[c], y1 = pair ? a * y[c + 1] : 0.0;
+#pragma unroll 4
+    for (int i = 0; i < RB; ++i) {
+        const long long r = r0 + i;
+        if (r >= n) break;
+        const double xr = __ldg(x + r);
+        double* ptr = Y + r * ldy + c;
+        if (vec_ok && pair) {
+            double2 v = *reinterpret_cast<double2*>(ptr);
+            v.x = fma(xr, y0, v.x);
+            v.y = fma(xr, y1, v.y);
+            *reinterpret_cast<double2*>(ptr) = v;
+        } else {
+            ptr[0] = fma(xr, y0, ptr[0]);
+            if (pair) ptr[1] = fma(xr, y1, ptr[1]);
+        }
+    }
+}
 __global__ void __launch_bounds__(256) axpby_kernel(long long n, long long m, double a, const double* __restrict__ X,
                                                     long long ldx, double b, double* __restrict__ Y, long long ldy) {
     const long long total = n * m;
@@ -840,6 +868,27 @@ extern "C" int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, co
     dim3 grid((unsigned)(((n + 1) / 2 + 255) / 256), (unsigned)by);
     subtract_row_kernel<RB><<<grid, 256, 0, (cudaStream_t)stream_>>>(N, n, X, ldx, shift, vec_ok);
     HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+extern "C" int hfb_rank1_update(int64_t n, int64_t m, double a, const double* x, const double* y, double* Y, int64_t ldy,
+                                void* stream_) {
+    if (n <= 0 || m <= 0 || !x || !y || !Y || ldy < m) return HFB_E_BADARG;
+    constexpr int RB = 16;
+    const long long by = (n + RB - 1) / RB;
+    if (by > 0x7fffffffLL) return HFB_E_UNSUPPORTED;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
+    // rows on grid.x (up to 2^31 - 1 blocks), column pairs on grid.y
+    const long long bx = ((m + 1) / 2 + 255) / 256;
+    if (bx > 65535) return HFB_E_UNSUPPORTED;
+    dim3 grid((unsigned)bx, 1, 1);
+    // blockIdx.y carries the row block in the kernel: split over y (<= 65535) and loop in chunks if needed
+    for (long long y0 = 0; y0 < by; y0 += 65535) {
+        const long long cnt = (by - y0 < 65535) ? (by - y0) : 65535;
+        grid.y = (unsigned)cnt;
+        rank1_update_kernel<RB><<<grid, 256, 0, (cudaStream_t)stream_>>>(n - y0 * RB, m, a, x + y0 * RB, y, Y + y0 * RB * ldy, ldy,
+                                                                          vec_ok);
+        HFB_LAUNCHED();
+    }
     return (int)cudaGetLastError();
 }
 extern "C" int hfb_axpby(int64_t n, int64_t m, double a, const double* X, int64_t ldx, double b, double* Y, int64_t ldy,

@@ -35,6 +35,8 @@ class CsrMatrix:
         # B rows (<= 128) are staged in shared memory by the kernel
         self.order = None
         self.plan = None
+        import os
+        self.impl = os.environ.get("HFB_SPMM_IMPL", "tma")       # "tma" (persistent, cp.async.bulk ring) | "staged" (cp.async panels)
         if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
             try:
                 self.plan = self._build_plan(M, device)
@@ -72,15 +74,23 @@ class CsrMatrix:
         ent[:, 0] = vals
         ent[:, 1] = lcol.astype(np.int64).view(np.float64)
         max_entries = int(np.diff(s_rowptr[cptr]).max())
-        return {"nclusters": int(ncl), "max_cols": int(np.diff(cl_colptr).max()), "max_entries": max_entries,
+        plan = {"nclusters": int(ncl), "max_cols": int(np.diff(cl_colptr).max()), "max_entries": max_entries,
                 "cl_rowptr": t(cptr, np.int32), "order": t(order, np.int32), "s_rowptr": t(s_rowptr, np.int32),
                 "entries": torch.as_tensor(ent, device=device), "cl_colptr": t(cl_colptr, np.int32),
                 "cl_cols": t(ukey % n, np.int32)}
+        # blobs of the persistent TMA-fed kernel (one fixed-stride record per cluster, packed on the host in C)
+        plan["max_rows"] = int(np.diff(cptr).max())
+        plan["max_cols_cap"] = plan["max_cols"]
+        plan["blobs"] = torch.as_tensor(K.csr_pack_clusters(M.indptr, M.indices, M.data, order, cptr, plan["max_rows"],
+                                                            plan["max_cols_cap"], max_entries), device=device)
+        return plan
 
     def matmat(self, B, out=None):
         """out (n, m) = M @ B for a dense row-major (n, m) block."""
         if self.plan is not None and B.shape[1] >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
+            if self.impl == "tma" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1):
+                return K.csr_spmm_tma(self.plan, B, out)
             return K.csr_spmm_staged(self.plan, B, out)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order)
 

@@ -63,6 +63,9 @@ int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alpha,
 /* Same with flags.  HFB_GEMM_SYMMETRIC: the caller asserts that the (M == N) result is symmetric (Gram matrices
  * X^T M X, Y^T B Y, W^T W); tiles strictly below the diagonal are not computed and are filled by a mirror kernel. */
 #define HFB_GEMM_SYMMETRIC 1
+/* HFB_GEMM_ACCUMULATE: C += alpha * op(A) op(B) (C is read; not combinable with HFB_GEMM_SYMMETRIC).  Used to sum the
+ * per-chunk lifts Y += X_c^T W_c while the snapshots are still being uploaded. */
+#define HFB_GEMM_ACCUMULATE 2
 size_t hfb_dgemm_ex_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int splits, int flags);
 int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha,
                  const double* A, int64_t lda, const double* B, int64_t ldb,
@@ -112,6 +115,19 @@ int hfb_csr_spmm_staged(int64_t nclusters, int64_t m, const int32_t* cl_rowptr, 
                         const int32_t* cl_colptr, const int32_t* cl_cols, int32_t max_cols, int32_t max_entries,
                         const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
+/* Persistent TMA-fed SpMM (default for wide blocks).  HOST preprocessing hfb_csr_pack_clusters packs the clusters of
+ * hfb_csr_cluster_rows_capped into fixed-stride blobs (layout in hippyflow_b200/csrc/spmm_tma.cu; stride from
+ * hfb_csr_cluster_blob_stride; max_entries = largest number of matrix entries in one cluster); the caller uploads the
+ * blob buffer.  One CTA per SM; a producer warp moves every blob and every distinct B row of a (cluster, column chunk)
+ * work item with cp.async.bulk into an mbarrier-guarded shared-memory ring, consumer warps do LDS.128 + DFMA.
+ * B, C, blobs: 16-byte aligned; ldb, ldc even; ldb >= m rounded up to even. */
+int64_t hfb_csr_cluster_blob_stride(int32_t max_rows, int32_t max_cols, int32_t max_entries);
+int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int32_t* colind, const double* val, const int32_t* order,
+                          const int32_t* cluster_ptr, int64_t nclusters, int32_t max_rows, int32_t max_cols,
+                          int32_t max_entries, void* blobs_out /* HOST, nclusters * stride bytes */);
+int hfb_csr_spmm_tma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols, int32_t max_entries,
+                     const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.
  * (M X)^T for symmetric M with X stored as u_data (N, n)  (PODProjector.py:750, 818).
@@ -140,6 +156,11 @@ int hfb_colsum(int64_t N, int64_t n, const double* X, int64_t ldx, double scale,
                void* workspace, size_t workspace_bytes, void* stream);
 /* X[i,j] -= shift[j]  (u_data - u_shift, PODProjector.py:734). */
 int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, const double* shift, void* stream);
+
+/* Y[i,j] += a * x[i] * y[j]  (rank-one update of an (n x m) block): the mean-shift corrections
+ * (X - 1 u^T)^T W = X^T W - u (1^T W) that stand in for u_data - u_shift (PODProjector.py:734) when the stored
+ * snapshots are not modified. */
+int hfb_rank1_update(int64_t n, int64_t m, double a, const double* x, const double* y, double* Y, int64_t ldy, void* stream);
 
 /* Y = a*X + b*Y elementwise on an (n x m) block (axpy/scale of MultiVectors; 'avg' scaling of
  * collective.py:65-68 after the NCCL sum). */

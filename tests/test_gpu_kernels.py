@@ -85,6 +85,52 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
+@pytest.mark.parametrize("impl", ["tma", "staged"])
+@pytest.mark.parametrize("m", [96, 137, 138, 266, 300, 511, 1100])
+def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
+    """The two cluster-plan kernels (persistent TMA ring / cp.async panels) on a mesh matrix large enough to get a
+    plan (n >= 4096), odd and even widths, widths that need 1..4 column chunks; padding columns stay untouched."""
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    M = syn.p1_mass_matrix(70, 63)
+    n = M.shape[0]
+    Md = CsrMatrix(M, cuda_device)
+    assert Md.plan is not None
+    Md.impl = impl
+    B = np.random.default_rng(m).standard_normal((n, m))
+    out = K.padded_empty(n, m, cuda_device)
+    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
+    full.fill_(7.0)
+    Md.matmat(K.to_padded(B, cuda_device), out=out)
+    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
+    if K._ld(out) > m:
+        assert bool((full[:, m:] == 7.0).all())
+    again = Md.matmat(K.to_padded(B, cuda_device))
+    assert torch.equal(again, out)                 # fixed summation order: bitwise reproducible
+
+
+@pytest.mark.parametrize("impl", ["tma", "staged"])
+def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
+    """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
+    import scipy.sparse as sp
+    from hippyflow_b200.linalg import CsrMatrix
+    rng = np.random.default_rng(3)
+    n = 6000
+    A = sp.random(n, n, density=4.0 / n, random_state=7, format="csr")
+    A = (A + A.T + sp.diags(rng.standard_normal(n))).tolil()
+    for r in (0, 17, n - 1):
+        A[r, :] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    Md = CsrMatrix(A, cuda_device)
+    assert Md.plan is not None
+    Md.impl = impl
+    B = rng.standard_normal((n, 138))
+    out = Md.matmat(K.to_padded(B, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(out, A @ B, rtol=1e-12, atol=1e-14)
+    assert np.all(out[[0, 17, n - 1]] == 0.0)
+
+
 def test_column_kernels(K, cuda_device):
     rng = np.random.default_rng(0)
     X, Y = rng.standard_normal((1000, 37)), rng.standard_normal((1000, 37))
