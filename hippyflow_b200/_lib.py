@@ -105,8 +105,13 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def is_device_tensor(t):
+    """True for a tensor that lives in device memory (the only place the kernels can read)."""
+    return isinstance(t, torch.Tensor) and t.is_cuda
+
+
 def _req(t, name):
-    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
+    if not (is_device_tensor(t) and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
         raise HfbError("%s must be a 2-D float64 CUDA tensor with unit inner stride" % name)
     return t
 
@@ -206,7 +211,7 @@ def dgemm_batched_small(layout, A, B, out, alpha=1.0):
         M, K = A.shape[1], A.shape[2]
     N = B.shape[2]
     for t in (A, B, out):
-        if not (t.is_cuda and t.dtype == torch.float64 and t.dim() == 3 and t.stride(2) == 1):
+        if not (is_device_tensor(t) and t.dtype == torch.float64 and t.dim() == 3 and t.stride(2) == 1):
             raise HfbError("dgemm_batched_small: operands must be 3-D float64 CUDA tensors")
     if B.shape[1] != K or tuple(out.shape[1:]) != (M, N):
         raise HfbError("dgemm_batched_small: shape mismatch")

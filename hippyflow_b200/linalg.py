@@ -115,7 +115,12 @@ class SampleCovariance:
     ``apply`` is the two-GEMM form  Y = Xt^T (G (Xt B)) / N_loc  of those column-by-column loops.
     """
 
-    def __init__(self, Xt, block=1, noise_cov_inv=None):
+    def __init__(self, Xt, block=1, noise_cov_inv=None, center=None):
+        """``center``: optional device vector c (n,).  The operator then acts on the rows x_i - c WITHOUT modifying
+        ``Xt``: (X - 1 c^T) B = X B - 1 (c^T B) and (X - 1 c^T)^T W = X^T W - c (1^T W).  This stands in for the explicit
+        ``u_data - u_shift`` of PODProjector.py:734 (saves a read+write sweep over the stored snapshots and leaves the
+        caller's array untouched).  Round-off grows like eps * |c| / |x_i - c|; ``center_ratio`` reports
+        (|c| / rms|x_i - c|)^2 (estimated through the first projection) so that callers can fall back to an explicit shift."""
         self.Xt = K._req(Xt, "Xt")
         self.rows, self.n = Xt.shape
         self.block = int(block)  # rows per sample (dQ for Jacobians, 1 for snapshots)
@@ -127,6 +132,12 @@ class SampleCovariance:
             assert tuple(G.shape) == (self.block, self.block)
             self.noise_cov_inv = G.contiguous()
         self._W = None
+        self.center = None
+        self.center_ratio = None        # device scalar, set by the first ``project`` when a center is present
+        if center is not None:
+            assert self.noise_cov_inv is None and self.block == 1, "implicit centering is for snapshot rows"
+            self.center = center.contiguous()
+            self._center_col = K.to_padded(self.center.unsqueeze(1), Xt.device, pad=2)     # (n, 1): A operand of c^T B
 
     def _wbuf(self, m):
         if self._W is None or self._W.shape[1] != m:
@@ -142,6 +153,11 @@ class SampleCovariance:
         if B.data_ptr() % 16 or K._ld(B) % 2:
             B = K.to_padded(B, B.device)      # e.g. one column of a multivector block: stage into a TMA-aligned buffer
         K.dgemm(K.HFB_NN, self.Xt, B, out=W)
+        if self.center is not None:
+            sb = K.dgemm(K.HFB_TN, self._center_col, B).reshape(-1).contiguous()      # c^T B  (m,)
+            K.subtract_row_(W, sb)
+            if self.center_ratio is None:
+                self.center_ratio = self.rows * torch.dot(sb, sb) / torch.clamp_min(K.coldot(W, W).sum(), 1e-300)
         if self.noise_cov_inv is None:
             return W, W
         q = self.block
@@ -154,14 +170,14 @@ class SampleCovariance:
         """out (n, m) = scale * Xt^T G Xt B with scale = 1/nsamples by default (the local 'average'
         of SummedListOperator(average=True) / LowRankOperator(ones/N_loc))."""
         _, GW = self.project(B)
-        if scale is None:
-            scale = 1.0 / self.nsamples
-        return K.dgemm(K.HFB_TN, self.Xt, GW, out=out, alpha=scale)
+        return self.lift(GW, out=out, scale=scale, weighted=True)
 
-    def lift(self, W, out=None, scale=None):
-        """out (n, m) = scale * Xt^T [G] W for an already computed projection W = Xt B (second half of ``apply``)."""
+    def lift(self, W, out=None, scale=None, weighted=False, rows=None):
+        """out = scale * Xt^T [G] W for an already computed projection W = Xt B (second half of ``apply``).
+        ``weighted``: W already carries Gamma^-1.  ``rows = (lo, hi)``: only rows lo..hi of the result (a column block of
+        Xt), used by the chunked lift that overlaps the sketch exchange."""
         GW = W
-        if self.noise_cov_inv is not None:
+        if self.noise_cov_inv is not None and not weighted:
             q, m = self.block, W.shape[1]
             GWb = K.padded_empty(self.rows, m, self.Xt.device)
             K.dgemm_batched_small(K.HFB_NN, self.noise_cov_inv.unsqueeze(0),
@@ -170,7 +186,11 @@ class SampleCovariance:
             GW = GWb
         if scale is None:
             scale = 1.0 / self.nsamples
-        return K.dgemm(K.HFB_TN, self.Xt, GW, out=out, alpha=scale)
+        lo, hi = (0, self.n) if rows is None else rows
+        out = K.dgemm(K.HFB_TN, self.Xt if rows is None else self.Xt[:, lo:hi], GW, out=out, alpha=scale)
+        if self.center is not None:
+            K.rank1_update_(out, -scale, self.center[lo:hi], K.colsum(GW, 1.0))       # - c (1^T W)
+        return out
 
     def gram_T(self, B, scale=None):
         """T_local (m, m) = scale * (Xt B)^T G (Xt B): the Rayleigh quotient B^T C B without forming C B
@@ -189,6 +209,24 @@ class SampleCovariance:
 
 def _sym(G):
     return 0.5 * (G + G.T)
+
+
+def sym_gram(Y, Z, alpha=1.0):
+    """G (m, m) = alpha * Y^T Z for a product known to be symmetric (Z = B Y with B symmetric), on the DMMA kernel.
+    The kernel's tiles have 128 rows; when m is a little above a multiple of 128 (m = 266: 10 columns over) the last
+    row of tiles would be almost empty, so the leading (m0 x m0) block (m0 = multiple of 128) is computed with the
+    symmetric flag (upper tiles + mirror) and the thin border G[:, m0:] by a second narrow GEMM, then mirrored:
+    61 k instead of 87 k tile entries per k-step at m = 266."""
+    m = Y.shape[1]
+    r = m % 128
+    if m <= 128 or r == 0 or r > 32 or Y.data_ptr() % 16 or Z.data_ptr() % 16 or K._ld(Y) % 2 or K._ld(Z) % 2:
+        return K.dgemm(K.HFB_TN, Y, Z, alpha=alpha, symmetric=True)
+    m0 = m - r
+    G = K.padded_empty(m, m, Y.device)
+    K.dgemm(K.HFB_TN, Y[:, :m0], Z[:, :m0], out=G[:m0, :m0], alpha=alpha, symmetric=True)
+    K.dgemm(K.HFB_TN, Y, Z[:, m0:], out=G[:, m0:], alpha=alpha)
+    G[m0:, :m0].copy_(G[:m0, m0:].t())
+    return G
 
 
 def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=False):
@@ -220,7 +258,7 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=Fals
     eye = np.eye(m)
     for it in range(max_passes):
         Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
-        G = _sym(K.dgemm(K.HFB_TN, Y, Z, symmetric=True).cpu().numpy())
+        G = _sym(sym_gram(Y, Z).cpu().numpy())
         d = np.sqrt(np.maximum(np.diag(G), 0.0))
         dead = d <= 0.0
         dinv = np.where(dead, 0.0, 1.0 / np.where(dead, 1.0, d))
@@ -254,7 +292,7 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=Fals
         info["passes"] += 1
         if defer_last and it == 0 and shift == 0.0 and cond * eps * m < 1e-4:
             Z = Bmat.matmat(Y, out=Z) if Bmat is not None else Y
-            info["gram"] = K.dgemm(K.HFB_TN, Y, Z, symmetric=True)                 # device (m x m); fetched by the caller, asynchronously
+            info["gram"] = sym_gram(Y, Z)                                          # device (m x m); fetched by the caller, asynchronously
             return Y, (Z if return_BQ else None), info
         if shift == 0.0 and it >= 1 and cond < 4.0:
             # the previous pass already left cond(G) ~ 1, so this pass is accurate to round-off

@@ -103,6 +103,7 @@ class PODProjectorFromData:
         self.device = device if device is not None else _default_device()
         self._Md = None
         self.timings = {}
+        self.shift_route = None     # how the last construct_subspace applied the mean shift
 
     @property
     def M_device(self):
@@ -110,14 +111,20 @@ class PODProjectorFromData:
             self._Md = CsrMatrix(self.M_csr, self.device)
         return self._Md
 
+    # (|mean| / rms fluctuation)^2 above which the implicit mean shift (round-off ~ eps * ratio^(1/2)) is replaced by the
+    # explicit subtraction of the reference
+    IMPLICIT_SHIFT_MAX_RATIO = 1.0e6
+
     def construct_subspace(self, u_data, u_rank, shifted=True, method='hep', verify=False,
                            oversampling=10, Omega=None, collective=None, return_device=False, faithful=False,
-                           overwrite_data=False, pipelined_upload=True):
+                           overwrite_data=False, pipelined_upload=True, implicit_shift=True):
         """Same contract as PODProjector.py:699-852: returns (d, phi, Mphi, u_shift) as NumPy arrays of shape
         (r,), (n, r), (n, r), (n,).  ``u_data`` may be a NumPy array or a float64 CUDA tensor (rows = samples;
         with a collective, the local shard).  Extra keywords (randomized method only): ``oversampling``,
         ``Omega`` ((n, r+p) array or DeviceMultiVector fed to the solver), ``collective`` (sample-parallel),
-        ``overwrite_data`` (allow the mean shift to be applied in place to a device-resident ``u_data``)."""
+        ``implicit_shift`` (apply the mean shift of :732-738 inside the products, (X - 1 u^T) B = X B - 1 (u^T B), instead
+        of rewriting the stored snapshots; falls back to the explicit shift when the mean dominates the fluctuations),
+        ``overwrite_data`` (allow an explicit shift to be applied in place to a device-resident ``u_data``)."""
         n_data, dim_u = u_data.shape
         collective = collective if collective is not None else NullCollective()
         n_total = n_data * collective.size()
@@ -127,33 +134,44 @@ class PODProjectorFromData:
         dev = self.device
         Md = self.M_device
         t0 = time.time()
-        owns = not (isinstance(u_data, torch.Tensor) and u_data.is_cuda)
-        first_W = None
+        owns = not (K.is_device_tensor(u_data))
+        pre = None          # pass-1 products formed while the snapshots were uploaded
+        center = None       # vector still to be subtracted (implicitly) from every stored row
         if owns and method == 'randomized' and pipelined_upload:
             # host input: stream the snapshots to the device in row chunks and overlap the upload with the sample mean
-            # and the first projection W = X (M Omega)
+            # and the whole range-finding pass  Y = X~^T X~ (M Omega)
             Omega = self._resolve_omega(Omega, dim_u, u_rank + oversampling)
-            Xt, first_W, u_shift_d = self._upload_pipelined(u_data, Md, Omega, shifted, collective)
+            Xt, u_shift_d, center, pre = self._upload_pipelined(u_data, Md, Omega, shifted, collective)
+            self.shift_route = 'pipelined' if shifted else 'none'
         else:
             Xt = _as_device_rows(u_data, dev)
-        if first_W is not None:
-            pass
-        elif shifted:
-            # u_shift = mean over ALL samples (np.mean(u_data, axis=0), PODProjector.py:733), then X - shift
-            u_shift_d = K.colsum(Xt, 1.0 / n_data)
-            collective.allReduce(u_shift_d, 'avg')
-            if not owns and not overwrite_data:
-                Xc = K.padded_empty(n_data, dim_u, dev)
-                Xc.copy_(Xt)
-                Xt = Xc
-            K.subtract_row_(Xt, u_shift_d)
-        else:
-            u_shift_d = torch.zeros(dim_u, dtype=torch.float64, device=dev)
+            if shifted:
+                # u_shift = mean over ALL samples (np.mean(u_data, axis=0), PODProjector.py:733), then X - shift
+                u_shift_d = K.colsum(Xt, 1.0 / n_data)
+                collective.allReduce(u_shift_d, 'avg')
+                if method == 'randomized' and implicit_shift:
+                    center = u_shift_d
+                    self.shift_route = 'implicit'
+                else:
+                    Xt = self._shift_explicit(Xt, u_shift_d, owns or overwrite_data)
+                    self.shift_route = 'explicit'
+            else:
+                u_shift_d = torch.zeros(dim_u, dtype=torch.float64, device=dev)
+                self.shift_route = 'none'
         self.timings['upload_shift'] = time.time() - t0
 
         t1 = time.time()
         if method == 'randomized':
-            d, phi_d, Mphi_d = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, first_W)
+            d, phi_d, Mphi_d, ratio = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, center, pre)
+            if ratio is not None:
+                worst = ratio.reshape(1).clone()
+                collective.allReduce(worst, 'sum')
+                if float(worst) > self.IMPLICIT_SHIFT_MAX_RATIO * collective.size():
+                    # the mean dominates the fluctuations: redo with the data shifted explicitly, as the reference does
+                    Xt = self._shift_explicit(Xt, center, owns or overwrite_data)
+                    center = None
+                    self.shift_route = 'explicit-fallback'
+                    d, phi_d, Mphi_d, _ = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, None, None)
         else:
             if collective.size() != 1:
                 raise NotImplementedError("method='%s' is serial like the reference (PODProjector.py:683); "
@@ -163,6 +181,8 @@ class PODProjectorFromData:
         self.timings['eigensolve'] = time.time() - t1
 
         if verify:
+            if center is not None:
+                Xt = self._shift_explicit(Xt, center, owns)
             r = u_rank - 1 if shifted else u_rank
             G = K.dgemm(K.HFB_TN, phi_d[:, :r], Mphi_d[:, :r]).cpu().numpy()
             print(f"Basis-Projector Orthogonality error: {np.linalg.norm(G - np.eye(r))}")
@@ -178,7 +198,34 @@ class PODProjectorFromData:
                 print(f"Max reconstruction error: {np.max(rel):.3e}")
         if return_device:
             return d, phi_d, Mphi_d, u_shift_d
-        return d, to_host(phi_d), to_host(Mphi_d), u_shift_d.cpu().numpy()
+        return self._results_to_host(d, phi_d, Mphi_d, u_shift_d)
+
+    @staticmethod
+    def _shift_explicit(Xt, shift, in_place):
+        """X - 1 shift^T written out (PODProjector.py:734); copies first unless the buffer may be overwritten."""
+        if not in_place:
+            Xc = K.padded_empty(Xt.shape[0], Xt.shape[1], Xt.device)
+            Xc.copy_(Xt)
+            Xt = Xc
+        K.subtract_row_(Xt, shift)
+        return Xt
+
+    def _results_to_host(self, d, phi_d, Mphi_d, u_shift_d):
+        """Device results -> NumPy through pinned staging buffers; the two (n x r) blocks travel back to back on the
+        copy stream."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        cs = _copy_stream(dev)
+        cs.wait_stream(main)
+        hosts = []
+        with torch.cuda.stream(cs):
+            for t in (phi_d, Mphi_d, u_shift_d):
+                h = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+                h.copy_(t, non_blocking=True)
+                t.record_stream(cs)
+                hosts.append(h)
+        cs.synchronize()
+        return d, hosts[0].numpy(), hosts[1].numpy(), hosts[2].numpy()
 
     # ---------------------------------------------------------------- randomized GHEP (north star (a))
     def _resolve_omega(self, Omega, n, m):
@@ -189,11 +236,15 @@ class PODProjectorFromData:
         return Omega
 
     def _upload_pipelined(self, u_host, Md, Omega, shifted, collective, max_chunks=8):
-        """Host snapshots -> device in row chunks on a copy stream; as each chunk lands the main stream adds its column
-        sums to the sample mean and computes its rows of the first projection W = X (M Omega) (DMMA GEMM), so that the
-        PCIe transfer hides that work.  The mean shift is then applied to W as the rank-one correction
-        (X - 1 u^T) B = X B - 1 (u^T B) and to X in place (so every later product sees the shifted data exactly as in
-        the resident path).  Returns (Xt shifted, W, u_shift)."""
+        """Host snapshots -> device in row chunks on a copy stream.  As each chunk X_c lands the main stream (i) removes a
+        PROVISIONAL mean p (the mean of the first chunk) from it in place, (ii) adds its column sums to the running mean,
+        (iii) computes its rows of the projection W' = X' (M Omega) and (iv) accumulates its share of the lift
+        Y0 += X_c'^T W_c' / N, so the PCIe transfer hides the whole range-finding pass.  With the true mean known at the
+        end, delta = mean - p is small (O(sigma / sqrt(chunk))), and the exactly shifted products follow from rank-one
+        corrections without cancellation:
+            W~ = W' - 1 (delta^T B),      Y = Y0 - mean' (delta^T B)^T - delta (1^T W' / N - delta^T B)^T,
+        where mean' = mean of the stored rows X'.  The stored rows keep the residual ``delta``; later products subtract it
+        implicitly (SampleCovariance(center=delta)).  Returns (Xt', u_shift, delta or None, (W~, Y_local))."""
         dev = self.device
         src = u_host if isinstance(u_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(u_host, dtype=np.float64))
         N, n = src.shape
@@ -201,6 +252,7 @@ class PODProjectorFromData:
         Xt = K.padded_empty(N, n, dev)
         B = Md.matmat(Omega.tensor())                                        # M Omega, ready before the data arrives
         W = K.padded_empty(N, m, dev)
+        Y = K.padded_empty(n, m, dev)
         nchunk = int(max(1, min(max_chunks, N // 256)))
         bounds = [(i * N // nchunk, (i + 1) * N // nchunk) for i in range(nchunk)]
         main = torch.cuda.current_stream(dev)
@@ -214,40 +266,49 @@ class PODProjectorFromData:
                 ev.record(copy_stream)
                 events.append(ev)
         colsum = None
-        for (lo, hi), ev in zip(bounds, events):
+        prov = None
+        for i, ((lo, hi), ev) in enumerate(zip(bounds, events)):
             main.wait_event(ev)
+            Xc = Xt[lo:hi]
             if shifted:
-                part = K.colsum(Xt[lo:hi], 1.0)
+                if i == 0:
+                    prov = K.colsum(Xc, 1.0 / (hi - lo))
+                K.subtract_row_(Xc, prov)
+                part = K.colsum(Xc, 1.0)
                 colsum = part if colsum is None else colsum.add_(part)
-            K.dgemm(K.HFB_NN, Xt[lo:hi], B, out=W[lo:hi])
+            K.dgemm(K.HFB_NN, Xc, B, out=W[lo:hi])
+            K.dgemm(K.HFB_TN, Xc, W[lo:hi], out=Y, alpha=1.0 / N, accumulate=(i > 0))
         Xt.record_stream(copy_stream)
-        if shifted:
-            u_shift = colsum.mul_(1.0 / N)
-            collective.allReduce(u_shift, 'avg')
-            sb = K.dgemm(K.HFB_TN, K.to_padded(u_shift.unsqueeze(1), dev, pad=2), B)     # (1, m) = u^T B
-            K.subtract_row_(W, sb.reshape(-1).contiguous())
-            K.subtract_row_(Xt, u_shift)
-        else:
-            u_shift = torch.zeros(n, dtype=torch.float64, device=dev)
-        return Xt, W, u_shift
+        if not shifted:
+            return Xt, torch.zeros(n, dtype=torch.float64, device=dev), None, (W, Y)
+        mean_p = colsum.mul_(1.0 / N)                                        # mean of the stored rows X' (local)
+        u_shift = prov + mean_p                                              # local mean of the original rows
+        collective.allReduce(u_shift, 'avg')                                 # global mean (equal shard sizes)
+        delta = u_shift - prov                                               # what the stored rows still carry
+        sb = K.dgemm(K.HFB_TN, K.to_padded(delta.unsqueeze(1), dev, pad=2), B).reshape(-1).contiguous()   # delta^T B
+        cw = K.colsum(W, 1.0 / N)                                            # 1^T W' / N
+        K.subtract_row_(W, sb)
+        K.rank1_update_(Y, -1.0, mean_p, sb)
+        K.rank1_update_(Y, -1.0, delta, cw - sb)
+        return Xt, u_shift, delta, (W, Y)
 
-    def _randomized(self, Xt, Md, u_rank, oversampling, Omega, collective, faithful, first_W=None):
+    def _randomized(self, Xt, Md, u_rank, oversampling, Omega, collective, faithful, center=None, pre=None):
         n = Xt.shape[1]
         m = u_rank + oversampling
         Omega = self._resolve_omega(Omega, n, m)
         assert Omega.nvec() >= u_rank
-        cov = SampleCovariance(Xt)
+        cov = SampleCovariance(Xt, center=center)
         C = SampleCovarianceOperator(cov, collective, 'avg')
         A = SandwichedCovarianceOperator(C, Md)
         self.info = {}
         Q0 = None
-        if first_W is not None:
-            # range finder from the pre-computed projection: Q0 = avg_g (1/N_loc) X_g^T W_g  (= C M Omega)
-            Q0 = DeviceMultiVector(K.padded_empty(n, m, self.device))
-            C.lift_reduced(first_W, Q0)
+        if pre is not None:
+            # range finder already formed during the upload: Q0 = avg_g (1/N_loc) X~_g^T W~_g  (= C M Omega)
+            Q0 = DeviceMultiVector(pre[1])
+            collective.allReduce(Q0, 'avg')
         d, U = doublePassG(A, Md, None, Omega, u_rank, s=1, faithful=faithful, info=self.info, Q0=Q0)
         Mphi = Md.matmat(U.tensor())
-        return d, U.tensor(), Mphi
+        return d, U.tensor(), Mphi, cov.center_ratio
 
     # ---------------------------------------------------------------- method of snapshots ('hep' :812-833)
     def _snapshot_eig(self, Xt, Md, u_rank, method):

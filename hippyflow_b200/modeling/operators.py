@@ -12,7 +12,7 @@ from ..multivector import DeviceMultiVector, DeviceVector
 
 def _as_device_rows(data, device):
     """(rows, n) float64 array -> padded row-major device block (zero-copy if already conforming)."""
-    if isinstance(data, torch.Tensor) and data.is_cuda and data.dtype == torch.float64 and data.dim() == 2 \
+    if K.is_device_tensor(data) and data.dtype == torch.float64 and data.dim() == 2 \
             and data.stride(1) == 1 and K._ld(data) % 2 == 0 and data.data_ptr() % 16 == 0:
         return data
     return K.to_padded(data, device)
@@ -53,7 +53,7 @@ class SampleCovarianceOperator:
         scale = 1.0 / self.cov.nsamples
         size = self.collective.size()
         if size == 1 or not hasattr(self.collective, "allReduce_async") or n < 4096:
-            K.dgemm(K.HFB_TN, self.cov.Xt, GW, out=Yt, alpha=scale)
+            self.cov.lift(GW, out=Yt, scale=scale, weighted=True)
             self.collective.allReduce(Y, self.mpi_op)
             return
         if self.mpi_op.lower() == "avg":
@@ -65,7 +65,7 @@ class SampleCovarianceOperator:
         works = []
         for lo in range(0, n, step):
             hi = min(n, lo + step)
-            K.dgemm(K.HFB_TN, self.cov.Xt[:, lo:hi], GW, out=Yt[lo:hi], alpha=scale)
+            self.cov.lift(GW, out=Yt[lo:hi], scale=scale, weighted=True, rows=(lo, hi))
             works.append(self.collective.allReduce_async(full[lo:hi], "sum"))
         for w in works:
             w.wait()
@@ -144,7 +144,7 @@ class MeanJTJfromDataOperator:
             assert hasattr(noise_cov_inv, "__matmul__")
         self._noise_cov_inv = noise_cov_inv
         if device is None:
-            device = J.device if isinstance(J, torch.Tensor) and J.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            device = J.device if K.is_device_tensor(J) else torch.device("cuda", torch.cuda.current_device())
         J2 = J.reshape(self.ndata * self.r, self.dM)
         self._cov = SampleCovariance(_as_device_rows(J2, device), block=self.r,
                                      noise_cov_inv=None if noise_cov_inv is None else np.asarray(noise_cov_inv))
@@ -199,7 +199,7 @@ class JTJ:
 
     def __init__(self, J, device=None):
         if device is None:
-            device = J.device if isinstance(J, torch.Tensor) and J.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            device = J.device if K.is_device_tensor(J) else torch.device("cuda", torch.cuda.current_device())
         self._cov = SampleCovariance(_as_device_rows(J, device), block=J.shape[0])
         self.dM = J.shape[1]
 

@@ -12,7 +12,7 @@ from .operators import _as_device_rows
 def _dev(a, device):
     if hasattr(a, "tensor"):
         return a.tensor()
-    if isinstance(a, torch.Tensor) and a.is_cuda:
+    if K.is_device_tensor(a):
         return a if (a.dim() == 2 and a.stride(1) == 1 and K._ld(a) % 2 == 0 and a.data_ptr() % 16 == 0) else K.to_padded(a, device)
     return K.to_padded(np.asarray(a, dtype=np.float64), device)
 

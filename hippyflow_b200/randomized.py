@@ -17,7 +17,6 @@ import numpy as np
 
 from . import _lib as K
 import torch
-from scipy.linalg import blas as _blas
 
 from .linalg import b_orthonormalize, cleanup_factor, top_k_eig
 from .multivector import DeviceMultiVector
@@ -60,36 +59,33 @@ def _fetch_async(t):
 
 
 def _rayleigh_ritz(A, Q, BQ, k, gram, faithful):
-    """T = Q^T A Q, top-k eigenpairs, and the (m x k) coefficient matrix C with U = Q C.  ``gram`` is the device
-    Gram matrix of a basis whose clean-up pass was deferred (see linalg.b_orthonormalize)."""
+    """T = Q^T A Q, top-k eigenpairs, and the (m x k) DEVICE coefficient matrix C with U = Q C.  ``gram`` is the device
+    Gram matrix of a basis whose clean-up pass was deferred (see linalg.b_orthonormalize).  The only host arithmetic is
+    the Cholesky factor of ``gram`` (in the shadow of the pass-2 GEMM) and eigh(T), as in hIPPYlib; the small products
+    with the clean-up factor S2 run on the device (a 266^3 product costs ~20 us there, milliseconds on the host)."""
+    dev = Q.tensor().device
     if gram is not None:
         G1h, done = _fetch_async(gram)
+    Td = None
     if hasattr(A, "rayleigh_device") and not faithful:
         Td = A.rayleigh_device(Q, BQ)                          # big GEMM(s) queued: overlaps with the host work below
-        S2 = None
-        if gram is not None:
-            done.synchronize()
-            S2 = cleanup_factor(G1h.numpy())
-        T = Td.cpu().numpy()
     elif hasattr(A, "rayleigh") and not faithful:
-        S2 = None
-        if gram is not None:
-            done.synchronize()
-            S2 = cleanup_factor(G1h.numpy())
         T = A.rayleigh(Q, BQ)
     else:
         AQ = _block_apply(A, Q)
-        S2 = None
-        if gram is not None:
-            done.synchronize()
-            S2 = cleanup_factor(G1h.numpy())
         T = AQ.dot_mv(Q)
-    if S2 is not None:
-        # small host products through SciPy's BLAS (the same OpenBLAS instance as the LAPACK calls: mixing in NumPy's
-        # own BLAS thread pool for 266 x 266 operands was measured to cost > 200 ms per product on these hosts)
-        T = _blas.dgemm(1.0, S2, _blas.dgemm(1.0, np.asarray(T), S2), trans_a=1)
+    S2d = None
+    if gram is not None:
+        done.synchronize()
+        S2d = K.to_padded(cleanup_factor(G1h.numpy()), dev)
+        if Td is None:
+            Td = K.to_padded(np.ascontiguousarray(T), dev)
+        Td = K.dgemm(K.HFB_TN, S2d, K.dgemm(K.HFB_NN, Td, S2d))          # S2^T T S2
+    if Td is not None:
+        T = Td.cpu().numpy()
     d, V = top_k_eig(T, k)
-    return d, (V if S2 is None else _blas.dgemm(1.0, S2, V))
+    Vd = K.to_padded(V, dev)
+    return d, (Vd if S2d is None else K.dgemm(K.HFB_NN, S2d, Vd))
 
 
 def doublePass(A, Omega, k, s=1, faithful=False, info=None):
@@ -102,7 +98,7 @@ def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     Qt, _, oinfo = b_orthonormalize(Q.tensor(), None, return_BQ=False, defer_last=True)
     Q = DeviceMultiVector(Qt)
     d, C = _rayleigh_ritz(A, Q, Q, k, oinfo.pop("gram", None), faithful)
-    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), K.to_padded(C, Q.tensor().device)))
+    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), C))
     if info is not None:
         info.update(oinfo)
     return d, U
@@ -130,7 +126,7 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None, Q0=None):
     Qt, BQt, oinfo = b_orthonormalize(Q.tensor(), B, return_BQ=True, defer_last=True)
     Q, BQ = DeviceMultiVector(Qt), DeviceMultiVector(BQt)
     d, C = _rayleigh_ritz(A, Q, BQ, k, oinfo.pop("gram", None), faithful)
-    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), K.to_padded(C, Q.tensor().device)))
+    U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), C))
     if info is not None:
         info.update(oinfo)
     return d, U

@@ -1,0 +1,257 @@
+"""TEST DOUBLE (test infrastructure only -- nothing under hippyflow_b200/ imports this file).
+
+The product has no CPU path: every numerical call goes to libhfb200.so on a B200.  To exercise the HOST logic of the
+projector classes in the CPU test suite (which route is taken, the order of the products, the rank-one corrections of
+the mean shift, the deferred clean-up pass, chunk bookkeeping, collectives) this module swaps the thin wrappers of
+``hippyflow_b200._lib`` for plain torch/NumPy fp64 evaluations of the same operations and stubs the CUDA stream /
+event API with no-ops.  Numbers produced under the shim say nothing about the kernels; the `-m gpu` tests check those.
+"""
+import contextlib
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+
+class _FakeStream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _FakeEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return 0.0
+
+
+def _scipy_csr(rowptr, colind, val, ncols=None):
+    rp, ci, v = rowptr.numpy(), colind.numpy(), val.numpy()
+    n = rp.size - 1
+    return sp.csr_matrix((v, ci, rp), shape=(n, ncols if ncols is not None else n))
+
+
+def _decode_blobs(K, plan):
+    """Rebuild the sparse matrix from the TMA kernel's per-cluster blobs (checks the packing the kernel will read)."""
+    mr, mc, me = plan["max_rows"], plan["max_cols_cap"], plan["max_entries"]
+    stride = int(K.lib().hfb_csr_cluster_blob_stride(mr, mc, me))
+    blobs = plan["blobs"].numpy().reshape(-1, stride)
+    r4 = lambda x: (x + 3) // 4 * 4
+    off_rowoff = 16
+    off_outrow = off_rowoff + 4 * r4(mr + 1)
+    off_cols = off_outrow + 4 * r4(mr)
+    off_ent = off_cols + 4 * r4(mc)
+    rows, cols, vals = [], [], []
+    nmax = 0
+    for b in blobs:
+        nrow, ncol, nent = (int(x) for x in b[:12].view(np.int32))
+        ro = b[off_rowoff:off_rowoff + 4 * (nrow + 1)].view(np.int32)
+        orow = b[off_outrow:off_outrow + 4 * nrow].view(np.int32)
+        cl = b[off_cols:off_cols + 4 * ncol].view(np.int32)
+        e = b[off_ent:off_ent + 16 * nent].reshape(-1, 16)
+        v = e[:, :8].copy().view(np.float64).ravel()
+        l = e[:, 8:12].copy().view(np.int32).ravel()
+        cnt = np.diff(ro)
+        rows.append(np.repeat(orow, cnt))
+        cols.append(cl[l])
+        vals.append(v)
+        nmax = max(nmax, int(orow.max()) + 1)
+    n = plan["order"].numel()
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+
+
+def _decode_staged(plan):
+    order = plan["order"].numpy().astype(np.int64)
+    s_rowptr = plan["s_rowptr"].numpy().astype(np.int64)
+    ent = plan["entries"].numpy()
+    vals = ent[:, 0]
+    lcol = ent[:, 1].copy().view(np.int64)
+    cl_rowptr = plan["cl_rowptr"].numpy().astype(np.int64)
+    cl_colptr = plan["cl_colptr"].numpy().astype(np.int64)
+    cl_cols = plan["cl_cols"].numpy().astype(np.int64)
+    n = order.size
+    counts = np.diff(s_rowptr)
+    rows = np.repeat(order, counts)
+    cl_of_slot = np.repeat(np.arange(cl_rowptr.size - 1), np.diff(cl_rowptr))
+    cl_of_nnz = np.repeat(cl_of_slot, counts)
+    cols = cl_cols[cl_colptr[cl_of_nnz] + lcol]
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+
+
+@contextlib.contextmanager
+def emulated_device():
+    """Context manager: hippyflow_b200 runs on torch CPU tensors.  Yields the torch.device to pass as ``device=``."""
+    from hippyflow_b200 import _lib as K
+    saved_K = dict(K.__dict__)
+    saved_torch = {"current_stream": torch.cuda.current_stream, "Stream": torch.cuda.Stream, "Event": torch.cuda.Event,
+                   "stream": torch.cuda.stream, "synchronize": torch.cuda.synchronize,
+                   "current_device": torch.cuda.current_device}
+    saved_empty = torch.empty
+    had_record = "record_stream" in torch.Tensor.__dict__
+    saved_record = torch.Tensor.__dict__.get("record_stream")
+    counter = {"n": 0}
+    cache = {}
+
+    def out_or_new(out, rows, cols, dev):
+        return out if out is not None else K.padded_empty(rows, cols, dev)
+
+    def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumulate=False):
+        K._req(A, "A"), K._req(B, "B")
+        opA = A.t() if layout == K.HFB_TN else A
+        opB = B.t() if layout == K.HFB_NT else B
+        if opA.shape[1] != opB.shape[0]:
+            raise K.HfbError("dgemm: inner dimensions differ")
+        if A.data_ptr() % 16 or B.data_ptr() % 16 or K._ld(A) % 2 or K._ld(B) % 2:
+            raise K.HfbError("hfb_dgemm: operand not 16-byte aligned or odd leading dimension (code -2)")
+        R = alpha * (opA @ opB)
+        if symmetric and R.shape[0] == R.shape[1]:
+            R = torch.triu(R) + torch.triu(R, 1).t()
+        if accumulate:
+            if out is None or symmetric:
+                raise K.HfbError("dgemm: accumulate needs an existing out")
+            out.add_(R)
+            counter["n"] += 1
+            return out
+        fresh = out_or_new(out, R.shape[0], R.shape[1], A.device)
+        if tuple(fresh.shape) != tuple(R.shape):
+            raise K.HfbError("dgemm: out has shape %s, expected %s" % (tuple(fresh.shape), tuple(R.shape)))
+        fresh.copy_(R)
+        counter["n"] += 1
+        return fresh
+
+    def dgemm_batched_small(layout, A, B, out, alpha=1.0):
+        opA = A.transpose(1, 2) if layout == K.HFB_TN else A
+        out.copy_(alpha * torch.matmul(opA, B))
+        counter["n"] += 1
+        return out
+
+    def _spmm(Msp, B, out):
+        n, m = B.shape
+        res = torch.from_numpy(np.ascontiguousarray(Msp @ B.numpy()))
+        out = out_or_new(out, Msp.shape[0], m, B.device)
+        out.copy_(res)
+        counter["n"] += 1
+        return out
+
+    def csr_spmm(rowptr, colind, val, B, out=None, order=None):
+        return _spmm(_scipy_csr(rowptr, colind, val, B.shape[0]), B, out)
+
+    def csr_spmm_staged(plan, B, out=None):
+        key = ("staged", id(plan))
+        if key not in cache:
+            cache[key] = _decode_staged(plan)
+        return _spmm(cache[key], B, out)
+
+    def csr_spmm_tma(plan, B, out=None):
+        key = ("tma", id(plan))
+        if key not in cache:
+            cache[key] = _decode_blobs(K, plan)
+        return _spmm(cache[key], B, out)
+
+    def csr_spmm_rows(rowptr, colind, val, X, out=None):
+        Msp = _scipy_csr(rowptr, colind, val, X.shape[1])
+        res = torch.from_numpy(np.ascontiguousarray((Msp @ X.numpy().T).T))
+        out = out_or_new(out, X.shape[0], Msp.shape[0], X.device)
+        out.copy_(res)
+        counter["n"] += 1
+        return out
+
+    def coldot(X, Y):
+        counter["n"] += 1
+        return (X * Y).sum(0)
+
+    def rowdot(X, Y):
+        counter["n"] += 1
+        return (X * Y).sum(1)
+
+    def colscale_(X, s):
+        X.mul_(s.reshape(1, -1))
+        return X
+
+    def colsum(X, scale=1.0):
+        counter["n"] += 1
+        return scale * X.sum(0)
+
+    def subtract_row_(X, shift):
+        X.sub_(shift.reshape(1, -1))
+        counter["n"] += 1
+        return X
+
+    def rank1_update_(Y, a, x, y):
+        if x.numel() != Y.shape[0] or y.numel() != Y.shape[1]:
+            raise K.HfbError("rank1_update_: vector lengths do not match Y")
+        Y.add_(a * torch.outer(x, y))
+        counter["n"] += 1
+        return Y
+
+    def axpby_(a, X, b, Y):
+        Y.copy_(a * X + (b * Y if b != 0.0 else 0.0))
+        return Y
+
+    def axpby_cols_(a, X, b, Y):
+        av = a.reshape(1, -1) if a is not None else 1.0
+        bv = b.reshape(1, -1) if b is not None else 1.0
+        Y.copy_(av * X + bv * Y)
+        return Y
+
+    def rowscale(s, X, out=None):
+        out = out_or_new(out, X.shape[0], X.shape[1], X.device)
+        out.copy_(s.reshape(-1, 1) * X)
+        return out
+
+    def fill_random_(X, seed, row_offset=0, kind="normal"):
+        g = torch.Generator().manual_seed(int(seed) * 1000003 + int(row_offset))
+        X.copy_(torch.randn(X.shape, dtype=torch.float64, generator=g) if kind == "normal"
+                else torch.rand(X.shape, dtype=torch.float64, generator=g))
+        return X
+
+    def empty_nopin(*a, **k):
+        k.pop("pin_memory", None)
+        return saved_empty(*a, **k)
+
+    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_staged=csr_spmm_staged,
+                   csr_spmm_tma=csr_spmm_tma, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
+                   colsum=colsum, subtract_row_=subtract_row_, rank1_update_=rank1_update_, axpby_=axpby_,
+                   axpby_cols_=axpby_cols_, rowscale=rowscale, fill_random_=fill_random_,
+                   measure_dmma_peak=lambda device: 1.0, launch_count=lambda: counter["n"],
+                   is_device_tensor=lambda t: isinstance(t, torch.Tensor))
+    try:
+        for k, v in patches.items():
+            setattr(K, k, v)
+        torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+        torch.cuda.Stream = _FakeStream
+        torch.cuda.Event = _FakeEvent
+        torch.cuda.stream = lambda s: contextlib.nullcontext()
+        torch.cuda.synchronize = lambda *a, **k: None
+        torch.cuda.current_device = lambda: 0
+        torch.Tensor.record_stream = lambda self, s: None
+        torch.empty = empty_nopin
+        yield torch.device("cpu")
+    finally:
+        for k in patches:
+            setattr(K, k, saved_K[k])
+        for k, v in saved_torch.items():
+            setattr(torch.cuda, k, v)
+        torch.empty = saved_empty
+        if had_record:
+            torch.Tensor.record_stream = saved_record
+        else:
+            del torch.Tensor.record_stream

@@ -416,3 +416,75 @@ def test_jacobian_truncated_svd_vs_numpy(hf, cuda_device, golden_jtj):
         ref = (u0[:, :10] * s0[:10]) @ vt0[:10]
         assert np.linalg.norm(rec - ref) / np.linalg.norm(ref) < 1e-8
         np.testing.assert_allclose(V[i].T @ V[i], np.eye(10), atol=1e-8)
+
+
+# ------------------------------------------------------------------ mean shift: implicit / pipelined / explicit routes
+def _blocked_weighted_pod(u, M, Om, rank):
+    """Blocked NumPy evaluation of the M-weighted double pass on explicitly shifted data (the reference's
+    u_data - np.mean(u_data, axis=0), PODProjector.py:732-734)."""
+    X = u - u.mean(0)
+    Y = X.T @ (X @ (M @ Om)) / X.shape[0]
+    Q = Y
+    for _ in range(2):
+        G = Q.T @ (M @ Q)
+        w, V = np.linalg.eigh((G + G.T) / 2)
+        Q = Q @ (V / np.sqrt(w))
+    W = X @ (M @ Q)
+    dd, VV = np.linalg.eigh(W.T @ W / X.shape[0])
+    return dd[::-1][:rank], Q @ VV[:, ::-1][:, :rank]
+
+
+@pytest.mark.parametrize("mean_scale", [0.0, 30.0])
+@pytest.mark.parametrize("route", ["pipelined", "resident_implicit", "resident_explicit", "host_unpipelined"])
+def test_pod_randomized_mean_shift_routes(hf, cuda_device, route, mean_scale):
+    """All routes of the mean shift give the reference's eigenpairs, also when the mean is 30x larger than the
+    fluctuations: (i) host input, upload pipelined in 4 chunks with a provisional mean and the lift accumulated per
+    chunk; (ii) device-resident input, shift applied inside the products (input array must stay untouched);
+    (iii) device-resident input shifted explicitly on a copy; (iv) host input without the pipelined upload."""
+    from hippyflow_b200 import _lib as K
+    nx = 64
+    M = syn.p1_mass_matrix(nx)
+    n = M.shape[0]
+    N, rank = 1024, 32
+    u = syn.snapshots(n, N, r0=96, decay=1.0, eps=1e-6, seed=5)
+    rms = np.sqrt(np.mean(u ** 2))
+    u = u + mean_scale * rms * (1.0 + 0.3 * np.sin(np.arange(n) * 0.01))[None, :]
+    Om = syn.gaussian_omega(n, rank + 10, seed=6)
+    d0, U0 = _blocked_weighted_pod(u, M, Om, rank)
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    if route == "pipelined":
+        d, phi, Mphi, shift = proj.construct_subspace(u.copy(), rank, shifted=True, method="randomized", Omega=Om)
+    elif route == "host_unpipelined":
+        d, phi, Mphi, shift = proj.construct_subspace(u.copy(), rank, shifted=True, method="randomized", Omega=Om,
+                                                      pipelined_upload=False)
+    else:
+        ud = K.to_padded(u, cuda_device)
+        keep = ud.clone()
+        d, phi, Mphi, shift = proj.construct_subspace(ud, rank, shifted=True, method="randomized", Omega=Om,
+                                                      implicit_shift=(route == "resident_implicit"))
+        assert torch.equal(ud, keep)                       # the caller's device array is never modified
+        assert proj.shift_route == ('implicit' if route == "resident_implicit" else 'explicit')
+    np.testing.assert_allclose(d, d0, rtol=EIG_RTOL)
+    k = leading(d0)
+    assert subspace_angle(phi[:, :k], U0[:, :k], M) < ANGLE_TOL
+    np.testing.assert_allclose(shift, u.mean(0), rtol=1e-13, atol=1e-14 * max(1.0, mean_scale))
+    assert np.linalg.norm(phi.T @ Mphi - np.eye(rank)) < 1e-10
+
+
+def test_pod_randomized_dominant_mean_falls_back_to_explicit_shift(hf, cuda_device):
+    """|mean| = 1e5 x fluctuations: (|mean|/rms)^2 = 1e10 is above IMPLICIT_SHIFT_MAX_RATIO, the implicit route must hand
+    over to the explicit shift and still resolve the fluctuation eigenpairs."""
+    from hippyflow_b200 import _lib as K
+    M = syn.p1_mass_matrix(64)
+    n = M.shape[0]
+    u = syn.snapshots(n, 512, r0=64, decay=1.0, eps=1e-6, seed=8)
+    u = u + 1.0e5 * np.sqrt(np.mean(u ** 2))
+    Om = syn.gaussian_omega(n, 26, seed=9)
+    d0, U0 = _blocked_weighted_pod(u, M, Om, 16)
+    proj = hf.PODProjectorFromData(None, M_output=M, device=cuda_device)
+    ud = K.to_padded(u, cuda_device)
+    d, phi, Mphi, shift = proj.construct_subspace(ud, 16, shifted=True, method="randomized", Omega=Om)
+    # the data themselves carry only ~11 digits of the fluctuations here (eps * 1e5), so the comparison is looser
+    assert proj.shift_route == 'explicit-fallback'
+    np.testing.assert_allclose(d, d0, rtol=1e-7)
+    assert subspace_angle(phi[:, :8], U0[:, :8], M) < 1e-6
