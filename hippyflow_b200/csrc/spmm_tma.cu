@@ -24,7 +24,7 @@ namespace hfb {
 
 constexpr int V4_CONSUMER_WARPS = 16;
 constexpr int V4_THREADS = (V4_CONSUMER_WARPS + 1) * 32;
-constexpr int V4_MAX_STAGES = 4;
+constexpr int V4_MAX_STAGES = 8;
 constexpr int V4_SMEM_BUDGET = 232448 - 128;  // opt-in dynamic shared memory per CTA minus the barrier block
 
 struct SpmmBlobLayout {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1)
             // does not always land on the same warps (warps run up to nstages - 1 stages apart)
             const int wslot = (warp + it * 5) % V4_CONSUMER_WARPS;
             for (int f = wslot * 32 + lane; f < total; f += V4_CONSUMER_WARPS * 32) {
-                const int r = (int)__umulhi((unsigned)f, magic);
+                const int r = (U == 1) ? f : (int)__umulhi((unsigned)f, magic);  // f / U (exact for f, U < 2^16)
                 const int u = f - r * U;
                 const int beg = sRowoff[r], end = sRowoff[r + 1];
                 const uint32_t bcol = sB_addr + (uint32_t)u * 16u;

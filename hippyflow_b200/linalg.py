@@ -36,7 +36,9 @@ class CsrMatrix:
         self.order = None
         self.plan = None
         import os
-        self.impl = os.environ.get("HFB_SPMM_IMPL", "tma")       # "tma" (persistent, cp.async.bulk ring) | "staged" (cp.async panels)
+        # "staged": cp.async panels, default (measured faster); "tma": persistent CTAs fed by cp.async.bulk row copies --
+        # its ring stays empty because the TMA engine completes ~1-KB row copies at only ~10 B/clk/SM (profiles/)
+        self.impl = os.environ.get("HFB_SPMM_IMPL", "staged")
         if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
             try:
                 self.plan = self._build_plan(M, device)
@@ -47,10 +49,11 @@ class CsrMatrix:
     @staticmethod
     def _build_plan(M, device, max_rows=None, max_cols=None):
         import os
-        # (32, 64) measured best on B200 (cfg2: 0.39 ms; (48, 96): 0.46 ms; (64, 128): 0.73 ms): smaller clusters keep
-        # three CTAs with double-buffered panels resident per SM
-        max_rows = int(os.environ.get("HFB_SPMM_ROWS", 32)) if max_rows is None else max_rows
-        max_cols = int(os.environ.get("HFB_SPMM_COLS", 64)) if max_cols is None else max_cols
+        # (16, 32) measured best on B200 for the panel kernel (cfg2, m = 266: 0.343 ms = 51 % of the HBM copy rate;
+        # (24, 48): 0.358, (32, 64): 0.389, (12, 24): 0.402, (64, 128): 0.73 ms): small clusters keep many CTAs with
+        # double-buffered panels resident per SM; the halo re-reads they add are served by L2
+        max_rows = int(os.environ.get("HFB_SPMM_ROWS", 16)) if max_rows is None else max_rows
+        max_cols = int(os.environ.get("HFB_SPMM_COLS", 32)) if max_cols is None else max_cols
         indptr, indices, data = np.asarray(M.indptr, dtype=np.int64), np.asarray(M.indices, dtype=np.int64), np.asarray(M.data)
         order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, max_rows, max_cols)
         n = M.shape[0]
@@ -78,11 +81,18 @@ class CsrMatrix:
                 "cl_rowptr": t(cptr, np.int32), "order": t(order, np.int32), "s_rowptr": t(s_rowptr, np.int32),
                 "entries": torch.as_tensor(ent, device=device), "cl_colptr": t(cl_colptr, np.int32),
                 "cl_cols": t(ukey % n, np.int32)}
-        # blobs of the persistent TMA-fed kernel (one fixed-stride record per cluster, packed on the host in C)
+        # the persistent TMA-fed kernel reads one fixed-stride record per cluster, packed on first use (_tma_blobs)
         plan["max_rows"] = int(np.diff(cptr).max())
         plan["max_cols_cap"] = plan["max_cols"]
-        plan["blobs"] = torch.as_tensor(K.csr_pack_clusters(M.indptr, M.indices, M.data, order, cptr, plan["max_rows"],
-                                                            plan["max_cols_cap"], max_entries), device=device)
+        plan["_host"] = (M.indptr, M.indices, M.data, order, cptr)
+        return plan
+
+    @staticmethod
+    def _tma_blobs(plan, device):
+        if "blobs" not in plan:
+            indptr, indices, data, order, cptr = plan["_host"]
+            plan["blobs"] = torch.as_tensor(K.csr_pack_clusters(indptr, indices, data, order, cptr, plan["max_rows"],
+                                                                plan["max_cols_cap"], plan["max_entries"]), device=device)
         return plan
 
     def matmat(self, B, out=None):
@@ -90,7 +100,7 @@ class CsrMatrix:
         if self.plan is not None and B.shape[1] >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
             if self.impl == "tma" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1):
-                return K.csr_spmm_tma(self.plan, B, out)
+                return K.csr_spmm_tma(self._tma_blobs(self.plan, self.device), B, out)
             return K.csr_spmm_staged(self.plan, B, out)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order)
 

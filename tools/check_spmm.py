@@ -1,17 +1,50 @@
-import sys, time, os
+"""SpMM micro-benchmark: the persistent TMA-fed kernel vs the cp.async panel kernel at the benchmark shapes, for a few
+cluster caps.  Usage (GPU box): python tools/check_spmm.py [--quick]"""
+import sys
 sys.path.insert(0, ".")
-import numpy as np, torch
+import numpy as np
+import torch
 from hippyflow_b200 import _lib as K, synthetic as syn
 from hippyflow_b200.linalg import CsrMatrix
+
 dev = torch.device("cuda:0")
-for n, m in ((263169, 266), (1002001, 266), (251001, 138), (263169, 25)):
-    M = syn.p1_mass_matrix_for(n); Md = CsrMatrix(M, dev)
-    B = K.padded_empty(n, m, dev).normal_(); C = K.padded_empty(n, m, dev)
-    for _ in range(3): Md.matmat(B, out=C)
-    torch.cuda.synchronize(); best = 1e9
-    for _ in range(10):
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); Md.matmat(B, out=C); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1))
-    by = Md.spmm_bytes(m)
-    ref = torch.sparse_csr_tensor(Md.rowptr.long(), Md.colind.long(), Md.val, size=M.shape) @ B.contiguous()
-    print(f"n={n} m={m}: {best:.3f} ms {by/best/1e6:.0f} GB/s ({by/best/1e6/6552.3*100:.1f}% of HBM peak) err {float((C-ref).abs().max()):.2e}", flush=True)
+PEAK = 6542.1   # MEASURED_PEAKS.json hbm_gbs
+quick = "--quick" in sys.argv
+shapes = ((263169, 266),) if quick else ((263169, 266), (1002001, 266), (251001, 138))
+caps = ((32, 64),) if quick else ((32, 64), (24, 48), (16, 32), (12, 24), (8, 16))
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+for n, m in shapes:
+    M = syn.p1_mass_matrix_for(n)
+    B = K.padded_empty(n, m, dev).normal_()
+    C = K.padded_empty(n, m, dev)
+    ref = None
+    for rows, cols in caps:
+        Md = CsrMatrix(M, dev, cluster_rows=False)
+        Md.plan = CsrMatrix._build_plan(M.tocsr(), dev, max_rows=rows, max_cols=cols)
+        Md.order = Md.plan["order"]
+        if ref is None:
+            ref = torch.sparse_csr_tensor(Md.rowptr.long(), Md.colind.long(), Md.val, size=M.shape) @ B.contiguous()
+        for impl in ("tma", "staged"):
+            Md.impl = impl
+            try:
+                t = timeit(lambda: Md.matmat(B, out=C))
+            except Exception as e:   # e.g. shared-memory budget of the panel kernel at large caps
+                print(f"n={n} m={m} caps=({rows},{cols}) {impl}: {type(e).__name__}: {e}", flush=True)
+                continue
+            by = Md.spmm_bytes(m)
+            err = float((C - ref).abs().max())
+            print(f"n={n} m={m} caps=({rows},{cols}) clusters={Md.plan['nclusters']} {impl}: {t:.3f} ms "
+                  f"{by / t / 1e6:.0f} GB/s ({by / t / 1e6 / PEAK * 100:.1f}% of HBM peak) err {err:.2e}", flush=True)
