@@ -66,6 +66,7 @@ def lib():
         "hfb_colscale": (i32, [i64, i64, vp, i64, vp, vp]),
         "hfb_colmean_workspace_bytes": (sz, [i64, i64]),
         "hfb_colsum": (i32, [i64, i64, vp, i64, dbl, vp, vp, sz, vp]),
+        "hfb_colsum_weighted": (i32, [i64, i64, vp, i64, vp, dbl, vp, vp, sz, vp]),
         "hfb_subtract_row": (i32, [i64, i64, vp, i64, vp, vp]),
         "hfb_rank1_update": (i32, [i64, i64, dbl, vp, vp, vp, i64, vp]),
         "hfb_axpby": (i32, [i64, i64, dbl, vp, i64, dbl, vp, i64, vp]),
@@ -88,7 +89,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
             "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
-            "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_subtract_row",
+            "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
             "hfb_measure_dmma_peak"]
 
@@ -358,15 +359,22 @@ def colscale_(X, s):
     return X
 
 
-def colsum(X, scale=1.0):
-    """scale * sum over rows (samples) of X -> vector of length X.shape[1]."""
+def colsum(X, scale=1.0, weights=None):
+    """scale * sum over rows (samples) of X -> vector of length X.shape[1]; with ``weights`` (device vector of length
+    X.shape[0]) the rows are weighted: scale * weights^T X."""
     L = lib()
     _req(X, "X")
     N, n = X.shape
     out = torch.empty(n, dtype=torch.float64, device=X.device)
     nbytes = L.hfb_colmean_workspace_bytes(N, n)
     ws = workspace(nbytes, X.device)
-    rc = L.hfb_colsum(N, n, X.data_ptr(), _ld(X), float(scale), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    if weights is not None:
+        if weights.numel() != N or not weights.is_contiguous():
+            raise HfbError("colsum: weights must be a contiguous vector with one entry per row")
+        rc = L.hfb_colsum_weighted(N, n, X.data_ptr(), _ld(X), weights.data_ptr(), float(scale), out.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream())
+    else:
+        rc = L.hfb_colsum(N, n, X.data_ptr(), _ld(X), float(scale), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _check(rc, "hfb_colsum")
     return out
 

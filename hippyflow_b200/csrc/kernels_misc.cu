@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(256) csr_spmm_rows_kernel(long long nsamples, 
 // stage 1: block b sums rows [b*rows_per_block, ...) of X.*Y (or X) per column into part[b][col]
 __global__ void __launch_bounds__(256) colreduce_stage1(long long nrows, long long ncols, const double* __restrict__ X,
                                                         long long ldx, const double* __restrict__ Y, long long ldy,
-                                                        long long rows_per_block, double* __restrict__ part) {
+                                                        long long rows_per_block, double* __restrict__ part,
+                                                        const double* __restrict__ wrow) {
     const long long col = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (col >= ncols) return;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -274,7 +275,15 @@ __global__ void __launch_bounds__(256) colreduce_stage1(long long nrows, long lo
     if (r1 > nrows) r1 = nrows;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     long long r = r0;
-    if (Y) {
+    if (wrow) {  // row-weighted column sums: sum_r w[r] X[r, col]  (w^T X, e.g. mean^T (M Omega))
+        for (; r + 3 < r1; r += 4) {
+            s0 = fma(__ldg(wrow + r), X[r * ldx + col], s0);
+            s1 = fma(__ldg(wrow + r + 1), X[(r + 1) * ldx + col], s1);
+            s2 = fma(__ldg(wrow + r + 2), X[(r + 2) * ldx + col], s2);
+            s3 = fma(__ldg(wrow + r + 3), X[(r + 3) * ldx + col], s3);
+        }
+        for (; r < r1; ++r) s0 = fma(__ldg(wrow + r), X[r * ldx + col], s0);
+    } else if (Y) {
         for (; r + 3 < r1; r += 4) {
             s0 = fma(X[r * ldx + col], Y[r * ldy + col], s0);
             s1 = fma(X[(r + 1) * ldx + col], Y[(r + 1) * ldy + col], s1);
@@ -816,7 +825,7 @@ extern "C" int hfb_coldot(int64_t n, int64_t m, const double* X, int64_t ldx, co
     if (!workspace || workspace_bytes < (size_t)parts * (size_t)m * 8) return HFB_E_WORKSPACE;
     const long long rpb = (n + parts - 1) / parts;
     dim3 grid((unsigned)((m + 255) / 256), (unsigned)parts);
-    colreduce_stage1<<<grid, 256, 0, stream>>>(n, m, X, ldx, Y, ldy, rpb, (double*)workspace);
+    colreduce_stage1<<<grid, 256, 0, stream>>>(n, m, X, ldx, Y, ldy, rpb, (double*)workspace, nullptr);
     HFB_LAUNCHED();
     colreduce_stage2<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(m, parts, (const double*)workspace, 1.0, out);
     HFB_LAUNCHED();
@@ -835,7 +844,22 @@ extern "C" int hfb_colsum(int64_t N, int64_t n, const double* X, int64_t ldx, do
     if (!workspace || workspace_bytes < (size_t)parts * (size_t)n * 8) return HFB_E_WORKSPACE;
     const long long rpb = (N + parts - 1) / parts;
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)parts);
-    colreduce_stage1<<<grid, 256, 0, stream>>>(N, n, X, ldx, nullptr, 0, rpb, (double*)workspace);
+    colreduce_stage1<<<grid, 256, 0, stream>>>(N, n, X, ldx, nullptr, 0, rpb, (double*)workspace, nullptr);
+    HFB_LAUNCHED();
+    colreduce_stage2<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, parts, (const double*)workspace, scale, out);
+    HFB_LAUNCHED();
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_colsum_weighted(int64_t N, int64_t n, const double* X, int64_t ldx, const double* w, double scale,
+                                   double* out, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N <= 0 || n <= 0 || !X || !w || !out || ldx < n) return HFB_E_BADARG;
+    const int parts = reduce_parts(N, n);
+    if (!workspace || workspace_bytes < (size_t)parts * (size_t)n * 8) return HFB_E_WORKSPACE;
+    const long long rpb = (N + parts - 1) / parts;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)parts);
+    colreduce_stage1<<<grid, 256, 0, stream>>>(N, n, X, ldx, nullptr, 0, rpb, (double*)workspace, w);
     HFB_LAUNCHED();
     colreduce_stage2<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, parts, (const double*)workspace, scale, out);
     HFB_LAUNCHED();

@@ -147,7 +147,6 @@ class SampleCovariance:
         if center is not None:
             assert self.noise_cov_inv is None and self.block == 1, "implicit centering is for snapshot rows"
             self.center = center.contiguous()
-            self._center_col = K.to_padded(self.center.unsqueeze(1), Xt.device, pad=2)     # (n, 1): A operand of c^T B
 
     def _wbuf(self, m):
         if self._W is None or self._W.shape[1] != m:
@@ -164,7 +163,7 @@ class SampleCovariance:
             B = K.to_padded(B, B.device)      # e.g. one column of a multivector block: stage into a TMA-aligned buffer
         K.dgemm(K.HFB_NN, self.Xt, B, out=W)
         if self.center is not None:
-            sb = K.dgemm(K.HFB_TN, self._center_col, B).reshape(-1).contiguous()      # c^T B  (m,)
+            sb = K.colsum(B, 1.0, weights=self.center)                                # c^T B  (m,), one sweep over B
             K.subtract_row_(W, sb)
             if self.center_ratio is None:
                 self.center_ratio = self.rows * torch.dot(sb, sb) / torch.clamp_min(K.coldot(W, W).sum(), 1e-300)

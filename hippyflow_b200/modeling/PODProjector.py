@@ -285,7 +285,7 @@ class PODProjectorFromData:
         u_shift = prov + mean_p                                              # local mean of the original rows
         collective.allReduce(u_shift, 'avg')                                 # global mean (equal shard sizes)
         delta = u_shift - prov                                               # what the stored rows still carry
-        sb = K.dgemm(K.HFB_TN, K.to_padded(delta.unsqueeze(1), dev, pad=2), B).reshape(-1).contiguous()   # delta^T B
+        sb = K.colsum(B, 1.0, weights=delta)                                 # delta^T B
         cw = K.colsum(W, 1.0 / N)                                            # 1^T W' / N
         K.subtract_row_(W, sb)
         K.rank1_update_(Y, -1.0, mean_p, sb)

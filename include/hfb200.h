@@ -154,6 +154,10 @@ int hfb_colscale(int64_t n, int64_t m, double* X, int64_t ldx, const double* s, 
 size_t hfb_colmean_workspace_bytes(int64_t N, int64_t n);
 int hfb_colsum(int64_t N, int64_t n, const double* X, int64_t ldx, double scale, double* out,
                void* workspace, size_t workspace_bytes, void* stream);
+/* out[j] = scale * sum_i w[i] X[i,j]  (w^T X): the row vector u_shift^T (M Omega) of the implicit mean shift; same
+ * two-stage deterministic reduction and workspace as hfb_colsum. */
+int hfb_colsum_weighted(int64_t N, int64_t n, const double* X, int64_t ldx, const double* w, double scale, double* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
 /* X[i,j] -= shift[j]  (u_data - u_shift, PODProjector.py:734). */
 int hfb_subtract_row(int64_t N, int64_t n, double* X, int64_t ldx, const double* shift, void* stream);
 

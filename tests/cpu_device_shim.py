@@ -186,8 +186,12 @@ def emulated_device():
         X.mul_(s.reshape(1, -1))
         return X
 
-    def colsum(X, scale=1.0):
+    def colsum(X, scale=1.0, weights=None):
         counter["n"] += 1
+        if weights is not None:
+            if weights.numel() != X.shape[0]:
+                raise K.HfbError("colsum: weights must be a contiguous vector with one entry per row")
+            return scale * (weights.reshape(1, -1) @ X).reshape(-1)
         return scale * X.sum(0)
 
     def subtract_row_(X, shift):

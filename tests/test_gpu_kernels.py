@@ -137,8 +137,14 @@ def test_column_kernels(K, cuda_device):
     Xd, Yd = K.to_padded(X, cuda_device), K.to_padded(Y, cuda_device)
     np.testing.assert_allclose(K.coldot(Xd, Yd).cpu().numpy(), np.einsum("ij,ij->j", X, Y), rtol=1e-13)
     np.testing.assert_allclose(K.colsum(Xd, 0.25).cpu().numpy(), 0.25 * X.sum(0), rtol=1e-12, atol=1e-14)
+    w = rng.standard_normal(1000)
+    np.testing.assert_allclose(K.colsum(Xd, 0.5, weights=torch.as_tensor(w, device=cuda_device)).cpu().numpy(),
+                               0.5 * (w @ X), rtol=1e-12, atol=1e-13)
     s = rng.standard_normal(37)
     sd = torch.as_tensor(s, device=cuda_device)
+    Z = Xd.clone()
+    K.rank1_update_(Z, -0.75, torch.as_tensor(w, device=cuda_device), sd)
+    np.testing.assert_allclose(Z.cpu().numpy(), X - 0.75 * np.outer(w, s), rtol=1e-14, atol=1e-15)
     Z = Xd.clone()
     K.colscale_(Z, sd)
     np.testing.assert_allclose(Z.cpu().numpy(), X * s, rtol=1e-15)
