@@ -11,6 +11,42 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def sharded_mean_shift_case(hf, dev, coll, rank, world):
+    """Sample-sharded weighted POD with a mean 20x the fluctuations, 1024 rows per rank (upload in 4 chunks with a
+    per-rank provisional mean + per-chunk lift) and the device-resident implicit shift: both must give the eigenpairs
+    of the explicitly shifted full data set."""
+    from hippyflow_b200 import _lib as K, synthetic as syn
+    M = syn.p1_mass_matrix(64)            # 4225 dofs: the lift runs in row blocks with asynchronous allreduces
+    n = M.shape[0]
+    per = 1024
+    u = syn.snapshots(n, per * world, r0=64, decay=1.0, eps=1e-6, seed=31)
+    u = u + 20.0 * np.sqrt(np.mean(u ** 2)) * (1.0 + 0.5 * np.cos(np.arange(n) * 0.02))[None, :]
+    # make the shards statistically different so that the per-rank provisional means differ from the global mean
+    u[per:] *= 1.5
+    Om = syn.gaussian_omega(n, 34, seed=32)
+    X = u - u.mean(0)
+    Y = X.T @ (X @ (M @ Om)) / X.shape[0]
+    Q = Y
+    for _ in range(2):
+        G = Q.T @ (M @ Q)
+        w, V = np.linalg.eigh((G + G.T) / 2)
+        Q = Q @ (V / np.sqrt(w))
+    W = X @ (M @ Q)
+    dd, VV = np.linalg.eigh(W.T @ W / X.shape[0])
+    d0, U0 = dd[::-1][:24], Q @ VV[:, ::-1][:, :24]
+    k = int(np.sum(d0 / d0[0] > 1e-5))
+    shard = u[rank * per:(rank + 1) * per]
+    proj = hf.PODProjectorFromData(None, M_output=M, device=dev)
+    for entry in ("host", "resident"):
+        data = shard.copy() if entry == "host" else K.to_padded(shard, dev)
+        d, phi, Mphi, shift = proj.construct_subspace(data, 24, shifted=True, method="randomized", Omega=Om, collective=coll)
+        assert proj.shift_route == ("pipelined" if entry == "host" else "implicit")
+        np.testing.assert_allclose(d, d0, rtol=1e-10)
+        from oracle import projectors_np as P
+        assert P.principal_angle(phi[:, :k], U0[:, :k], M) < 1e-8
+        np.testing.assert_allclose(shift, u.mean(0), rtol=1e-13)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -84,6 +120,8 @@ def main():
     Xd = hf._lib.to_padded(ub[rank * 32:(rank + 1) * 32], dev)
     db2, _, _, _ = pb.construct_subspace(Xd, 8, shifted=True, method="randomized", Omega=Omb, collective=coll)
     np.testing.assert_allclose(db2, db0, rtol=1e-10)
+
+    sharded_mean_shift_case(hf, dev, coll, rank, world)
 
     # collective on device blocks: one NCCL call for the whole padded block, 'avg' = sum / size
     mv = hf.DeviceMultiVector(50, 7, device=dev)

@@ -98,6 +98,40 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _shim_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import hippyflow_b200 as hf
+        from cpu_device_shim import emulated_device
+        from multigpu_worker import sharded_mean_shift_case
+        with emulated_device() as dev:
+            sharded_mean_shift_case(hf, dev, hf.MultipleSerialPDEsCollective(), rank, world)
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_mean_shift_host_logic_gloo_world2():
+    """The N > 1 host logic of the weighted randomized POD (per-rank provisional means, global mean allreduce, rank-one
+    corrections, sketch allreduce) over a world_size-2 gloo group, kernels replaced by the CPU test double."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shim_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == {0: "ok", 1: "ok"}
+
+
 def test_torch_collective_gloo_world2():
     world = 2
     ctx = mp.get_context("spawn")
