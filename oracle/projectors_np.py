@@ -181,6 +181,33 @@ def pod_randomized_weighted(u_data, M_csr, u_rank, Omega, shifted=True, ranks=1)
     return d, U.to_dense(), enc.to_dense(), u_shift
 
 
+def pod_randomized_weighted_blocked(u_data, M_csr, u_rank, Omega, shifted=True):
+    """Best-effort CPU evaluation of the same M-weighted double pass with every operator apply done on the whole
+    (n x m) block at once (BLAS-3 instead of the reference's column-by-column hp.MatMvMult loop) and the
+    M-orthonormalisation done by two eigen-based Cholesky-QR sweeps instead of MGS.  d and span(decoder) agree with
+    ``pod_randomized_weighted`` (they do not depend on the choice of M-orthonormal basis of the sketch).  Used as the
+    "fair" CPU baseline of SURVEY.md 8(d) next to the faithful column-by-column port."""
+    if shifted:
+        u_shift = np.mean(u_data, axis=0)
+        X = u_data - u_shift
+    else:
+        u_shift = np.zeros(u_data.shape[1])
+        X = u_data
+    N = X.shape[0]
+    Q = X.T @ (X @ (M_csr @ Omega)) / N                  # M^-1 A Omega = C M Omega
+    for _ in range(2):
+        G = Q.T @ (M_csr @ Q)
+        w, V = np.linalg.eigh(0.5 * (G + G.T))
+        keep = w > w.max() * Q.shape[1] * np.finfo(float).eps        # a rank-deficient sketch keeps its range only
+        Q = Q @ (V * np.where(keep, 1.0 / np.sqrt(np.where(keep, w, 1.0)), 0.0))
+    W = X @ (M_csr @ Q)
+    T = W.T @ W / N                                      # Q^T A Q
+    dd, VV = np.linalg.eigh(0.5 * (T + T.T))
+    d = dd[::-1][:u_rank]
+    U = Q @ VV[:, ::-1][:, :u_rank]
+    return d, U, M_csr @ U, u_shift
+
+
 def pod_randomized(u_data, rank, Omega, ranks=1):
     """PODProjector.construct_subspace, PODProjector.py:359-376: LowRankOperator(ones/N_loc, U_loc)
     per rank, CollectiveOperator(..., 'avg'), doublePass(s=1).  No weighting, no shift."""
