@@ -236,6 +236,7 @@ def run_ours(args):
     if sampler is not None:
         sampler.mark()
     launches0 = K.launch_count()
+    segs0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     K.start_timing()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -246,6 +247,7 @@ def run_ours(args):
     barrier()
     gemm_times = K.stop_timing()
     launches = K.launch_count() - launches0
+    new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - segs0     # cudaMalloc calls while timing
     clocks = sampler.stop() if sampler is not None else None
     elapsed = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -335,7 +337,8 @@ def run_ours(args):
                            "samples_total": N, "rank": k, "oversampling": p, "parallelism": "sample-sharded x%d" % world,
                            "flops_per_step": flops_short(n, N, m), "flop_accounting": "6 n N m + 2 N m^2 (executed GEMM work)",
                            "l2": "inputs (%.1f GB/GPU) exceed L2" % (n_loc * n * 8 / 1e9)},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "cuda_mallocs_in_timed_region": int(new_segments), "clocks": clocks,
                 "eigenvalues_head": [float(x) for x in d_last[:3]]}
         print(json.dumps(line))
     if world > 1:
