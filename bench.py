@@ -199,6 +199,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound = None
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    if os.environ.get("HFB_BIND_NUMA", "1") != "0":
+        from hippyflow_b200.utilities import bind_to_gpu_numa_node
+        bound = bind_to_gpu_numa_node(local_rank)      # pinned staging buffers are first-touched on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -317,12 +322,15 @@ def run_ours(args):
         e2e = {"value": flops_short(n, N, m) / t_e2e * 1e-12, "unit": "TFLOP/s", "ms_per_step": t_e2e * 1e3,
                "h2d_bytes_per_step": int(world * n_loc * n * 8),
                "d2h_bytes_per_step": int(world * (2 * n * k + n + k) * 8), "steps": n_e2e,
-               "api": "PODProjectorFromData.construct_subspace(host array, method='randomized') -> NumPy (d, phi, Mphi, u_shift)"}
+               "api": "PODProjectorFromData.construct_subspace(host array, method='randomized') -> NumPy (d, phi, Mphi, u_shift)",
+               "host_cpus_bound": (len(bound) if bound else None)}
         del host
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if bound and full_affinity:
+            os.sched_setaffinity(0, full_affinity)      # the CPU baseline may use every host core
         s = CPU_SAMPLE
         t, _ = cpu_reference_step(s)
         cpu = {"value": flops_faithful(s["n"], s["N"], s["rank"] + s["oversampling"]) / t * 1e-12, "unit": "TFLOP/s",
