@@ -61,6 +61,36 @@ def test_dgemm_linearity_at_config2_width(K, cuda_device):
     assert rel(Y, A.t() @ lhs) < 1e-13
 
 
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("splits", [0, 1, 3])
+def test_dgemm_accumulate_flag(K, cuda_device, layout, splits):
+    """HFB_GEMM_ACCUMULATE: C += alpha op(A) op(B), in the epilogue (one split) and in the split-K reduce (several);
+    the chunked lift Y += X_c^T W_c of the pipelined upload relies on it."""
+    for (M, N, Kd) in ((300, 266, 700), (129, 25, 4100), (64, 138, 33)):
+        g = torch.Generator(device="cpu").manual_seed(M + N + Kd + splits)
+        A = torch.randn(M, Kd, dtype=torch.float64, generator=g).to(cuda_device)
+        B = torch.randn(Kd, N, dtype=torch.float64, generator=g).to(cuda_device)
+        C0 = torch.randn(M, N, dtype=torch.float64, generator=g).to(cuda_device)
+        Ad = K.to_padded(A.t().contiguous() if layout == K.HFB_TN else A, cuda_device)
+        Bd = K.to_padded(B.t().contiguous() if layout == K.HFB_NT else B, cuda_device)
+        C = K.to_padded(C0, cuda_device)
+        K.dgemm(layout, Ad, Bd, out=C, alpha=-0.25, splits=splits, accumulate=True)
+        ref = C0 - 0.25 * (A @ B)
+        assert rel(C, ref) < 1e-13
+    with pytest.raises(K.HfbError):
+        K.dgemm(layout, Ad, Bd, alpha=1.0, accumulate=True)              # accumulate needs an existing out
+
+
+def test_rank1_update_many_rows(K, cuda_device):
+    """More than 65535 * 16 rows: the launch is split over several grids."""
+    n, m = 1_100_003, 5
+    Y = K.padded_zeros(n, m, cuda_device)
+    x = torch.arange(n, dtype=torch.float64, device=cuda_device) * 1e-6
+    y = torch.tensor([1.0, -2.0, 0.5, 3.0, 7.0], dtype=torch.float64, device=cuda_device)
+    K.rank1_update_(Y, 2.0, x, y)
+    assert torch.equal(Y, 2.0 * torch.outer(x, y))
+
+
 def test_dgemm_rejects_bad_operands(K, cuda_device):
     A = torch.randn(8, 9, dtype=torch.float64, device=cuda_device)     # odd leading dimension
     B = K.padded_empty(9, 4, cuda_device).normal_()
