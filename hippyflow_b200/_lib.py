@@ -59,6 +59,7 @@ def lib():
         "hfb_csr_cluster_blob_stride": (i64, [i32, i32, i32]),
         "hfb_csr_pack_clusters": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
         "hfb_csr_spmm_tma": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_spmm_regblock": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -87,7 +88,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_ex_workspace_bytes",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
-            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma",
+            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma", "hfb_csr_spmm_regblock",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -301,6 +302,20 @@ def csr_spmm_tma(plan, B, out=None):
     rc = L.hfb_csr_spmm_tma(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
                             plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
     _check(rc, "hfb_csr_spmm_tma")
+    return out
+
+
+def csr_spmm_regblock(plan, B, out=None):
+    """C = M @ B with the register-blocked kernel (dense per-cluster block in shared memory, B rows straight from global
+    memory into registers); ``plan`` is the dict built by linalg.CsrMatrix._build_plan with its blobs packed."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_regblock(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+                                 plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_regblock")
     return out
 
 

@@ -6,7 +6,7 @@
 //     int32 rowoff[max_rows + 1]   entry offsets of the cluster's rows (relative to the cluster's first entry)
 //     int32 outrow[max_rows]       global row index of each cluster row (where its result goes in C)
 //     int32 cols[max_cols]         the distinct global columns (= rows of B) the cluster touches
-//     {double v; int32 l; int32 0} entries[nent]   value + cluster-LOCAL column index
+//     {double v; int32 l; int32 r} entries[nent]   value + cluster-LOCAL column index + cluster-LOCAL row index
 // One persistent CTA per SM walks work items (cluster, column chunk).  A producer warp issues, per item, one bulk
 // copy (cp.async.bulk, the TMA engine's linear mode; SASS UBLKCP) of the blob and one per distinct B row
 // (cw*8 contiguous bytes) into a 3-stage shared-memory ring guarded by full/empty mbarriers; no thread of the
@@ -16,6 +16,7 @@
 // of 7), and the ring keeps ~140 KB of loads in flight per SM, which is what the HBM latency needs.
 #include "../../include/hfb200.h"
 #include "hfb_common.cuh"
+#include "spmm_blob.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -26,22 +27,6 @@ constexpr int V4_CONSUMER_WARPS = 16;
 constexpr int V4_THREADS = (V4_CONSUMER_WARPS + 1) * 32;
 constexpr int V4_MAX_STAGES = 8;
 constexpr int V4_SMEM_BUDGET = 232448 - 128;  // opt-in dynamic shared memory per CTA minus the barrier block
-
-struct SpmmBlobLayout {
-    int off_rowoff, off_outrow, off_cols, off_ent, stride;  // bytes
-};
-
-static inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
-
-static SpmmBlobLayout blob_layout(int max_rows, int max_cols, int max_entries) {
-    SpmmBlobLayout L;
-    L.off_rowoff = 16;
-    L.off_outrow = L.off_rowoff + 4 * round_up(max_rows + 1, 4);
-    L.off_cols = L.off_outrow + 4 * round_up(max_rows, 4);
-    L.off_ent = L.off_cols + 4 * round_up(max_cols, 4);
-    L.stride = round_up(L.off_ent + 16 * max_entries, 128);
-    return L;
-}
 
 struct SpmmV4Params {
     int m;          // columns of B / C
@@ -252,6 +237,7 @@ extern "C" int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int
                 memcpy(ent + 16 * (size_t)nent, &val[j], 8);
                 const int32_t l = local[col];
                 memcpy(ent + 16 * (size_t)nent + 8, &l, 4);
+                memcpy(ent + 16 * (size_t)nent + 12, &r, 4);
                 ++nent;
             }
         }

@@ -24,7 +24,9 @@ class CsrMatrix:
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
-        M.sort_indices()
+        if not M.has_canonical_format:      # the cluster kernels scatter entries by (row, column): no duplicates allowed
+            M = M.copy()
+            M.sum_duplicates()
         self.shape = M.shape
         self.nnz = M.nnz
         self.device = device
@@ -37,7 +39,8 @@ class CsrMatrix:
         self.plan = None
         import os
         # "staged": cp.async panels, default (measured faster); "tma": persistent CTAs fed by cp.async.bulk row copies --
-        # its ring stays empty because the TMA engine completes ~1-KB row copies at only ~10 B/clk/SM (profiles/)
+        # its ring stays empty because the TMA engine completes ~1-KB row copies at only ~10 B/clk/SM (profiles/);
+        # "regblock": dense per-cluster block in shared memory, B rows from global memory straight into registers
         self.impl = os.environ.get("HFB_SPMM_IMPL", "staged")
         if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
             try:
@@ -101,6 +104,8 @@ class CsrMatrix:
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
             if self.impl == "tma" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1):
                 return K.csr_spmm_tma(self._tma_blobs(self.plan, self.device), B, out)
+            if self.impl == "regblock" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1) and self.plan["max_rows"] <= 32:
+                return K.csr_spmm_regblock(self._tma_blobs(self.plan, self.device), B, out)
             return K.csr_spmm_staged(self.plan, B, out)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order)
 

@@ -115,7 +115,7 @@ int hfb_csr_spmm_staged(int64_t nclusters, int64_t m, const int32_t* cl_rowptr, 
                         const int32_t* cl_colptr, const int32_t* cl_cols, int32_t max_cols, int32_t max_entries,
                         const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
-/* Persistent TMA-fed SpMM (default for wide blocks).  HOST preprocessing hfb_csr_pack_clusters packs the clusters of
+/* Persistent TMA-fed SpMM (evaluated alternative, HFB_SPMM_IMPL=tma).  HOST preprocessing hfb_csr_pack_clusters packs the clusters of
  * hfb_csr_cluster_rows_capped into fixed-stride blobs (layout in hippyflow_b200/csrc/spmm_tma.cu; stride from
  * hfb_csr_cluster_blob_stride; max_entries = largest number of matrix entries in one cluster); the caller uploads the
  * blob buffer.  One CTA per SM; a producer warp moves every blob and every distinct B row of a (cluster, column chunk)
@@ -127,6 +127,14 @@ int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int32_t* colin
                           int32_t max_entries, void* blobs_out /* HOST, nclusters * stride bytes */);
 int hfb_csr_spmm_tma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols, int32_t max_entries,
                      const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
+/* Register-blocked SpMM over the same blobs (max_rows <= 32).  One CTA per cluster, warp w owns the 64-column panel w of
+ * the result: the cluster's entries are scattered into a dense [distinct columns][rows] block in shared memory, every
+ * distinct B row is loaded once per cluster straight from global memory into registers (coalesced LDG.128, software ring),
+ * and all rows of the cluster accumulate in registers from broadcast LDS.128 of the dense block -- B is never staged in
+ * shared memory.  B, C, blobs: 16-byte aligned; ldb, ldc even. */
+int hfb_csr_spmm_regblock(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                          int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.

@@ -115,10 +115,10 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged"])
+@pytest.mark.parametrize("impl", ["tma", "staged", "regblock"])
 @pytest.mark.parametrize("m", [96, 137, 138, 266, 300, 511, 1100])
 def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
-    """The two cluster-plan kernels (persistent TMA ring / cp.async panels) on a mesh matrix large enough to get a
+    """The cluster-plan kernels (persistent TMA ring / cp.async panels / register-blocked) on a mesh matrix large enough to get a
     plan (n >= 4096), odd and even widths, widths that need 1..4 column chunks; padding columns stay untouched."""
     from hippyflow_b200 import synthetic as syn
     from hippyflow_b200.linalg import CsrMatrix
@@ -139,7 +139,7 @@ def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     assert torch.equal(again, out)                 # fixed summation order: bitwise reproducible
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged"])
+@pytest.mark.parametrize("impl", ["tma", "staged", "regblock"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
     import scipy.sparse as sp

@@ -1,5 +1,8 @@
-"""SpMM micro-benchmark: the persistent TMA-fed kernel vs the cp.async panel kernel at the benchmark shapes, for a few
-cluster caps.  Usage (GPU box): python tools/check_spmm.py [--quick]"""
+"""SpMM micro-benchmark: the cluster-plan kernels (cp.async panels "staged", persistent TMA ring "tma", register-blocked
+"regblock") at the benchmark shapes, for a few cluster caps.
+Usage (GPU box): python tools/check_spmm.py [--quick] [--impls staged,regblock] [--json out.json]"""
+import json
+import os
 import sys
 sys.path.insert(0, ".")
 import numpy as np
@@ -11,7 +14,11 @@ dev = torch.device("cuda:0")
 PEAK = 6542.1   # MEASURED_PEAKS.json hbm_gbs
 quick = "--quick" in sys.argv
 shapes = ((263169, 266),) if quick else ((263169, 266), (1002001, 266), (251001, 138))
-caps = ((32, 64),) if quick else ((32, 64), (24, 48), (16, 32), (12, 24), (8, 16))
+caps = ((16, 32),) if quick else ((32, 64), (24, 48), (16, 32), (16, 40), (12, 24), (12, 28), (8, 16), (8, 20))
+impls = ("tma", "staged", "regblock")
+if "--impls" in sys.argv:
+    impls = tuple(sys.argv[sys.argv.index("--impls") + 1].split(","))
+results = []
 
 
 def timeit(fn, reps=20):
@@ -37,14 +44,27 @@ for n, m in shapes:
         Md.order = Md.plan["order"]
         if ref is None:
             ref = torch.sparse_csr_tensor(Md.rowptr.long(), Md.colind.long(), Md.val, size=M.shape) @ B.contiguous()
-        for impl in ("tma", "staged"):
+        for impl in impls:
             Md.impl = impl
-            try:
-                t = timeit(lambda: Md.matmat(B, out=C))
-            except Exception as e:   # e.g. shared-memory budget of the panel kernel at large caps
-                print(f"n={n} m={m} caps=({rows},{cols}) {impl}: {type(e).__name__}: {e}", flush=True)
-                continue
-            by = Md.spmm_bytes(m)
-            err = float((C - ref).abs().max())
-            print(f"n={n} m={m} caps=({rows},{cols}) clusters={Md.plan['nclusters']} {impl}: {t:.3f} ms "
-                  f"{by / t / 1e6:.0f} GB/s ({by / t / 1e6 / PEAK * 100:.1f}% of HBM peak) err {err:.2e}", flush=True)
+            depths = (0, 4, 8) if impl == "regblock" and not quick else (0,)
+            for dep in depths:
+                os.environ.pop("HFB_SPMM_RB_DEPTH", None)
+                if dep:
+                    os.environ["HFB_SPMM_RB_DEPTH"] = str(dep)
+                C.zero_()
+                try:
+                    t = timeit(lambda: Md.matmat(B, out=C))
+                except Exception as e:   # e.g. shared-memory budget of the panel kernel at large caps
+                    print(f"n={n} m={m} caps=({rows},{cols}) {impl}: {type(e).__name__}: {e}", flush=True)
+                    continue
+                by = Md.spmm_bytes(m)
+                err = float((C - ref).abs().max())
+                tag = impl + (f"/depth{dep}" if dep else "")
+                print(f"n={n} m={m} caps=({rows},{cols}) clusters={Md.plan['nclusters']} {tag}: {t:.3f} ms "
+                      f"{by / t / 1e6:.0f} GB/s ({by / t / 1e6 / PEAK * 100:.1f}% of HBM peak) err {err:.2e}", flush=True)
+                results.append({"n": n, "m": m, "caps": [rows, cols], "clusters": Md.plan["nclusters"], "impl": tag, "ms": t,
+                                "gbs": by / t / 1e6, "frac_hbm": by / t / 1e6 / PEAK, "max_abs_err": err})
+os.environ.pop("HFB_SPMM_RB_DEPTH", None)
+if "--json" in sys.argv:
+    with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+        json.dump(results, f, indent=1)
