@@ -287,7 +287,28 @@ def run_ours(args):
             c2, t2 = gemm_times[tagTN]
             roof["second_kernel"] = {"kernel": "dgemm_dmma_kernel<TN,17>", "achieved": 2.0 * n * n_loc * m / (t2 / c2 * 1e-3) * 1e-12,
                                      "avg_launch_ms": t2 / c2, "launches_timed": c2}
-        roof["gemm_share_of_step"] = sum(t for _, t in gemm_times.values()) / (ms_per_step * args.steps)
+        roof["gemm_share_of_step"] = sum(t for tag, (_, t) in gemm_times.items() if tag[0] != "spmm") / (ms_per_step * args.steps)
+
+    # ---- roofline of the HBM-bound kernel on the path: the CSR SpMM  Z = M Q  (north star (b))
+    roof_hbm = None
+    spmm = [(tag, ct) for tag, ct in gemm_times.items() if tag[0] == "spmm" and tag[3] == m]
+    if spmm:
+        tag, (calls, tot) = max(spmm, key=lambda x: x[1][0])
+        avg_ms = tot / calls
+        by = proj.M_device.spmm_bytes(m)
+        peak_hbm, src = 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s; MEASURED_PEAKS.json absent)"
+        pf = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pf):
+            try:
+                peak_hbm, src = float(json.load(open(pf))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            except Exception:
+                pass
+        ach = by / (avg_ms * 1e-3) * 1e-9
+        roof_hbm = {"bound": "hbm", "kernel": tag[1], "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
+                    "traffic": None, "peak_source": src, "launches_timed": calls, "avg_launch_ms": avg_ms,
+                    "algorithmic_bytes_per_launch": by,
+                    "byte_accounting": "nnz*12 + (n+1)*4 + 2*n*m*8 (CSR once, dense block read once, result written once)",
+                    "share_of_step": tot / (ms_per_step * args.steps)}
 
     # ---- end to end: host (pinned) snapshots -> NumPy results, through the reference-facing API
     e2e = None
@@ -345,7 +366,7 @@ def run_ours(args):
                            "samples_total": N, "rank": k, "oversampling": p, "parallelism": "sample-sharded x%d" % world,
                            "flops_per_step": flops_short(n, N, m), "flop_accounting": "6 n N m + 2 N m^2 (executed GEMM work)",
                            "l2": "inputs (%.1f GB/GPU) exceed L2" % (n_loc * n * 8 / 1e9)},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "cuda_mallocs_in_timed_region": int(new_segments), "clocks": clocks,
                 "eigenvalues_head": [float(x) for x in d_last[:3]]}
         print(json.dumps(line))

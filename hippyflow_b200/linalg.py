@@ -100,14 +100,24 @@ class CsrMatrix:
 
     def matmat(self, B, out=None):
         """out (n, m) = M @ B for a dense row-major (n, m) block."""
+        if K.TIMING is None:
+            return self._matmat(B, out)[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # bench.py's roofline leg
+        e0.record()
+        out, kernel = self._matmat(B, out)
+        e1.record()
+        K.TIMING.append((("spmm", kernel, self.shape[0], B.shape[1]), e0, e1))
+        return out
+
+    def _matmat(self, B, out):
         if self.plan is not None and B.shape[1] >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
             if self.impl == "tma" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1):
-                return K.csr_spmm_tma(self._tma_blobs(self.plan, self.device), B, out)
+                return K.csr_spmm_tma(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_tma_kernel"
             if self.impl == "regblock" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1) and self.plan["max_rows"] <= 32:
-                return K.csr_spmm_regblock(self._tma_blobs(self.plan, self.device), B, out)
-            return K.csr_spmm_staged(self.plan, B, out)
-        return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order)
+                return K.csr_spmm_regblock(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_regblock_kernel"
+            return K.csr_spmm_staged(self.plan, B, out), "csr_spmm_staged_kernel"
+        return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order), "csr_spmm_panel_kernel"
 
     def matmat_rows(self, X, out=None):
         """out (N, n): row i = M @ X[i]  (= (M X^T)^T for sample-major X)."""

@@ -78,6 +78,32 @@ def _decode_blobs(K, plan):
     return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
 
 
+def _decode_blobs_regblock(K, plan):
+    """Rebuild the matrix the way csr_spmm_regblock_kernel reads the blobs: (local column, local ROW) fields of every
+    entry scattered into a dense per-cluster block -- the row offsets are not consulted."""
+    mr, mc, me = plan["max_rows"], plan["max_cols_cap"], plan["max_entries"]
+    stride = int(K.lib().hfb_csr_cluster_blob_stride(mr, mc, me))
+    blobs = plan["blobs"].numpy().reshape(-1, stride)
+    r4 = lambda x: (x + 3) // 4 * 4
+    off_outrow = 16 + 4 * r4(mr + 1)
+    off_cols = off_outrow + 4 * r4(mr)
+    off_ent = off_cols + 4 * r4(mc)
+    rows, cols, vals = [], [], []
+    for b in blobs:
+        nrow, ncol, nent = (int(x) for x in b[:12].view(np.int32))
+        orow = b[off_outrow:off_outrow + 4 * mr].view(np.int32)
+        cl = b[off_cols:off_cols + 4 * mc].view(np.int32)
+        e = b[off_ent:off_ent + 16 * nent].reshape(-1, 16)
+        v = e[:, :8].copy().view(np.float64).ravel()
+        lr = e[:, 8:16].copy().view(np.int32).reshape(-1, 2)
+        D = np.zeros((mc, mr))
+        D[lr[:, 0], lr[:, 1]] = v
+        jj, rr = np.nonzero(D[:ncol, :nrow])
+        rows.append(orow[rr]); cols.append(cl[jj]); vals.append(D[jj, rr])
+    n = plan["order"].numel()
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+
+
 def _decode_staged(plan):
     order = plan["order"].numpy().astype(np.int64)
     s_rowptr = plan["s_rowptr"].numpy().astype(np.int64)
@@ -166,6 +192,12 @@ def emulated_device():
             cache[key] = _decode_blobs(K, plan)
         return _spmm(cache[key], B, out)
 
+    def csr_spmm_regblock(plan, B, out=None):
+        key = ("regblock", id(plan))
+        if key not in cache:
+            cache[key] = _decode_blobs_regblock(K, plan)
+        return _spmm(cache[key], B, out)
+
     def csr_spmm_rows(rowptr, colind, val, X, out=None):
         Msp = _scipy_csr(rowptr, colind, val, X.shape[1])
         res = torch.from_numpy(np.ascontiguousarray((Msp @ X.numpy().T).T))
@@ -232,7 +264,7 @@ def emulated_device():
         return saved_empty(*a, **k)
 
     patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_staged=csr_spmm_staged,
-                   csr_spmm_tma=csr_spmm_tma, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
+                   csr_spmm_tma=csr_spmm_tma, csr_spmm_regblock=csr_spmm_regblock, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
                    colsum=colsum, subtract_row_=subtract_row_, rank1_update_=rank1_update_, axpby_=axpby_,
                    axpby_cols_=axpby_cols_, rowscale=rowscale, fill_random_=fill_random_,
                    measure_dmma_peak=lambda device: 1.0, launch_count=lambda: counter["n"],

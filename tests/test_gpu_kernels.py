@@ -139,6 +139,29 @@ def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     assert torch.equal(again, out)                 # fixed summation order: bitwise reproducible
 
 
+@pytest.mark.parametrize("caps", [(8, 20), (12, 24), (16, 32), (24, 48), (32, 64), (5, 20)])
+@pytest.mark.parametrize("m", [10, 74, 96, 138, 266, 267, 600])
+def test_csr_spmm_regblock_cluster_caps(K, cuda_device, caps, m):
+    """Every register-block instantiation (R = 8, 12, 16, 24, 32) and both lane maps (full 64-column panels, narrow tail
+    panels that fold several row groups into one warp) against SciPy; padding columns stay untouched."""
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    M = syn.p1_mass_matrix(41, 37).tocsr()
+    n = M.shape[0]
+    Md = CsrMatrix(M, cuda_device, cluster_rows=False)
+    plan = CsrMatrix._tma_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
+    B = np.random.default_rng(m).standard_normal((n, m))
+    out = K.padded_empty(n, m, cuda_device)
+    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
+    full.fill_(7.0)
+    K.csr_spmm_regblock(plan, K.to_padded(B, cuda_device), out)
+    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
+    if K._ld(out) > m:
+        assert bool((full[:, m:] == 7.0).all())
+    assert torch.equal(K.csr_spmm_regblock(plan, K.to_padded(B, cuda_device)), out)       # bitwise reproducible
+    del Md
+
+
 @pytest.mark.parametrize("impl", ["tma", "staged", "regblock"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
@@ -152,8 +175,9 @@ def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
         A[r, :] = 0
     A = A.tocsr()
     A.eliminate_zeros()
-    Md = CsrMatrix(A, cuda_device)
-    assert Md.plan is not None
+    Md = CsrMatrix(A, cuda_device, cluster_rows=False)
+    Md.plan = CsrMatrix._build_plan(A, cuda_device, max_rows=16, max_cols=64)    # rows have up to ~20 entries
+    Md.order = Md.plan["order"]
     Md.impl = impl
     B = rng.standard_normal((n, 138))
     out = Md.matmat(K.to_padded(B, cuda_device)).cpu().numpy()

@@ -14,7 +14,9 @@ dev = torch.device("cuda:0")
 PEAK = 6542.1   # MEASURED_PEAKS.json hbm_gbs
 quick = "--quick" in sys.argv
 shapes = ((263169, 266),) if quick else ((263169, 266), (1002001, 266), (251001, 138))
-caps = ((16, 32),) if quick else ((32, 64), (24, 48), (16, 32), (16, 40), (12, 24), (12, 28), (8, 16), (8, 20))
+caps = ((16, 32),) if quick else ((24, 48), (16, 32), (12, 24), (8, 16), (8, 20))
+if os.environ.get("HFB_CHECK_CAPS", "").replace(",", "").isdigit():
+    caps = (tuple(int(v) for v in os.environ["HFB_CHECK_CAPS"].split(",")),)
 impls = ("tma", "staged", "regblock")
 if "--impls" in sys.argv:
     impls = tuple(sys.argv[sys.argv.index("--impls") + 1].split(","))
@@ -46,11 +48,12 @@ for n, m in shapes:
             ref = torch.sparse_csr_tensor(Md.rowptr.long(), Md.colind.long(), Md.val, size=M.shape) @ B.contiguous()
         for impl in impls:
             Md.impl = impl
-            depths = (0, 4, 8) if impl == "regblock" and not quick else (0,)
+            depths = (0, 4, 8) if impl == "regblock" and not quick else (None,)     # None: leave the environment alone
             for dep in depths:
-                os.environ.pop("HFB_SPMM_RB_DEPTH", None)
-                if dep:
-                    os.environ["HFB_SPMM_RB_DEPTH"] = str(dep)
+                if dep is not None:
+                    os.environ.pop("HFB_SPMM_RB_DEPTH", None)
+                    if dep:
+                        os.environ["HFB_SPMM_RB_DEPTH"] = str(dep)
                 C.zero_()
                 try:
                     t = timeit(lambda: Md.matmat(B, out=C))
@@ -64,7 +67,6 @@ for n, m in shapes:
                       f"{by / t / 1e6:.0f} GB/s ({by / t / 1e6 / PEAK * 100:.1f}% of HBM peak) err {err:.2e}", flush=True)
                 results.append({"n": n, "m": m, "caps": [rows, cols], "clusters": Md.plan["nclusters"], "impl": tag, "ms": t,
                                 "gbs": by / t / 1e6, "frac_hbm": by / t / 1e6 / PEAK, "max_abs_err": err})
-os.environ.pop("HFB_SPMM_RB_DEPTH", None)
 if "--json" in sys.argv:
     with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
         json.dump(results, f, indent=1)
