@@ -60,6 +60,10 @@ def lib():
         "hfb_csr_pack_clusters": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
         "hfb_csr_spmm_tma": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_regblock": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_spmm_dmma": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_frag_blob_stride": (i64, [i32, i32]),
+        "hfb_csr_pack_clusters_frag": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+        "hfb_csr_spmm_dmma_frag": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -88,7 +92,8 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_ex_workspace_bytes",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
-            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma", "hfb_csr_spmm_regblock",
+            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma", "hfb_csr_spmm_regblock", "hfb_csr_spmm_dmma",
+            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -316,6 +321,55 @@ def csr_spmm_regblock(plan, B, out=None):
     rc = L.hfb_csr_spmm_regblock(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
                                  plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
     _check(rc, "hfb_csr_spmm_regblock")
+    return out
+
+
+def csr_spmm_dmma(plan, B, out=None):
+    """C = M @ B with the cluster-dense DMMA kernel (A fragments of the per-cluster dense block in registers, B rows staged
+    by cp.async); ``plan`` is the dict built by linalg.CsrMatrix._build_plan with its blobs packed."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_dmma(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+                             plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_dmma")
+    return out
+
+
+def csr_pack_clusters_frag(indptr, indices, data, order, cptr, max_rows, max_cols):
+    """Host preprocessing for the fragment-blob DMMA SpMM: uint8 NumPy buffer of per-cluster records holding the dense
+    cluster block in DMMA A-fragment order (hfb_csr_pack_clusters_frag)."""
+    import numpy as np
+    L = lib()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    cptr = np.ascontiguousarray(cptr, dtype=np.int32)
+    ncl = cptr.size - 1
+    stride = int(L.hfb_csr_frag_blob_stride(int(max_rows), int(max_cols)))
+    if stride <= 0:
+        raise HfbError("hfb_csr_frag_blob_stride: cluster caps (%d, %d) exceed the DMMA kernel's (16, 48)" % (max_rows, max_cols))
+    blobs = np.empty(ncl * stride, dtype=np.uint8)
+    rc = L.hfb_csr_pack_clusters_frag(indptr.size - 1, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data,
+                                      order.ctypes.data, cptr.ctypes.data, ncl, int(max_rows), int(max_cols), blobs.ctypes.data)
+    _check(rc, "hfb_csr_pack_clusters_frag")
+    return blobs
+
+
+def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0):
+    """C = M @ B with the fragment-blob DMMA kernel; ``plan`` carries ``fblobs`` (linalg.CsrMatrix._frag_blobs).
+    ``chunk_cols`` = columns staged per CTA (0: whole rows up to 320 columns)."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_dmma_frag(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+                                  int(chunk_cols), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_dmma_frag")
     return out
 
 

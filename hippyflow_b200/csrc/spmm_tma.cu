@@ -206,6 +206,8 @@ extern "C" int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int
         return HFB_E_BADARG;
     const SpmmBlobLayout L = blob_layout(max_rows, max_cols, max_entries);
     std::vector<int32_t> stamp((size_t)n, -1), local((size_t)n, 0);
+    std::vector<int32_t> touched;                 // distinct columns of the current cluster, first-touch order
+    std::vector<unsigned char> half((size_t)n, 0);  // bit 0: touched by cluster rows 0..7, bit 1: by rows >= 8
     unsigned char* out = static_cast<unsigned char*>(blobs_out);
     for (int64_t c = 0; c < nclusters; ++c) {
         unsigned char* blob = out + (size_t)c * L.stride;
@@ -218,24 +220,43 @@ extern "C" int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int
         const int32_t s0 = cluster_ptr[c], s1 = cluster_ptr[c + 1];
         const int32_t nrow = s1 - s0;
         if (nrow <= 0 || nrow > max_rows) return HFB_E_BADARG;
-        int32_t ncol = 0, nent = 0;
+        // pass 1: the distinct columns and which 8-row half of the cluster touches them
+        touched.clear();
         for (int32_t r = 0; r < nrow; ++r) {
             const int32_t row = order[s0 + r];
             if (row < 0 || row >= n) return HFB_E_BADARG;
-            rowoff[r] = nent;
-            outrow[r] = row;
             for (int32_t j = rowptr[row]; j < rowptr[row + 1]; ++j) {
                 const int32_t col = colind[j];
                 if (col < 0 || col >= n) return HFB_E_BADARG;
                 if (stamp[col] != (int32_t)c) {
-                    if (ncol >= max_cols) return HFB_E_UNSUPPORTED;
+                    if ((int32_t)touched.size() >= max_cols) return HFB_E_UNSUPPORTED;
                     stamp[col] = (int32_t)c;
+                    half[col] = 0;
+                    touched.push_back(col);
+                }
+                half[col] |= (r < 8) ? 1 : 2;
+            }
+        }
+        // local numbering: columns only the upper half touches, then shared ones, then lower-half only (first-touch order
+        // within a class).  Each half's nonzeros then fill a contiguous range of local columns, so the DMMA kernel skips
+        // the 8 x 4 blocks of the dense cluster matrix outside that range; the other kernels do not care about the order.
+        int32_t ncol = 0;
+        for (unsigned char want : {(unsigned char)1, (unsigned char)3, (unsigned char)2})
+            for (int32_t col : touched)
+                if (half[col] == want) {
                     local[col] = ncol;
                     cols[ncol++] = col;
                 }
+        // pass 2: the entries
+        int32_t nent = 0;
+        for (int32_t r = 0; r < nrow; ++r) {
+            const int32_t row = order[s0 + r];
+            rowoff[r] = nent;
+            outrow[r] = row;
+            for (int32_t j = rowptr[row]; j < rowptr[row + 1]; ++j) {
                 if (nent >= max_entries) return HFB_E_UNSUPPORTED;
                 memcpy(ent + 16 * (size_t)nent, &val[j], 8);
-                const int32_t l = local[col];
+                const int32_t l = local[colind[j]];
                 memcpy(ent + 16 * (size_t)nent + 8, &l, 4);
                 memcpy(ent + 16 * (size_t)nent + 12, &r, 4);
                 ++nent;

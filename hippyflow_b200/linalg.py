@@ -38,10 +38,15 @@ class CsrMatrix:
         self.order = None
         self.plan = None
         import os
-        # "staged": cp.async panels, default (measured faster); "tma": persistent CTAs fed by cp.async.bulk row copies --
-        # its ring stays empty because the TMA engine completes ~1-KB row copies at only ~10 B/clk/SM (profiles/);
-        # "regblock": dense per-cluster block in shared memory, B rows from global memory straight into registers
-        self.impl = os.environ.get("HFB_SPMM_IMPL", "staged")
+        # SpMM kernel for wide blocks (m >= 96) over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
+        #   "auto"     (default) "frag" for m >= 192, "dmma" for narrower blocks, "staged" when the clusters exceed the
+        #              DMMA kernels' register budget (16 rows x 48 distinct columns)
+        #   "frag"     dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
+        #   "dmma"     same arithmetic, records decoded in the kernel, double-buffered 64-column panels
+        #   "staged"   cp.async panels + one LDS.128 pair per matrix entry (round-1 default, LSU-bound)
+        #   "regblock" dense cluster block against B rows loaded straight into registers (scoreboard-bound)
+        #   "tma"      persistent CTAs fed by cp.async.bulk row copies (TMA small-copy rate bound)
+        self.impl = os.environ.get("HFB_SPMM_IMPL", "auto")
         if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
             try:
                 self.plan = self._build_plan(M, device)
@@ -98,6 +103,14 @@ class CsrMatrix:
                                                                 plan["max_cols_cap"], plan["max_entries"]), device=device)
         return plan
 
+    @staticmethod
+    def _frag_blobs(plan, device):
+        if "fblobs" not in plan:
+            indptr, indices, data, order, cptr = plan["_host"]
+            plan["fblobs"] = torch.as_tensor(K.csr_pack_clusters_frag(indptr, indices, data, order, cptr, plan["max_rows"],
+                                                                      plan["max_cols_cap"]), device=device)
+        return plan
+
     def matmat(self, B, out=None):
         """out (n, m) = M @ B for a dense row-major (n, m) block."""
         if K.TIMING is None:
@@ -110,11 +123,25 @@ class CsrMatrix:
         return out
 
     def _matmat(self, B, out):
-        if self.plan is not None and B.shape[1] >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
+        m = B.shape[1]
+        wide = K._ld(B) >= m + (m & 1)                      # the padding column of an odd width may be read
+        if self.plan is not None and m >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
-            if self.impl == "tma" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1):
+            impl = self.impl
+            dmma_ok = wide and self.plan["max_rows"] <= 16 and self.plan["max_cols_cap"] <= 48
+            if impl == "auto":
+                # measured on B200 (profiles/r01_spmm_variants.md): whole-row fragment-record kernel for wide blocks,
+                # double-buffered 64-column panels for narrow ones (a CTA's share is too small to amortise its latency chain)
+                impl = ("frag" if m >= 192 else "dmma") if dmma_ok else "staged"
+            if impl == "frag" and dmma_ok:
+                import os
+                return K.csr_spmm_dmma_frag(self._frag_blobs(self.plan, self.device), B, out,
+                                            int(os.environ.get("HFB_SPMM_FRAG_W", 0))), "csr_spmm_dmma_frag_kernel"
+            if impl == "dmma" and dmma_ok:
+                return K.csr_spmm_dmma(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_dmma_kernel"
+            if impl == "tma" and wide:
                 return K.csr_spmm_tma(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_tma_kernel"
-            if self.impl == "regblock" and K._ld(B) >= B.shape[1] + (B.shape[1] & 1) and self.plan["max_rows"] <= 32:
+            if impl == "regblock" and wide and self.plan["max_rows"] <= 32:
                 return K.csr_spmm_regblock(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_regblock_kernel"
             return K.csr_spmm_staged(self.plan, B, out), "csr_spmm_staged_kernel"
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order), "csr_spmm_panel_kernel"

@@ -136,6 +136,28 @@ int hfb_csr_spmm_tma(int64_t nclusters, int64_t m, const void* blobs, int32_t ma
 int hfb_csr_spmm_regblock(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                           int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
+/* Cluster-dense DMMA SpMM over the same blobs (max_rows <= 16, max_cols <= 48).  One CTA per cluster: the cluster's entries
+ * become a dense [rows][distinct columns] block whose DMMA A-fragments stay in registers; the distinct B rows are staged
+ * panel by panel into shared memory with cp.async (double-buffered) and multiplied as DMMA.8x8x4 tiles, so every staged B
+ * element is read from shared memory once and the matrix never is.  B, C, blobs: 16-byte aligned; ldb, ldc even;
+ * ldb >= m rounded up to even. */
+int hfb_csr_spmm_dmma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                      int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
+/* The same product from "fragment blobs": HOST preprocessing hfb_csr_pack_clusters_frag stores each cluster's dense block
+ * already in DMMA A-fragment order together with its nonzero-block masks, distinct columns and result rows (fixed stride
+ * hfb_csr_frag_blob_stride; max_rows <= 16, max_cols <= 48).  The kernel needs no record staging or dense-block build:
+ * it requests the whole chunk (chunk_cols columns, 0 = whole rows up to 320 columns) of every distinct B row with cp.async
+ * right after reading the column list, keeps the accumulators of all its column groups in registers with the k-steps as
+ * the outer loop, and starts the DMMAs of k-steps 2i, 2i+1 when rows 8i..8i+7 have landed.  256-bit result stores when C
+ * rows are 32-byte aligned.  B, C, blobs: 16-byte aligned; ldb, ldc even; ldb >= m rounded up to even. */
+int64_t hfb_csr_frag_blob_stride(int32_t max_rows, int32_t max_cols);
+int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, const int32_t* colind, const double* val, const int32_t* order,
+                               const int32_t* cluster_ptr, int64_t nclusters, int32_t max_rows, int32_t max_cols,
+                               void* blobs_out /* HOST, nclusters * stride bytes */);
+int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                           int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.
  * (M X)^T for symmetric M with X stored as u_data (N, n)  (PODProjector.py:750, 818).

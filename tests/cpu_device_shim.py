@@ -104,6 +104,37 @@ def _decode_blobs_regblock(K, plan):
     return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
 
 
+def decode_frag_blobs(K, fblobs, max_rows, max_cols, n):
+    """Rebuild the matrix from the fragment records of csr_spmm_dmma_frag_kernel, reading them the way the kernel does:
+    a[ks] of lane (g = lane >> 2, t = lane & 3) of row half h is D[g + 8h][4 ks + t]; blocks whose mask bit is clear are
+    taken as zero WITHOUT looking at the stored values."""
+    rh = 1 if max_rows <= 8 else 2
+    maxks = 4 if max_cols <= 16 else 6 if max_cols <= 24 else 8 if max_cols <= 32 else 12
+    stride = int(K.lib().hfb_csr_frag_blob_stride(int(max_rows), int(max_cols)))
+    off_outrow = 32
+    off_cols = off_outrow + 4 * 8 * rh
+    off_afrag = (off_cols + 4 * 4 * maxks + 255) // 256 * 256
+    assert stride == (off_afrag + 8 * 32 * rh * maxks + 255) // 256 * 256
+    blobs = np.asarray(fblobs).reshape(-1, stride)
+    rows, cols, vals = [], [], []
+    lane = np.arange(32)
+    g, t = lane >> 2, lane & 3
+    for b in blobs:
+        nrow, ncol, nz0, nz1 = (int(x) for x in b[:16].view(np.int32))
+        orow = b[off_outrow:off_outrow + 4 * 8 * rh].view(np.int32)
+        cl = b[off_cols:off_cols + 4 * 4 * maxks].view(np.int32)
+        af = b[off_afrag:off_afrag + 8 * 32 * rh * maxks].view(np.float64).reshape(maxks, rh, 32)
+        D = np.zeros((8 * rh, 4 * maxks))
+        for ks in range(maxks):
+            for h in range(rh):
+                if (nz0, nz1)[h] >> ks & 1:
+                    D[g + 8 * h, 4 * ks + t] = af[ks, h]
+        assert not D[nrow:].any() and not D[:, ncol:].any()
+        rr, jj = np.nonzero(D)
+        rows.append(orow[rr]); cols.append(cl[jj]); vals.append(D[rr, jj])
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+
+
 def _decode_staged(plan):
     order = plan["order"].numpy().astype(np.int64)
     s_rowptr = plan["s_rowptr"].numpy().astype(np.int64)
@@ -198,6 +229,15 @@ def emulated_device():
             cache[key] = _decode_blobs_regblock(K, plan)
         return _spmm(cache[key], B, out)
 
+    def csr_spmm_dmma(plan, B, out=None):
+        return csr_spmm_regblock(plan, B, out)     # reads the same fields of the same records
+
+    def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0):
+        key = ("frag", id(plan))
+        if key not in cache:
+            cache[key] = decode_frag_blobs(K, plan["fblobs"].numpy(), plan["max_rows"], plan["max_cols_cap"], plan["order"].numel())
+        return _spmm(cache[key], B, out)
+
     def csr_spmm_rows(rowptr, colind, val, X, out=None):
         Msp = _scipy_csr(rowptr, colind, val, X.shape[1])
         res = torch.from_numpy(np.ascontiguousarray((Msp @ X.numpy().T).T))
@@ -264,7 +304,7 @@ def emulated_device():
         return saved_empty(*a, **k)
 
     patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_staged=csr_spmm_staged,
-                   csr_spmm_tma=csr_spmm_tma, csr_spmm_regblock=csr_spmm_regblock, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
+                   csr_spmm_tma=csr_spmm_tma, csr_spmm_regblock=csr_spmm_regblock, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
                    colsum=colsum, subtract_row_=subtract_row_, rank1_update_=rank1_update_, axpby_=axpby_,
                    axpby_cols_=axpby_cols_, rowscale=rowscale, fill_random_=fill_random_,
                    measure_dmma_peak=lambda device: 1.0, launch_count=lambda: counter["n"],

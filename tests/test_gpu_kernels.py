@@ -115,7 +115,7 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged", "regblock"])
+@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag"])
 @pytest.mark.parametrize("m", [96, 137, 138, 266, 300, 511, 1100])
 def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     """The cluster-plan kernels (persistent TMA ring / cp.async panels / register-blocked) on a mesh matrix large enough to get a
@@ -162,7 +162,105 @@ def test_csr_spmm_regblock_cluster_caps(K, cuda_device, caps, m):
     del Md
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged", "regblock"])
+@pytest.mark.parametrize("mode", ["panel64", "panel128", "slab64", "slab144", "slabfull"])
+@pytest.mark.parametrize("caps", [(8, 16), (8, 20), (8, 32), (8, 40), (12, 24), (16, 24), (16, 32), (16, 48), (5, 20)])
+@pytest.mark.parametrize("m", [10, 74, 138, 266, 267, 600])
+def test_csr_spmm_dmma_cluster_caps(K, cuda_device, caps, m, mode, monkeypatch):
+    """Every instantiation of the cluster-dense DMMA kernel (1 or 2 row halves, 4..12 k-steps; double-buffered 64- and
+    128-column panels, and the row-slab staging with one or several column chunks) against SciPy: narrow blocks, partial
+    last panels / chunks, odd widths; padding columns stay untouched; run-to-run bitwise equal."""
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    monkeypatch.delenv("HFB_SPMM_DMMA_W", raising=False)
+    monkeypatch.delenv("HFB_SPMM_DMMA_NT", raising=False)
+    if mode.startswith("panel"):
+        monkeypatch.setenv("HFB_SPMM_DMMA_NT", "2" if mode == "panel128" else "1")
+    else:
+        monkeypatch.setenv("HFB_SPMM_DMMA_W", {"slab64": "64", "slab144": "144", "slabfull": "100000"}[mode])
+    M = syn.p1_mass_matrix(41, 37).tocsr()
+    n = M.shape[0]
+    plan = CsrMatrix._tma_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
+    B = np.random.default_rng(m).standard_normal((n, m))
+    out = K.padded_empty(n, m, cuda_device)
+    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
+    full.fill_(7.0)
+    K.csr_spmm_dmma(plan, K.to_padded(B, cuda_device), out)
+    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
+    if K._ld(out) > m:
+        assert bool((full[:, m:] == 7.0).all())
+    assert torch.equal(K.csr_spmm_dmma(plan, K.to_padded(B, cuda_device)), out)
+
+
+@pytest.mark.parametrize("chunk", [0, 64, 144])
+@pytest.mark.parametrize("caps", [(8, 16), (8, 24), (8, 32), (8, 40), (12, 24), (16, 24), (16, 32), (16, 48), (5, 20)])
+@pytest.mark.parametrize("m", [10, 74, 138, 266, 267, 330, 600])
+def test_csr_spmm_dmma_frag_cluster_caps(K, cuda_device, caps, m, chunk):
+    """Fragment-record DMMA kernel: every (row halves, k-steps) instantiation, whole-row and chunked staging, widths that
+    need 1..5 column groups per warp and several chunks, odd widths; padding untouched; bitwise reproducible."""
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    M = syn.p1_mass_matrix(41, 37).tocsr()
+    n = M.shape[0]
+    plan = CsrMatrix._frag_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
+    B = np.random.default_rng(m).standard_normal((n, m))
+    out = K.padded_empty(n, m, cuda_device)
+    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
+    full.fill_(7.0)
+    K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), out, chunk_cols=chunk)
+    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
+    if K._ld(out) > m:
+        assert bool((full[:, m:] == 7.0).all())
+    assert torch.equal(K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), chunk_cols=chunk), out)
+
+
+def test_csr_spmm_dmma_frag_irregular_and_unaligned_rows(K, cuda_device):
+    """Ragged pattern with empty rows; result block whose rows are only 16-byte aligned (128-bit store path)."""
+    import scipy.sparse as sp
+    from hippyflow_b200.linalg import CsrMatrix
+    rng = np.random.default_rng(3)
+    n = 6000
+    A = sp.random(n, n, density=4.0 / n, random_state=7, format="csr")
+    A = (A + A.T + sp.diags(rng.standard_normal(n))).tolil()
+    for r in (0, 17, n - 1):
+        A[r, :] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    plan = CsrMatrix._frag_blobs(CsrMatrix._build_plan(A, cuda_device, max_rows=16, max_cols=48), cuda_device)
+    B = rng.standard_normal((n, 138))
+    Bd = K.to_padded(B, cuda_device)
+    out = K.csr_spmm_dmma_frag(plan, Bd).cpu().numpy()
+    np.testing.assert_allclose(out, A @ B, rtol=1e-12, atol=1e-14)
+    assert np.all(out[[0, 17, n - 1]] == 0.0)
+    wide = torch.zeros((n, 146), dtype=torch.float64, device=cuda_device)      # ld = 146: even, not a multiple of 4
+    view = wide[:, 2:140]                                                     # base 16-byte aligned, rows not 32-byte aligned
+    K.csr_spmm_dmma_frag(plan, Bd, view)
+    np.testing.assert_allclose(view.cpu().numpy(), A @ B, rtol=1e-12, atol=1e-14)
+    assert bool((wide[:, :2] == 0).all()) and bool((wide[:, 140:] == 0).all())
+
+
+def test_csr_spmm_dmma_irregular_matrix_and_limits(K, cuda_device):
+    """Ragged non-mesh pattern with empty rows through the DMMA kernel; caps beyond its register budget are refused."""
+    import scipy.sparse as sp
+    from hippyflow_b200.linalg import CsrMatrix
+    rng = np.random.default_rng(3)
+    n = 6000
+    A = sp.random(n, n, density=4.0 / n, random_state=7, format="csr")
+    A = (A + A.T + sp.diags(rng.standard_normal(n))).tolil()
+    for r in (0, 17, n - 1):
+        A[r, :] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    plan = CsrMatrix._tma_blobs(CsrMatrix._build_plan(A, cuda_device, max_rows=16, max_cols=48), cuda_device)
+    B = rng.standard_normal((n, 138))
+    out = K.csr_spmm_dmma(plan, K.to_padded(B, cuda_device)).cpu().numpy()
+    np.testing.assert_allclose(out, A @ B, rtol=1e-12, atol=1e-14)
+    assert np.all(out[[0, 17, n - 1]] == 0.0)
+    big = CsrMatrix._tma_blobs(CsrMatrix._build_plan(A, cuda_device, max_rows=32, max_cols=64), cuda_device)
+    with pytest.raises(K.HfbError):
+        K.csr_spmm_dmma(big, K.to_padded(B, cuda_device))
+
+
+@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
     import scipy.sparse as sp

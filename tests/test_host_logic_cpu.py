@@ -101,6 +101,6 @@ def test_shim_decodes_the_cluster_plans():
         assert Md.plan is not None
         B = K.to_padded(np.random.default_rng(0).standard_normal((M.shape[0], 138)), dev)
         ref = M @ B.numpy()
-        for impl in ("tma", "staged", "regblock"):
+        for impl in ("tma", "staged", "regblock", "dmma", "frag"):
             Md.impl = impl
             np.testing.assert_allclose(Md.matmat(B).numpy(), ref, rtol=1e-13, atol=1e-16)

@@ -80,3 +80,36 @@ def test_pack_rejects_bad_arguments():
         K.csr_pack_clusters(M.indptr, M.indices, M.data, order, cptr, 16, 4, 200)
     with pytest.raises(K.HfbError):     # entry budget too small
         K.csr_pack_clusters(M.indptr, M.indices, M.data, order, cptr, 16, 32, 3)
+
+
+@pytest.mark.parametrize("caps", [(16, 32), (8, 24), (12, 24), (16, 48), (8, 16), (5, 20)])
+def test_fragment_records_rebuild_matrix(caps):
+    """hfb_csr_pack_clusters_frag: the DMMA A-fragment records, decoded with the kernel's lane map and block masks, give
+    back the matrix bit for bit (mesh matrix and a ragged one with empty rows)."""
+    from cpu_device_shim import decode_frag_blobs
+    rng = np.random.default_rng(8)
+    n = 2500
+    A0 = sp.random(n, n, density=2.0 / n, random_state=3, format="csr")
+    A0 = (A0 + A0.T + sp.diags(rng.standard_normal(n))).tolil()
+    A0[7, :] = 0
+    A0 = A0.tocsr()
+    A0.eliminate_zeros()
+    for M in (syn.p1_mass_matrix(23, 31).tocsr(), A0):
+        order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, *caps)
+        mr = int(np.diff(cptr).max())
+        distinct = max(np.unique(M.indices[np.concatenate([np.arange(M.indptr[r], M.indptr[r + 1]) for r in order[a:b]])]).size
+                       if M.indptr[order[a:b] + 1].sum() > M.indptr[order[a:b]].sum() else 0
+                       for a, b in zip(cptr[:-1], cptr[1:]))
+        blobs = K.csr_pack_clusters_frag(M.indptr, M.indices, M.data, order, cptr, mr, distinct)
+        A = decode_frag_blobs(K, blobs, mr, distinct, M.shape[0])
+        assert (A != M).nnz == 0
+
+
+def test_fragment_records_limits():
+    M = syn.p1_mass_matrix(8, 8).tocsr()
+    order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, 32, 64)
+    with pytest.raises(K.HfbError):                      # more rows / columns than the A fragments can hold
+        K.csr_pack_clusters_frag(M.indptr, M.indices, M.data, order, cptr, 32, 64)
+    order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, 16, 32)
+    with pytest.raises(K.HfbError):                      # column budget smaller than what the clusters touch
+        K.csr_pack_clusters_frag(M.indptr, M.indices, M.data, order, cptr, 16, 8)

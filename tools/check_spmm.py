@@ -14,10 +14,10 @@ dev = torch.device("cuda:0")
 PEAK = 6542.1   # MEASURED_PEAKS.json hbm_gbs
 quick = "--quick" in sys.argv
 shapes = ((263169, 266),) if quick else ((263169, 266), (1002001, 266), (251001, 138))
-caps = ((16, 32),) if quick else ((24, 48), (16, 32), (12, 24), (8, 16), (8, 20))
+caps = ((16, 32),) if quick else ((16, 32), (12, 32), (8, 24), (8, 20))
 if os.environ.get("HFB_CHECK_CAPS", "").replace(",", "").isdigit():
     caps = (tuple(int(v) for v in os.environ["HFB_CHECK_CAPS"].split(",")),)
-impls = ("tma", "staged", "regblock")
+impls = ("tma", "staged", "regblock", "dmma", "frag")
 if "--impls" in sys.argv:
     impls = tuple(sys.argv[sys.argv.index("--impls") + 1].split(","))
 results = []
@@ -48,12 +48,14 @@ for n, m in shapes:
             ref = torch.sparse_csr_tensor(Md.rowptr.long(), Md.colind.long(), Md.val, size=M.shape) @ B.contiguous()
         for impl in impls:
             Md.impl = impl
-            depths = (0, 4, 8) if impl == "regblock" and not quick else (None,)     # None: leave the environment alone
+            # tuning knobs swept per variant (None: leave the environment alone)
+            knob = {"regblock": "HFB_SPMM_RB_DEPTH", "dmma": "HFB_SPMM_DMMA_W", "frag": "HFB_SPMM_FRAG_W"}.get(impl)
+            depths = {"regblock": (0,), "dmma": (0,), "frag": (0,)}.get(impl, (None,)) if not quick else (None,)
             for dep in depths:
                 if dep is not None:
-                    os.environ.pop("HFB_SPMM_RB_DEPTH", None)
+                    os.environ.pop(knob, None)
                     if dep:
-                        os.environ["HFB_SPMM_RB_DEPTH"] = str(dep)
+                        os.environ[knob] = str(dep)
                 C.zero_()
                 try:
                     t = timeit(lambda: Md.matmat(B, out=C))
@@ -62,7 +64,7 @@ for n, m in shapes:
                     continue
                 by = Md.spmm_bytes(m)
                 err = float((C - ref).abs().max())
-                tag = impl + (f"/depth{dep}" if dep else "")
+                tag = impl + (f"/{'depth' if impl == 'regblock' else 'w'}{dep}" if dep else "")
                 print(f"n={n} m={m} caps=({rows},{cols}) clusters={Md.plan['nclusters']} {tag}: {t:.3f} ms "
                       f"{by / t / 1e6:.0f} GB/s ({by / t / 1e6 / PEAK * 100:.1f}% of HBM peak) err {err:.2e}", flush=True)
                 results.append({"n": n, "m": m, "caps": [rows, cols], "clusters": Md.plan["nclusters"], "impl": tag, "ms": t,
