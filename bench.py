@@ -304,8 +304,15 @@ def run_ours(args):
             except Exception:
                 pass
         ach = by / (avg_ms * 1e-3) * 1e-9
+        traffic_hbm = None
+        tf = os.path.join(ROOT, "profiles", "dgemm_traffic.json")
+        if os.path.exists(tf) and tag[1] == "csr_spmm_dmma_frag_kernel":
+            try:
+                traffic_hbm = json.load(open(tf)).get(args.workload, {}).get("spmm_frag_dram_bytes_per_launch")
+            except Exception:
+                traffic_hbm = None
         roof_hbm = {"bound": "hbm", "kernel": tag[1], "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
-                    "traffic": None, "peak_source": src, "launches_timed": calls, "avg_launch_ms": avg_ms,
+                    "traffic": traffic_hbm, "peak_source": src, "launches_timed": calls, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": by,
                     "byte_accounting": "nnz*12 + (n+1)*4 + 2*n*m*8 (CSR once, dense block read once, result written once)",
                     "share_of_step": tot / (ms_per_step * args.steps)}
