@@ -103,7 +103,7 @@ int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const 
  * symmetric pattern into groups of `cluster` neighbouring rows; writes a permutation of 0..n-1. O(nnz). */
 int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t cluster, int32_t* order_out);
 
-/* Cluster-staged SpMM (the fast path): HOST preprocessing hfb_csr_cluster_rows_capped groups the rows into clusters of
+/* Cluster-staged SpMM (round-1 baseline of the cluster kernels; the default is hfb_csr_spmm_dmma_frag below): HOST preprocessing hfb_csr_cluster_rows_capped groups the rows into clusters of
  * <= max_rows rows touching <= max_cols distinct columns; the caller then builds, in cluster order, the row offsets
  * s_rowptr, the 16-byte entries {value, cluster-LOCAL column index} and the per-cluster distinct-column lists
  * (cl_colptr, cl_cols) -- see hippyflow_b200/linalg.py:CsrMatrix._build_plan.  The kernel stages each cluster's distinct
