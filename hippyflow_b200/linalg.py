@@ -57,11 +57,14 @@ class CsrMatrix:
     @staticmethod
     def _build_plan(M, device, max_rows=None, max_cols=None):
         import os
-        # (16, 32) measured best on B200 for the panel kernel (cfg2, m = 266: 0.343 ms = 51 % of the HBM copy rate;
-        # (24, 48): 0.358, (32, 64): 0.389, (12, 24): 0.402, (64, 128): 0.73 ms): small clusters keep many CTAs with
-        # double-buffered panels resident per SM; the halo re-reads they add are served by L2
+        # (16, 32) measured best on B200 for the cluster kernels (cfg2, m = 266; profiles/r01_spmm_variants.md: DMMA
+        # fragment kernel 0.271 ms, (12, 32) 0.283, (8, 24) 0.286, (8, 20) 0.326; cp.async-panel kernel 0.343 ms, (24, 48)
+        # 0.358, (32, 64) 0.389): one cluster = two DMMA row halves x eight k-steps, 71 KB of staged rows, 3 CTAs per SM
         max_rows = int(os.environ.get("HFB_SPMM_ROWS", 16)) if max_rows is None else max_rows
-        max_cols = int(os.environ.get("HFB_SPMM_COLS", 32)) if max_cols is None else max_cols
+        if max_cols is None:
+            # 7-point P1 stencils fill (16, 32) clusters; denser rows (9-point, P2: 9-20 entries) would shrink them to 2-3 rows
+            # under 32 columns, so they get the DMMA kernels' largest column budget instead
+            max_cols = int(os.environ.get("HFB_SPMM_COLS", 32 if M.nnz <= 8 * M.shape[0] else 48))
         indptr, indices, data = np.asarray(M.indptr, dtype=np.int64), np.asarray(M.indices, dtype=np.int64), np.asarray(M.data)
         order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, max_rows, max_cols)
         n = M.shape[0]

@@ -104,3 +104,44 @@ def test_shim_decodes_the_cluster_plans():
         for impl in ("tma", "staged", "regblock", "dmma", "frag"):
             Md.impl = impl
             np.testing.assert_allclose(Md.matmat(B).numpy(), ref, rtol=1e-13, atol=1e-16)
+
+
+def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
+    """Host side of the SpMM dispatch: a 7-point mesh matrix gets (16, 32) clusters, a 21-point one the (16, 48) budget
+    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the fragment kernel for wide blocks, the panel kernel for
+    narrow ones, the generic CSR kernel below 96 columns, and duplicates in the input matrix are summed first."""
+    import numpy as np
+    import scipy.sparse as sp
+    from hippyflow_b200 import _lib as K, synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    nx = 70
+    idx = np.arange(nx * nx).reshape(nx, nx)
+    r, c = [], []
+    for dx in range(-2, 3):
+        for dy in range(-2, 3):
+            if abs(dx) + abs(dy) <= 3:
+                a = idx[max(0, -dx):nx - max(0, dx), max(0, -dy):nx - max(0, dy)]
+                b = idx[max(0, dx):nx - max(0, -dx), max(0, dy):nx - max(0, -dy)]
+                r.append(a.ravel()); c.append(b.ravel())
+    r, c = np.concatenate(r), np.concatenate(c)
+    dense = sp.csr_matrix((np.random.default_rng(1).standard_normal(r.size), (r, c)), shape=(nx * nx, nx * nx))
+    with emulated_device() as dev:
+        Md = CsrMatrix(syn.p1_mass_matrix(70, 63), dev)
+        assert Md.impl == "auto" and Md.plan["max_rows"] <= 16 and Md.plan["max_cols_cap"] <= 32
+        Dd = CsrMatrix(dense, dev)
+        assert Dd.plan is not None and 32 < Dd.plan["max_cols_cap"] <= 48
+        assert Dd.shape[0] / Dd.plan["nclusters"] > 6                      # (16, 32) would leave ~2.4 rows per cluster
+        rng = np.random.default_rng(0)
+        for m, kernel in ((266, "csr_spmm_dmma_frag_kernel"), (138, "csr_spmm_dmma_kernel"), (40, "csr_spmm_panel_kernel")):
+            B = K.to_padded(rng.standard_normal((dense.shape[0], m)), dev)
+            out, used = Dd._matmat(B, None)
+            assert used == kernel
+            np.testing.assert_allclose(out.numpy(), dense @ B.numpy(), rtol=1e-12, atol=1e-13)
+        # duplicate entries (non-canonical CSR) are summed before the plan is built
+        raw = sp.csr_matrix(dense.shape)                                   # row 0 carries its first 7 entries twice
+        raw.data, raw.indices, raw.indptr = np.r_[dense.data[:7], dense.data], np.r_[dense.indices[:7], dense.indices], \
+            np.r_[0, dense.indptr[1:] + 7]
+        assert not raw.has_canonical_format
+        Rd = CsrMatrix(raw, dev)
+        B = K.to_padded(rng.standard_normal((dense.shape[0], 266)), dev)
+        np.testing.assert_allclose(Rd.matmat(B).numpy(), raw @ B.numpy(), rtol=1e-12, atol=1e-13)
