@@ -306,7 +306,7 @@ def run_ours(args):
         ach = by / (avg_ms * 1e-3) * 1e-9
         traffic_hbm = None
         tf = os.path.join(ROOT, "profiles", "dgemm_traffic.json")
-        if os.path.exists(tf) and tag[1] == "csr_spmm_dmma_frag_kernel":
+        if os.path.exists(tf) and tag[1] in ("csr_spmm_dmma_frag_kernel", "csr_spmm_dmma_pipe_kernel"):   # same records, same bytes
             try:
                 traffic_hbm = json.load(open(tf)).get(args.workload, {}).get("spmm_frag_dram_bytes_per_launch")
             except Exception:

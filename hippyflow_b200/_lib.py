@@ -64,6 +64,7 @@ def lib():
         "hfb_csr_frag_blob_stride": (i64, [i32, i32]),
         "hfb_csr_pack_clusters_frag": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
         "hfb_csr_spmm_dmma_frag": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_spmm_dmma_pipe": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -93,7 +94,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
             "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma", "hfb_csr_spmm_regblock", "hfb_csr_spmm_dmma",
-            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag",
+            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", "hfb_csr_spmm_dmma_pipe",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -359,17 +360,19 @@ def csr_pack_clusters_frag(indptr, indices, data, order, cptr, max_rows, max_col
     return blobs
 
 
-def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0):
+def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0, pipelined=False):
     """C = M @ B with the fragment-blob DMMA kernel; ``plan`` carries ``fblobs`` (linalg.CsrMatrix._frag_blobs).
-    ``chunk_cols`` = columns staged per CTA (0: whole rows up to 320 columns)."""
+    ``chunk_cols`` = columns staged per CTA (0: whole rows up to 320 columns); ``pipelined`` = resident CTAs walking the
+    clusters with double-buffered rows (hfb_csr_spmm_dmma_pipe)."""
     L = lib()
     _req(B, "B")
     n, m = B.shape
     if out is None:
         out = padded_empty(n, m, B.device)
-    rc = L.hfb_csr_spmm_dmma_frag(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
-                                  int(chunk_cols), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
-    _check(rc, "hfb_csr_spmm_dmma_frag")
+    fn = L.hfb_csr_spmm_dmma_pipe if pipelined else L.hfb_csr_spmm_dmma_frag
+    rc = fn(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+            int(chunk_cols), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_dmma_pipe" if pipelined else "hfb_csr_spmm_dmma_frag")
     return out
 
 

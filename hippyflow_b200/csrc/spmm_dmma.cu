@@ -578,6 +578,215 @@ static int launch_dmma_frag(int64_t nclusters, int m, int W, const FragBlobLayou
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------- cluster-pipelined variant
+// The fragment-record kernel with the per-CTA latency chain taken off the critical path: a CTA walks clusters
+// c = blockIdx.x, blockIdx.x + gridDim.x, ... (grid = resident CTAs only) with two row buffers.  While the DMMAs of cluster c
+// run from buffer b, the cp.asyncs of cluster c' = c + gridDim.x fill buffer b^1, its A fragments / masks / result row
+// arrive in a second register set, and the column list of the cluster after that is already being fetched -- so every
+// global-memory round trip of a cluster overlaps the arithmetic of its predecessor inside the same CTA.
+template <int RH, int MAXKS>
+__global__ void __launch_bounds__(DM_WARPS * 32, 1)
+    csr_spmm_dmma_pipe_kernel(int m, int W, int st256, int nclusters, FragBlobLayout F, const unsigned char* __restrict__ blobs,
+                              const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc) {
+    constexpr int COLS = 4 * MAXKS;
+    constexpr int TILEW = 8 * RH;
+    constexpr int JW = (COLS + DM_WARPS - 1) / DM_WARPS;
+    constexpr int NA = 2 * RH;
+    constexpr int GSTRIDE = (DM_WARPS / RH) * TILEW;
+    extern __shared__ __align__(16) unsigned char smem_dm[];
+    double* sB = reinterpret_cast<double*>(smem_dm);                         // [2][COLS][pitch]
+    const int pitch = W + 4;
+    const uint32_t buf_bytes = (uint32_t)(COLS * pitch) * 8u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int h = warp % RH, cg = warp / RH;
+    const int c0 = blockIdx.y * W;
+    const int wcur = min(W, m - c0);
+    const int width = m + (m & 1);
+    const int npiece = (min(W, width - c0) + 1) >> 1;
+    const int npiece_all = (((wcur + TILEW - 1) / TILEW) * TILEW) >> 1;
+    const int ngrp = (wcur > cg * TILEW) ? (wcur - cg * TILEW + GSTRIDE - 1) / GSTRIDE : 0;
+    const uint32_t kstep_bytes = (uint32_t)(4 * pitch) * 8u;
+    uint32_t bfrag0, stage0;
+    asm volatile("mov.u32 %0, %1;" : "=r"(bfrag0) : "r"(smem_u32(sB + t * pitch + cg * TILEW + (RH == 2 ? 2 * g : g))));
+    asm volatile("mov.u32 %0, %1;" : "=r"(stage0) : "r"(smem_u32(sB + warp * pitch)));
+
+    int mycol[JW];
+    int ncol_s = 0;                                                         // columns of the cluster whose list is in mycol
+    auto load_cols = [&](int c) {
+        const unsigned char* blob = blobs + (size_t)c * F.stride;
+        ncol_s = __ldg(reinterpret_cast<const int*>(blob) + 1);
+        const int* gcols = reinterpret_cast<const int*>(blob + F.off_cols);
+#pragma unroll
+        for (int i = 0; i < JW; ++i) mycol[i] = __ldg(gcols + warp + DM_WARPS * i);
+    };
+    auto stage = [&](int which) {                                           // rows of the cluster described by mycol / ncol_s
+        const int kpad = ((ncol_s + 3) >> 2) << 2;
+#pragma unroll
+        for (int i = 0; i < JW; ++i) {
+            const int j = warp + DM_WARPS * i;
+            if (j < kpad) {
+                const bool real = j < ncol_s;
+                const double* src = B + (real ? (long long)mycol[i] * ldb + c0 : 0);
+                const uint32_t dst = stage0 + which * buf_bytes + (uint32_t)(i * DM_WARPS * pitch) * 8u;
+                for (int p = lane; p < npiece_all; p += 32) {
+                    const bool valid = real && p < npiece;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u * p),
+                                 "l"(src + (valid ? 2 * p : 0)), "r"(valid ? 16 : 0)
+                                 : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_frags = [&](int c, double (&af)[MAXKS], unsigned& nzf, int& orowf) {
+        const unsigned char* blob = blobs + (size_t)c * F.stride;
+        const int* hdr = reinterpret_cast<const int*>(blob);
+        const int nrow = __ldg(hdr);
+        nzf = (unsigned)__ldg(hdr + 2 + h);
+        const double* afrag = reinterpret_cast<const double*>(blob + F.off_afrag) + h * 32 + lane;
+#pragma unroll
+        for (int ks = 0; ks < MAXKS; ++ks) af[ks] = __ldg(afrag + ks * RH * 32);   // zero blocks are stored as zeros
+        const int r = g + 8 * h;
+        orowf = r < nrow ? __ldg(reinterpret_cast<const int*>(blob + F.off_outrow) + r) : -1;
+    };
+
+    int c = blockIdx.x;
+    if (c >= nclusters) return;
+    load_cols(c);
+    stage(0);
+    double a[MAXKS];
+    unsigned nz;
+    int orow;
+    load_frags(c, a, nz, orow);
+    int cn = c + gridDim.x;
+    if (cn < nclusters) load_cols(cn);
+    int buf = 0;
+    while (true) {
+        const bool has_next = cn < nclusters;
+        double an[MAXKS];
+        unsigned nzn = 0;
+        int orown = -1;
+#pragma unroll
+        for (int ks = 0; ks < MAXKS; ++ks) an[ks] = 0.0;
+        if (has_next) {
+            stage(buf ^ 1);                                  // free since the closing barrier of the previous iteration
+            load_frags(cn, an, nzn, orown);
+            if (cn + (int)gridDim.x < nclusters) load_cols(cn + gridDim.x);
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
+        }
+        __syncthreads();
+        double acc[SLAB_NG][NA];
+#pragma unroll
+        for (int i = 0; i < SLAB_NG; ++i)
+#pragma unroll
+            for (int q = 0; q < NA; ++q) acc[i][q] = 0.0;
+        const uint32_t bcur = bfrag0 + buf * buf_bytes;
+#pragma unroll
+        for (int ks = 0; ks < MAXKS; ++ks) {
+            if (nz >> ks & 1u) {
+                const uint32_t bk = bcur + ks * kstep_bytes;
+#pragma unroll
+                for (int i = 0; i < SLAB_NG; ++i) {
+                    if (i < ngrp) {
+                        if (RH == 2) {
+                            const double2 b = lds128(bk + (uint32_t)(i * GSTRIDE) * 8u);
+                            dmma884(acc[i][0], acc[i][1], a[ks], b.x);
+                            dmma884(acc[i][NA - 2], acc[i][NA - 1], a[ks], b.y);
+                        } else {
+                            const double b = lds64(bk + (uint32_t)(i * GSTRIDE) * 8u);
+                            dmma884(acc[i][0], acc[i][1], a[ks], b);
+                        }
+                    }
+                }
+            }
+        }
+        if (orow >= 0) {
+            double* outp = C + (long long)orow * ldc + c0 + cg * TILEW + (RH == 2 ? 4 * t : 2 * t);
+#pragma unroll
+            for (int i = 0; i < SLAB_NG; ++i) {
+                if (i < ngrp) {
+                    double* cp = outp + i * GSTRIDE;
+                    const int cc = c0 + cg * TILEW + i * GSTRIDE + (RH == 2 ? 4 * t : 2 * t);
+                    if (RH == 2) {
+                        if (st256 && cc + 3 < m) {
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(cp)),
+                                         "d"(acc[i][0]), "d"(acc[i][NA - 2]), "d"(acc[i][1]), "d"(acc[i][NA - 1])
+                                         : "memory");
+                        } else {
+                            if (cc + 1 < m) {
+                                *reinterpret_cast<double2*>(cp) = make_double2(acc[i][0], acc[i][NA - 2]);
+                            } else if (cc < m) {
+                                cp[0] = acc[i][0];
+                            }
+                            if (cc + 3 < m) {
+                                *reinterpret_cast<double2*>(cp + 2) = make_double2(acc[i][1], acc[i][NA - 1]);
+                            } else if (cc + 2 < m) {
+                                cp[2] = acc[i][1];
+                            }
+                        }
+                    } else {
+                        if (cc + 1 < m) {
+                            *reinterpret_cast<double2*>(cp) = make_double2(acc[i][0], acc[i][1]);
+                        } else if (cc < m) {
+                            cp[0] = acc[i][0];
+                        }
+                    }
+                }
+            }
+        }
+        if (!has_next) break;
+        __syncthreads();                                     // everyone is done reading `buf` before the next stage refills it
+#pragma unroll
+        for (int ks = 0; ks < MAXKS; ++ks) a[ks] = an[ks];
+        nz = nzn;
+        orow = orown;
+        cn += gridDim.x;
+        buf ^= 1;
+    }
+}
+
+template <int RH, int MAXKS>
+static int launch_dmma_pipe(int64_t nclusters, int m, int W, const FragBlobLayout& F, const void* blobs, const double* B,
+                            int64_t ldb, double* C, int64_t ldc, cudaStream_t stream) {
+    constexpr int COLS = 4 * MAXKS;
+    const size_t smem = 2 * sizeof(double) * (size_t)COLS * (W + 4);
+    if (smem > 227 * 1024 || W > 64 * SLAB_NG) return HFB_E_UNSUPPORTED;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_pipe_kernel<RH, MAXKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    const int nchunk = (m + W - 1) / W;
+    if (nchunk > 65535) return HFB_E_UNSUPPORTED;
+    static int sms = 0, per_sm = 0;
+    static size_t per_sm_for = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;
+    }
+    if (!per_sm || per_sm_for != smem) {           // resident CTAs per SM for this shared-memory size (cached)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_dmma_pipe_kernel<RH, MAXKS>, DM_WARPS * 32, smem) !=
+                cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        per_sm_for = smem;
+    }
+    long long gx = (long long)sms * per_sm;
+    if (gx > nclusters) gx = nclusters;
+    const int st256 = ((reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc & 3) == 0) ? 1 : 0;
+    dim3 grid((unsigned)gx, (unsigned)nchunk);
+    csr_spmm_dmma_pipe_kernel<RH, MAXKS><<<grid, DM_WARPS * 32, smem, stream>>>(
+        m, W, st256, (int)nclusters, F, static_cast<const unsigned char*>(blobs), B, ldb, C, ldc);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
 }  // namespace hfb
 
 using namespace hfb;
@@ -711,8 +920,8 @@ extern "C" int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, cons
     return 0;
 }
 
-extern "C" int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
-                                      int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
+static int dmma_frag_dispatch(int pipelined, int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                              int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nclusters <= 0 || m <= 0 || !blobs || !B || !C || B == C || chunk_cols < 0) return HFB_E_BADARG;
     if (ldb < m + (m & 1) || ldc < m) return HFB_E_BADARG;
@@ -730,7 +939,9 @@ extern "C" int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* 
         W = (int)(((m + nchunk - 1) / nchunk + 15) / 16 * 16);
         if (8u * (size_t)(4 * maxks) * (W + 4) <= 100u * 1024u || W <= 16) break;
     }
-#define HFB_DM_FRAG(RH_, KS_) launch_dmma_frag<RH_, KS_>(nclusters, (int)m, W, F, blobs, B, ldb, C, ldc, stream)
+#define HFB_DM_FRAG(RH_, KS_)                                                                         \
+    (pipelined ? launch_dmma_pipe<RH_, KS_>(nclusters, (int)m, W, F, blobs, B, ldb, C, ldc, stream) \
+               : launch_dmma_frag<RH_, KS_>(nclusters, (int)m, W, F, blobs, B, ldb, C, ldc, stream))
     if (rh == 1) {
         if (maxks == 4) return HFB_DM_FRAG(1, 4);
         if (maxks == 6) return HFB_DM_FRAG(1, 6);
@@ -741,4 +952,14 @@ extern "C" int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* 
     if (maxks == 8) return HFB_DM_FRAG(2, 8);
     return HFB_DM_FRAG(2, 12);
 #undef HFB_DM_FRAG
+}
+
+extern "C" int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                                      int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream) {
+    return dmma_frag_dispatch(0, nclusters, m, blobs, max_rows, max_cols, chunk_cols, B, ldb, C, ldc, stream);
+}
+
+extern "C" int hfb_csr_spmm_dmma_pipe(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                                      int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream) {
+    return dmma_frag_dispatch(1, nclusters, m, blobs, max_rows, max_cols, chunk_cols, B, ldb, C, ldc, stream);
 }

@@ -22,6 +22,8 @@ class CsrMatrix:
     """Sparse SPD weight matrix (mass matrix M, prior precision R) resident on the device as int32 CSR,
     the format the reference exports (PODProjector.py:695-697)."""
 
+    WIDE_DEFAULT = "pipe"       # kernel 'auto' uses for blocks of >= 192 columns ("pipe" or "frag")
+
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
         if not M.has_canonical_format:      # the cluster kernels scatter entries by (row, column): no duplicates allowed
@@ -42,6 +44,7 @@ class CsrMatrix:
         #   "auto"     (default) "frag" for m >= 192, "dmma" for narrower blocks, "staged" when the clusters exceed the
         #              DMMA kernels' register budget (16 rows x 48 distinct columns)
         #   "frag"     dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
+        #   "pipe"     "frag" with resident CTAs walking the clusters, next cluster's rows in flight during the DMMAs
         #   "dmma"     same arithmetic, records decoded in the kernel, double-buffered 64-column panels
         #   "staged"   cp.async panels + one LDS.128 pair per matrix entry (round-1 default, LSU-bound)
         #   "regblock" dense cluster block against B rows loaded straight into registers (scoreboard-bound)
@@ -130,16 +133,17 @@ class CsrMatrix:
         wide = K._ld(B) >= m + (m & 1)                      # the padding column of an odd width may be read
         if self.plan is not None and m >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
+            import os
             impl = self.impl
             dmma_ok = wide and self.plan["max_rows"] <= 16 and self.plan["max_cols_cap"] <= 48
             if impl == "auto":
                 # measured on B200 (profiles/r01_spmm_variants.md): whole-row fragment-record kernel for wide blocks,
                 # double-buffered 64-column panels for narrow ones (a CTA's share is too small to amortise its latency chain)
-                impl = ("frag" if m >= 192 else "dmma") if dmma_ok else "staged"
-            if impl == "frag" and dmma_ok:
-                import os
+                impl = (os.environ.get("HFB_SPMM_WIDE", self.WIDE_DEFAULT) if m >= 192 else "dmma") if dmma_ok else "staged"
+            if impl in ("frag", "pipe") and dmma_ok:
                 return K.csr_spmm_dmma_frag(self._frag_blobs(self.plan, self.device), B, out,
-                                            int(os.environ.get("HFB_SPMM_FRAG_W", 0))), "csr_spmm_dmma_frag_kernel"
+                                            int(os.environ.get("HFB_SPMM_FRAG_W", 0)), pipelined=(impl == "pipe")), \
+                    ("csr_spmm_dmma_pipe_kernel" if impl == "pipe" else "csr_spmm_dmma_frag_kernel")
             if impl == "dmma" and dmma_ok:
                 return K.csr_spmm_dmma(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_dmma_kernel"
             if impl == "tma" and wide:

@@ -157,6 +157,11 @@ int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, const int32_t* 
                                void* blobs_out /* HOST, nclusters * stride bytes */);
 int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                            int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+/* Cluster-pipelined form of the same kernel: only the resident CTAs are launched and each walks clusters blockIdx.x,
+ * blockIdx.x + gridDim.x, ... with two row buffers, so the row copies, fragment loads and column list of the next clusters
+ * overlap the DMMAs of the current one inside the CTA.  Same arguments and results (bitwise) as hfb_csr_spmm_dmma_frag. */
+int hfb_csr_spmm_dmma_pipe(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                           int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.

@@ -232,7 +232,7 @@ def emulated_device():
     def csr_spmm_dmma(plan, B, out=None):
         return csr_spmm_regblock(plan, B, out)     # reads the same fields of the same records
 
-    def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0):
+    def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0, pipelined=False):
         key = ("frag", id(plan))
         if key not in cache:
             cache[key] = decode_frag_blobs(K, plan["fblobs"].numpy(), plan["max_rows"], plan["max_cols_cap"], plan["order"].numel())

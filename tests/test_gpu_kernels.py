@@ -115,7 +115,7 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag"])
+@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag", "pipe"])
 @pytest.mark.parametrize("m", [96, 137, 138, 266, 300, 511, 1100])
 def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     """The cluster-plan kernels (persistent TMA ring / cp.async panels / register-blocked) on a mesh matrix large enough to get a
@@ -191,26 +191,29 @@ def test_csr_spmm_dmma_cluster_caps(K, cuda_device, caps, m, mode, monkeypatch):
     assert torch.equal(K.csr_spmm_dmma(plan, K.to_padded(B, cuda_device)), out)
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
 @pytest.mark.parametrize("chunk", [0, 64, 144])
 @pytest.mark.parametrize("caps", [(8, 16), (8, 24), (8, 32), (8, 40), (12, 24), (16, 24), (16, 32), (16, 48), (5, 20)])
 @pytest.mark.parametrize("m", [10, 74, 138, 266, 267, 330, 600])
-def test_csr_spmm_dmma_frag_cluster_caps(K, cuda_device, caps, m, chunk):
+def test_csr_spmm_dmma_frag_cluster_caps(K, cuda_device, caps, m, chunk, pipelined):
     """Fragment-record DMMA kernel: every (row halves, k-steps) instantiation, whole-row and chunked staging, widths that
     need 1..5 column groups per warp and several chunks, odd widths; padding untouched; bitwise reproducible."""
     from hippyflow_b200 import synthetic as syn
     from hippyflow_b200.linalg import CsrMatrix
-    M = syn.p1_mass_matrix(41, 37).tocsr()
+    # the pipelined kernel launches resident CTAs only: the larger mesh gives every CTA 2-4 clusters to walk
+    M = (syn.p1_mass_matrix(90, 80) if pipelined else syn.p1_mass_matrix(41, 37)).tocsr()
     n = M.shape[0]
     plan = CsrMatrix._frag_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
     B = np.random.default_rng(m).standard_normal((n, m))
     out = K.padded_empty(n, m, cuda_device)
     full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
     full.fill_(7.0)
-    K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), out, chunk_cols=chunk)
+    K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), out, chunk_cols=chunk, pipelined=pipelined)
     np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
     if K._ld(out) > m:
         assert bool((full[:, m:] == 7.0).all())
-    assert torch.equal(K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), chunk_cols=chunk), out)
+    # the per-cluster and the cluster-pipelined kernel add in the same order: bitwise equal, run to run and to each other
+    assert torch.equal(K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), chunk_cols=chunk, pipelined=not pipelined), out)
 
 
 def test_csr_spmm_dmma_frag_irregular_and_unaligned_rows(K, cuda_device):
@@ -260,7 +263,7 @@ def test_csr_spmm_dmma_irregular_matrix_and_limits(K, cuda_device):
         K.csr_spmm_dmma(big, K.to_padded(B, cuda_device))
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag"])
+@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag", "pipe"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
     import scipy.sparse as sp

@@ -14,10 +14,10 @@ dev = torch.device("cuda:0")
 PEAK = 6542.1   # MEASURED_PEAKS.json hbm_gbs
 quick = "--quick" in sys.argv
 shapes = ((263169, 266),) if quick else ((263169, 266), (1002001, 266), (251001, 138))
-caps = ((16, 32),) if quick else ((16, 32), (12, 32), (8, 24), (8, 20))
+caps = ((16, 32),) if quick else ((16, 32), (12, 32), (8, 24))
 if os.environ.get("HFB_CHECK_CAPS", "").replace(",", "").isdigit():
     caps = (tuple(int(v) for v in os.environ["HFB_CHECK_CAPS"].split(",")),)
-impls = ("tma", "staged", "regblock", "dmma", "frag")
+impls = ("tma", "staged", "regblock", "dmma", "frag", "pipe")
 if "--impls" in sys.argv:
     impls = tuple(sys.argv[sys.argv.index("--impls") + 1].split(","))
 results = []

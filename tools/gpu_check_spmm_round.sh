@@ -15,10 +15,13 @@ stamp "smoke rc=$?: $(tail -1 gpurun_out/smoke.log)"
 timeout 600 python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err
 stamp "bench rc=$?"
 head -c 400 gpurun_out/bench_1gpu.json; echo
-HFB_CHECK_CAPS=16,32 timeout 300 python tools/check_spmm.py --impls staged,tma,regblock,dmma,frag --json gpurun_out/spmm_variants.json \
+HFB_CHECK_CAPS=16,32 timeout 300 python tools/check_spmm.py --impls staged,tma,regblock,dmma,frag,pipe --json gpurun_out/spmm_variants.json \
     > gpurun_out/spmm_variants.log 2>&1
 stamp "variant table rc=$?"
 grep "GB/s" gpurun_out/spmm_variants.log | cut -c1-130
+HFB_CHECK_CAPS=8,24 timeout 200 python tools/check_spmm.py --impls frag,pipe --json gpurun_out/spmm_variants_8_24.json \
+    > gpurun_out/spmm_variants_8_24.log 2>&1
+grep "GB/s" gpurun_out/spmm_variants_8_24.log | cut -c1-130
 timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/bench_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 stamp "ncu launch list rc=$?"
