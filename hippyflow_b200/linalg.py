@@ -22,7 +22,7 @@ class CsrMatrix:
     """Sparse SPD weight matrix (mass matrix M, prior precision R) resident on the device as int32 CSR,
     the format the reference exports (PODProjector.py:695-697)."""
 
-    WIDE_DEFAULT = "pipe"       # kernel 'auto' uses for blocks of >= 192 columns ("pipe" or "frag")
+    WIDE_DEFAULT = "frag"       # kernel 'auto' uses for blocks of >= 192 columns ("frag"; "pipe" measured 2x slower, kept as an evaluated alternative)
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
