@@ -35,8 +35,8 @@ class CsrMatrix:
         self.rowptr = torch.as_tensor(np.asarray(M.indptr, dtype=np.int32), device=device)
         self.colind = torch.as_tensor(np.asarray(M.indices, dtype=np.int32), device=device)
         self.val = torch.as_tensor(np.asarray(M.data, dtype=np.float64), device=device)
-        # cluster-staged SpMM plan (one-time host preprocessing): clusters of <= 64 mesh-neighbouring rows whose distinct
-        # B rows (<= 128) are staged in shared memory by the kernel
+        # SpMM plan (one-time host preprocessing, _build_plan): clusters of <= 16 mesh-neighbouring rows touching <= 32 (48
+        # for dense rows) distinct columns; the cluster kernels stage exactly those rows of B in shared memory
         self.order = None
         self.plan = None
         import os
