@@ -2,7 +2,7 @@
 collective API.  Importing the package does not load the CUDA library; the first
 numerical call does, and raises if it is missing (no CPU fallback)."""
 from .collectives import (CollectiveOperator, MatrixMultCollectiveOperator, MultipleSamePartitioningPDEsCollective,
-                          MultipleSerialPDEsCollective, NcclCollective, NullCollective, TorchCollective)
+                          MultipleSerialPDEsCollective, NcclCollective, NullCollective, TorchCollective, splitCommunicators)
 from .multivector import DeviceMultiVector, DeviceVector, dense_to_mv_local, mv_to_dense, mv_to_dense_local
 from .parameterList import ParameterList
 from .randomized import doublePass, doublePassG

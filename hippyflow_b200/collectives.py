@@ -184,6 +184,33 @@ def MultipleSerialPDEsCollective(comm=None):
 NcclCollective = TorchCollective
 
 
+def splitCommunicators(comm_world, n_subdomain, n_instances):
+    """hippyflow/collectives/comm_utils.py:19-40 on torch.distributed: split the ranks of ``comm_world`` (a process
+    group, or None for the default group) into an (n_instances x n_subdomain) grid.  Rows (colour = rank // n_subdomain)
+    are the mesh-parallel groups of one sampling instance, columns (colour = rank % n_subdomain) the sample-parallel
+    groups handed to the collectives.  Returns (mesh_constructor_comm, collective_comm) -- the groups this rank belongs
+    to.  Every rank of ``comm_world`` must call it (``dist.new_group`` is collective).  The stored-data path of this
+    package runs with n_subdomain = 1: the collective group is then the whole world."""
+    if dist is None or not dist.is_initialized():
+        raise RuntimeError("splitCommunicators needs an initialised torch.distributed process group")
+    world_size = dist.get_world_size(comm_world)
+    my_rank = dist.get_rank(comm_world)
+    assert world_size == n_subdomain * n_instances
+    to_global = (lambda r: dist.get_global_rank(comm_world, r)) if comm_world is not None else (lambda r: r)
+    mesh_comm = collective_comm = None
+    for color in range(n_instances):                       # rows: consecutive ranks, ordered by key = rank % n_subdomain
+        ranks = [to_global(color * n_subdomain + key) for key in range(n_subdomain)]
+        grp = dist.new_group(ranks=ranks)
+        if my_rank // n_subdomain == color:
+            mesh_comm = grp
+    for key in range(n_subdomain):                         # columns: stride n_subdomain, ordered by colour
+        ranks = [to_global(color * n_subdomain + key) for color in range(n_instances)]
+        grp = dist.new_group(ranks=ranks)
+        if my_rank % n_subdomain == key:
+            collective_comm = grp
+    return mesh_comm, collective_comm
+
+
 class CollectiveOperator:
     """hippyflow/collectives/collectiveOperator.py:14-55 -- local apply, then allReduce of the result."""
 

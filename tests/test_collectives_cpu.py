@@ -115,6 +115,45 @@ def _shim_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _split_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import hippyflow_b200 as hf
+        mesh_comm, coll_comm = hf.splitCommunicators(None, 2, 2)            # 2 instances x 2 subdomains
+        mesh, coll = hf.MultipleSamePartitioningPDEsCollective(mesh_comm), hf.MultipleSerialPDEsCollective(coll_comm)
+        res = {"mesh": (mesh.size(), mesh.rank()), "coll": (coll.size(), coll.rank()),
+               "mesh_sum": mesh.allReduce(float(rank), "sum"), "coll_avg": coll.allReduce(float(rank), "avg")}
+        b = np.array([float(rank)])
+        coll.bcast(b, root=1)                                                # root is a rank WITHIN the sample group
+        res["coll_bcast"] = float(b[0])
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_communicators_grid_gloo_world4():
+    """comm_utils.py:19-40: rank r sits in row r // n_subdomain (mesh group, key r % n_subdomain) and column
+    r % n_subdomain (sample group, key r // n_subdomain)."""
+    world, port = 4, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_split_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert out[r]["mesh"] == (2, r % 2) and out[r]["coll"] == (2, r // 2)
+        assert out[r]["mesh_sum"] == float(2 * (r // 2) * 2 + 1)              # ranks {0,1} -> 1, {2,3} -> 5
+        assert out[r]["coll_avg"] == float(r % 2) + 1.0                        # ranks {0,2} -> 1, {1,3} -> 2
+        assert out[r]["coll_bcast"] == float(2 + r % 2)                        # group rank 1 of column k is world rank 2 + k
+
+
 def test_sharded_mean_shift_host_logic_gloo_world2():
     """The N > 1 host logic of the weighted randomized POD (per-rank provisional means, global mean allreduce, rank-one
     corrections, sketch allreduce) over a world_size-2 gloo group, kernels replaced by the CPU test double."""
