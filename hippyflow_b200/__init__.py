@@ -8,5 +8,6 @@ from .parameterList import ParameterList
 from .randomized import doublePass, doublePassG
 from .linalg import CsrCGSolver, CsrMatrix, SampleCovariance, b_orthonormalize
 from .modeling import *
+from .dataIO import compress_dataset
 
 __version__ = "0.1.0"

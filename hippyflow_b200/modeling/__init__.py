@@ -2,7 +2,7 @@ from .PODProjector import PODParameterList, PODProjector, PODProjectorFromData, 
 from .KLEProjector import KLEParameterList, KLEProjector, MassPreconditionedCovarianceOperator, SampleCovariancePrior
 from .activeSubspaceProjector import (ActiveSubspaceParameterList, ActiveSubspaceProjector, SparsePrior,
                                       StoredJacobians)
-from .operators import (JTJ, MeanJTJfromDataOperator, SampleCovarianceOperator, SandwichedCovarianceOperator,
-                        SummedListOperator)
+from .operators import (JJT, JTJ, LowRankRectangularOperator, MeanJTJfromDataOperator, SampleCovarianceOperator,
+                        SandwichedCovarianceOperator, SummedListOperator, npToDolfinOperator)
 from .projection import jacobian_action, jacobian_transpose_action, project_data, reduced_jacobians
 from .errors import PriorPreconditionedProjector, jacobian_truncated_svd, projection_errors

@@ -241,3 +241,134 @@ class SummedListOperator:
     def matMvMult(self, X, Y):
         self._accumulate(lambda op, a, b: op.matMvMult(a, b), X, Y,
                          lambda: DeviceMultiVector(Y.tensor().shape[0], Y.nvec(), device=Y.tensor().device))
+
+
+def _tma_operand(t):
+    """A GEMM operand must start on a 16-byte boundary with an even leading dimension (TMA); a column view of a
+    multivector block (``mv[j]``) may not -- stage it into an aligned buffer then."""
+    if t.data_ptr() % 16 or K._ld(t) % 2:
+        return K.to_padded(t, t.device, pad=2 if t.shape[1] == 1 else 16)
+    return t
+
+
+class JJT:
+    """J J^T of ONE stored Jacobian (dQ, dM): the stored-data form of hippyflow/modeling/jacobian.py:169-193
+    (``J.transpmult`` then ``J.mult``, each a PDE solve there, each one DMMA GEMM here).  Output-space operator, used by
+    the output active subspace E[J J^T] (activeSubspaceProjector.py:576-583)."""
+
+    overwrites = True
+
+    def __init__(self, J, device=None):
+        if device is None:
+            device = J.device if K.is_device_tensor(J) else torch.device("cuda", torch.cuda.current_device())
+        self._J = _as_device_rows(J, device)                      # (dQ, dM)
+        self.dQ, self.dM = self._J.shape
+
+    def init_vector(self, x, dim=None):
+        x.init(self.dQ)
+
+    def matMvMult(self, X, Y):
+        W = K.dgemm(K.HFB_TN, self._J, _tma_operand(X.tensor()))  # J^T X   (dM, m)
+        K.dgemm(K.HFB_NN, self._J, W, out=Y.tensor())             # J (J^T X)
+
+    def mult(self, x, y):
+        W = K.dgemm(K.HFB_TN, self._J, _tma_operand(x.storage_tensor()))
+        K.dgemm(K.HFB_NN, self._J, W, out=y.storage_tensor())
+
+    transpmult = mult
+
+
+class npToDolfinOperator:
+    """Dense matrix as an operator (hippyflow/modeling/operatorWrappers.py:19-52; the name is the reference's): the
+    matrix lives in HBM, ``mult`` / ``transpmult`` are one GEMM each on device vectors or multivector blocks."""
+
+    overwrites = True
+
+    def __init__(self, npArray, device=None):
+        assert len(npArray.shape) == 2
+        if device is None:
+            device = npArray.device if K.is_device_tensor(npArray) else torch.device("cuda", torch.cuda.current_device())
+        self.matrix = _as_device_rows(npArray, device)
+        self.domain_help = None
+        self.range_help = None
+
+    def init_vector(self, x, dim):
+        if dim == 0:
+            x.init(self.matrix.shape[0])
+        elif dim == 1:
+            x.init(self.matrix.shape[1])
+        else:
+            raise ValueError("dim must be 0 or 1")
+
+    def mult(self, x, y):
+        K.dgemm(K.HFB_NN, self.matrix, _tma_operand(x.storage_tensor()), out=y.storage_tensor())
+
+    def transpmult(self, x, y):
+        K.dgemm(K.HFB_TN, self.matrix, _tma_operand(x.storage_tensor()), out=y.storage_tensor())
+
+    def matMvMult(self, X, Y):
+        K.dgemm(K.HFB_NN, self.matrix, _tma_operand(X.tensor()), out=Y.tensor())
+
+    def matMvTranspmult(self, X, Y):
+        K.dgemm(K.HFB_TN, self.matrix, _tma_operand(X.tensor()), out=Y.tensor())
+
+
+class LowRankRectangularOperator:
+    """A = U diag(s) V^T with U (dQ, r), V (dM, r) device multivectors and s (r,) -- hippyflow/modeling/
+    lowRankRectangularOperator.py:19-72, e.g. the truncated SVD of a stored Jacobian (``Jsvd_data.npz``).
+    ``mult`` / ``transpmult`` follow the reference step by step (dot_v, elementwise scale, reduce into a zeroed y);
+    ``matMvMult`` / ``matMvTranspmult`` do the same for a whole block with two GEMMs and a row scaling."""
+
+    def __init__(self, U, s, V, U_init_vector=None, V_init_vector=None):
+        self.U = U if isinstance(U, DeviceMultiVector) else DeviceMultiVector.from_dense(np.asarray(U), _default_dev())
+        dev = self.U.tensor().device
+        self.V = V if isinstance(V, DeviceMultiVector) else DeviceMultiVector.from_dense(np.asarray(V), dev)
+        self.s = np.asarray(s.cpu() if isinstance(s, torch.Tensor) else s, dtype=np.float64).ravel()
+        assert self.U.nvec() == self.V.nvec() == self.s.size
+        self._s_dev = torch.as_tensor(self.s, device=dev)
+        self.U_init_vector = U_init_vector
+        self.V_init_vector = V_init_vector
+
+    def init_vector(self, x, dim):
+        if dim == 0:
+            if self.U_init_vector is not None:
+                self.U_init_vector(x)
+            else:
+                x.init(self.U.tensor().shape[0])
+        elif dim == 1:
+            if self.V_init_vector is not None:
+                self.V_init_vector(x)
+            else:
+                x.init(self.V.tensor().shape[0])
+        else:
+            raise ValueError('dim must be 0 or 1')
+
+    def mult(self, x, y):
+        """y = U s V^T x  (lowRankRectangularOperator.py:50-57)."""
+        Vtx = self.V.dot_v(x)
+        sVtx = self.s * Vtx
+        y.zero()
+        self.U.reduce(y, sVtx)
+
+    def transpmult(self, x, y):
+        """y = V s U^T x  (lowRankRectangularOperator.py:59-66)."""
+        Utx = self.U.dot_v(x)
+        sUtx = self.s * Utx
+        y.zero()
+        self.V.reduce(y, sUtx)
+
+    def _block(self, left, right, X, Y):
+        coef = K.dgemm(K.HFB_TN, right.tensor(), _tma_operand(X.tensor()))        # right^T X   (r, m)
+        K.dgemm(K.HFB_NN, left.tensor(), K.rowscale(self._s_dev, coef), out=Y.tensor())
+
+    def matMvMult(self, X, Y):
+        self._block(self.U, self.V, X, Y)
+
+    def matMvTranspmult(self, X, Y):
+        self._block(self.V, self.U, X, Y)
+
+
+def _default_dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("hippyflow_b200 needs a CUDA device: the hot path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())

@@ -104,7 +104,10 @@ class DeviceMultiVector:
         return K.dgemm(K.HFB_TN, self._t, mv._t).cpu().numpy()
 
     def dot_v(self, v):
-        return K.dgemm(K.HFB_TN, self._t, v._t).cpu().numpy()[:, 0]
+        vt = v._t
+        if vt.data_ptr() % 16 or K._ld(vt) % 2:          # a column view mv[j] with odd j: stage it for TMA
+            vt = K.to_padded(vt, vt.device, pad=2)
+        return K.dgemm(K.HFB_TN, self._t, vt).cpu().numpy()[:, 0]
 
     def reduce(self, y, alpha):
         """y += sum_i alpha_i self[i]."""

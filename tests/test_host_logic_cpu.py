@@ -146,3 +146,9 @@ def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
         Rd = CsrMatrix(raw, dev)
         B = K.to_padded(rng.standard_normal((dense.shape[0], 266)), dev)
         np.testing.assert_allclose(Rd.matmat(B).numpy(), raw @ B.numpy(), rtol=1e-12, atol=1e-13)
+
+
+def test_small_operator_classes(request):
+    import test_gpu_operators_extra as E
+    _run(E.test_jjt_and_dense_operator, request)
+    _run(E.test_low_rank_rectangular_operator, request)
