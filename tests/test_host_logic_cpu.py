@@ -152,3 +152,55 @@ def test_small_operator_classes(request):
     import test_gpu_operators_extra as E
     _run(E.test_jjt_and_dense_operator, request)
     _run(E.test_low_rank_rectangular_operator, request)
+
+
+def test_small_operator_classes_vs_reference_golden():
+    """LowRankRectangularOperator, PriorPreconditionedProjector and npToDolfinOperator of this package (host logic under the
+    CPU test double) against outputs of the UNMODIFIED reference classes (tests/golden/small_operators_ref.npz, generated by
+    oracle/make_golden_small_ops.py)."""
+    import os
+    import numpy as np
+    import hippyflow_b200 as hf
+    from hippyflow_b200 import synthetic as syn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_operators_ref.npz"))
+    # the golden vectors themselves obey the defining formulas
+    A = g["lr_U"] @ np.diag(g["lr_s"]) @ g["lr_V"].T
+    np.testing.assert_allclose(g["lr_mult"], g["lr_x"] @ A.T, rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(g["lr_transpmult"], g["lr_w"] @ A, rtol=1e-13, atol=1e-14)
+    with emulated_device() as dev:
+        op = hf.LowRankRectangularOperator(hf.DeviceMultiVector.from_dense(g["lr_U"], dev), g["lr_s"],
+                                           hf.DeviceMultiVector.from_dense(g["lr_V"], dev))
+        x, y = hf.DeviceVector(121, dev), hf.DeviceVector(100, dev)
+        for i in range(4):
+            x.set_local(g["lr_x"][i])
+            y.set_local(np.full(100, 3.0))
+            op.mult(x, y)
+            np.testing.assert_allclose(y.get_local(), g["lr_mult"][i], rtol=1e-12, atol=1e-13)
+            y.set_local(g["lr_w"][i])
+            op.transpmult(y, x)
+            np.testing.assert_allclose(x.get_local(), g["lr_transpmult"][i], rtol=1e-12, atol=1e-13)
+        X = hf.DeviceMultiVector.from_dense(g["lr_x"].T.copy(), dev)
+        Y = hf.DeviceMultiVector(100, 4, device=dev)
+        op.matMvMult(X, Y)
+        np.testing.assert_allclose(Y.to_dense(), g["lr_mult"].T, rtol=1e-12, atol=1e-13)
+
+        M = syn.p1_mass_matrix(int(g["pp_nx"]))
+        proj = hf.PriorPreconditionedProjector(hf.DeviceMultiVector.from_dense(g["pp_U"], dev), hf.CsrMatrix(M, dev))
+        n = M.shape[0]
+        px, py = hf.DeviceVector(n, dev), hf.DeviceVector(n, dev)
+        for i in range(4):
+            px.set_local(g["pp_x"][i])
+            py.set_local(np.ones(n))
+            proj.mult(px, py)
+            np.testing.assert_allclose(py.get_local(), g["pp_mult"][i], rtol=1e-12, atol=1e-13)
+
+        dop = hf.npToDolfinOperator(g["np_A"], device=dev)
+        u, v = hf.DeviceVector(1, dev), hf.DeviceVector(1, dev)
+        dop.init_vector(u, 0)
+        dop.init_vector(v, 1)
+        v.set_local(g["np_x"])
+        dop.mult(v, u)
+        np.testing.assert_allclose(u.get_local(), g["np_mult"], rtol=1e-13, atol=1e-14)
+        u.set_local(g["np_w"])
+        dop.transpmult(u, v)
+        np.testing.assert_allclose(v.get_local(), g["np_transpmult"], rtol=1e-13, atol=1e-14)
