@@ -217,7 +217,10 @@ class JTJ:
 
 class SummedListOperator:
     """hippyflow/modeling/activeSubspaceProjector.py:69-95: sum (or average) of a list of operators of equal
-    dimension.  Works on device vectors and, block-wise, on device multivectors."""
+    dimension.  Works on device vectors and, block-wise, on device multivectors.  One deliberate difference: the
+    reference seeds its accumulator with a copy of ``y`` (``temp = dl.Vector(y)``, :84-85), so whatever ``y`` holds on
+    entry is added to the sum; here the accumulator starts from zero.  Both agree for the zero-initialised ``y`` every
+    caller on the path passes (hIPPYlib's MatMvMult, activeSubspaceProjector.py:214-221)."""
 
     def __init__(self, operators, communicator=None, average=True):
         assert type(operators) is list
