@@ -1,6 +1,8 @@
-"""SpMM micro-benchmark: the cluster-plan kernels (cp.async panels "staged", persistent TMA ring "tma", register-blocked
-"regblock") at the benchmark shapes, for a few cluster caps.
-Usage (GPU box): python tools/check_spmm.py [--quick] [--impls staged,regblock] [--json out.json]"""
+"""SpMM micro-benchmark: the cluster-plan kernels ("staged" cp.async panels, "tma" persistent bulk-copy ring, "regblock"
+register-blocked, "dmma" DMMA panels, "frag" fragment records with whole-row staging, "pipe" cluster-pipelined frag) at the
+benchmark shapes, for a few cluster caps; every result is checked against torch's sparse product.
+Usage (GPU box): python tools/check_spmm.py [--quick] [--impls staged,frag] [--json out.json]; HFB_CHECK_CAPS=16,32 pins the caps.
+Operands (0.56-2.1 GB) exceed L2; times are the best of 20 launches (CUDA events)."""
 import json
 import os
 import sys
