@@ -204,3 +204,49 @@ def test_small_operator_classes_vs_reference_golden():
         u.set_local(g["np_w"])
         dop.transpmult(u, v)
         np.testing.assert_allclose(v.get_local(), g["np_transpmult"], rtol=1e-13, atol=1e-14)
+
+
+def test_pod_randomized_random_shapes_vs_oracle():
+    """Property test of the host logic (hypothesis): for random mesh sizes, sample counts, ranks, oversampling, mean
+    offsets, host / resident input and all mean-shift routes, the weighted randomized POD driven through the CPU test
+    double reproduces the oracle's eigenvalues (rel 1e-10 on the leading ones), M-orthonormality, encoder = M decoder and
+    the sample mean."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    import hippyflow_b200 as hf
+    from hippyflow_b200 import synthetic as syn
+    from oracle import projectors_np as P
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(nx=st.integers(5, 12), ny=st.integers(5, 12), N=st.integers(24, 90), rank=st.integers(2, 12),
+           over=st.integers(2, 10), mean=st.sampled_from([0.0, 0.5, 20.0]), shifted=st.booleans(),
+           route=st.sampled_from(["host_pipelined", "host_unpipelined", "resident_implicit", "resident_explicit"]),
+           seed=st.integers(0, 10_000))
+    def run(nx, ny, N, rank, over, mean, shifted, route, seed):
+        M = syn.p1_mass_matrix(nx, ny)
+        n = M.shape[0]
+        rank = min(rank, N - 1, n - 1)
+        m = min(rank + over, n)
+        u = syn.snapshots(n, N, r0=min(20, N), seed=seed) + mean * np.cos(np.linspace(0, 2, n))[None, :]
+        Om = syn.gaussian_omega(n, m, seed=seed + 1)
+        d0, U0, E0, s0 = P.pod_randomized_weighted(u, M, rank, Om, shifted=shifted)
+        with emulated_device() as dev:
+            proj = hf.PODProjectorFromData(None, M_output=M, device=dev)
+            kw = dict(shifted=shifted, method="randomized", Omega=Om, oversampling=m - rank)
+            if route.startswith("host"):
+                d, phi, Mphi, shift = proj.construct_subspace(u.copy(), rank, pipelined_upload=(route == "host_pipelined"), **kw)
+            else:
+                from hippyflow_b200 import _lib as K
+                Xd = K.to_padded(u, dev)
+                d, phi, Mphi, shift = proj.construct_subspace(Xd, rank, implicit_shift=(route == "resident_implicit"), **kw)
+        lead = d0 / d0[0] > 1e-5
+        np.testing.assert_allclose(d[lead], d0[lead], rtol=1e-10)
+        np.testing.assert_allclose(d[~lead], d0[~lead], rtol=0, atol=1e-12 * d0[0])
+        np.testing.assert_allclose(shift, s0, rtol=0, atol=1e-13 * (1.0 + abs(mean)))
+        G = phi.T @ Mphi
+        assert np.abs(G - np.eye(rank)).max() < 1e-9
+        np.testing.assert_allclose(Mphi, M @ phi, rtol=1e-11, atol=1e-14)
+        k = int(lead.sum())
+        assert P.principal_angle(phi[:, :k], U0[:, :k], M) < 1e-7
+
+    run()
