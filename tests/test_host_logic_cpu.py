@@ -250,3 +250,72 @@ def test_pod_randomized_random_shapes_vs_oracle():
         assert P.principal_angle(phi[:, :k], U0[:, :k], M) < 1e-7
 
     run()
+
+
+def test_active_subspace_and_kle_random_shapes_vs_oracle():
+    """Property test of the host logic (hypothesis) for the other two projectors: input active subspace from stored
+    Jacobians (plain / noise-weighted / prior-preconditioned with a CSR prior and the device block CG) and KLE from stored
+    draws ('mass' / 'identity'), random shapes and ranks, CPU test double vs oracle."""
+    import numpy as np
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    import hippyflow_b200 as hf
+    from hippyflow_b200 import synthetic as syn
+    from oracle import projectors_np as P
+
+    def check(d, d0, V, V0, Mw):
+        lead = d0 / d0[0] > 1e-5
+        np.testing.assert_allclose(d[lead], d0[lead], rtol=1e-9)
+        np.testing.assert_allclose(d, d0, rtol=0, atol=1e-10 * d0[0])
+        k = int(lead.sum())
+        assert P.principal_angle(V[:, :k], V0[:, :k], Mw) < 1e-7
+
+    @settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(nx=st.integers(4, 9), N=st.integers(4, 20), dQ=st.integers(3, 24), rank=st.integers(2, 10),
+           over=st.integers(2, 8), mode=st.sampled_from(["plain", "noise", "prior"]), seed=st.integers(0, 10_000))
+    def run_as(nx, N, dQ, rank, over, mode, seed):
+        Mp = syn.p1_mass_matrix(nx)
+        dM = Mp.shape[0]
+        rank = min(rank, dM - 1)
+        m = min(rank + over, dM)
+        J = syn.jacobians(N, dQ, dM, r0=min(16, dQ), seed=seed)
+        Om = syn.gaussian_omega(dM, m, seed=seed + 1)
+        G = None
+        if mode == "noise":
+            A = np.random.default_rng(seed).standard_normal((dQ, dQ))
+            G = A @ A.T / dQ + np.eye(dQ)
+        d0, V0, E0 = P.as_input_from_jacobians(J, rank, Om, noise_cov_inv=G, B_csr=Mp if mode == "prior" else None)
+        params = hf.ActiveSubspaceParameterList()
+        params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = rank, m - rank, False, False
+        with emulated_device() as dev:
+            prior = hf.SparsePrior(Mp, device=dev) if mode == "prior" else None
+            proj = hf.ActiveSubspaceProjector(hf.StoredJacobians(J, G), prior, parameters=params, device=dev)
+            proj.Omega_GN = Om
+            d, dec, enc = proj.construct_input_subspace(prior_preconditioned=(mode == "prior"))
+            V, E = hf.mv_to_dense(dec), hf.mv_to_dense(enc)
+        check(d, d0, V, V0, Mp if mode == "prior" else None)
+        if mode == "prior":
+            np.testing.assert_allclose(E, Mp @ V, rtol=1e-11, atol=1e-14)
+        else:
+            np.testing.assert_array_equal(E, V)
+
+    @settings(max_examples=10, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(nx=st.integers(5, 10), N=st.integers(30, 80), rank=st.integers(2, 12), over=st.integers(2, 8),
+           orth=st.sampled_from(["mass", "identity"]), seed=st.integers(0, 10_000))
+    def run_kle(nx, N, rank, over, orth, seed):
+        M = syn.p1_mass_matrix(nx)
+        n = M.shape[0]
+        m = min(rank + over, n)
+        m_data = syn.snapshots(n, N, r0=min(24, N), decay=1.5, seed=seed)
+        Om = syn.gaussian_omega(n, m, seed=seed + 1)
+        d0, V0, E0 = P.kle_from_samples(m_data, M, rank, Om, orth)
+        params = hf.KLEParameterList()
+        params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = rank, m - rank, False, False
+        with emulated_device() as dev:
+            proj = hf.KLEProjector(hf.SampleCovariancePrior(m_data, M, device=dev), parameters=params)
+            d, dec, enc = proj.construct_input_subspace(orth, Omega=Om)
+            V, E = hf.mv_to_dense(dec), hf.mv_to_dense(enc)
+        check(d, d0, V, V0, M if orth == "mass" else None)
+        np.testing.assert_allclose(E, (M @ V) if orth == "mass" else V, rtol=1e-11, atol=1e-14)
+
+    run_as()
+    run_kle()
