@@ -154,6 +154,80 @@ def test_split_communicators_grid_gloo_world4():
         assert out[r]["coll_bcast"] == float(2 + r % 2)                        # group rank 1 of column k is world rank 2 + k
 
 
+def _shim_sharded_worker(rank, world, port, q):
+    """Sample-sharded active subspace, collective PODProjector (Omega drawn on rank 0 + bcast) and sharded KLE through the
+    CPU test double over gloo: the cases the NCCL worker (tests/multigpu_worker.py) runs on GPUs."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import hippyflow_b200 as hf
+        from hippyflow_b200 import synthetic as syn
+        from oracle import projectors_np as P
+        from cpu_device_shim import emulated_device
+        with emulated_device() as dev:
+            coll = hf.MultipleSerialPDEsCollective()
+            # active subspace from sharded stored Jacobians (activeSubspaceProjector.py:427-463 with 'avg' over ranks)
+            J = syn.jacobians(8 * world, 30, 121, r0=16, seed=13)
+            OmJ = syn.gaussian_omega(121, 26, seed=14)
+            pa = hf.ActiveSubspaceParameterList()
+            pa["rank"], pa["oversampling"], pa["verbose"], pa["save_and_plot"] = 16, 10, False, False
+            asp = hf.ActiveSubspaceProjector(hf.StoredJacobians(J[rank * 8:(rank + 1) * 8]), None, collective=coll,
+                                             parameters=pa, device=dev)
+            asp.Omega_GN = OmJ
+            dj, Vj, _ = asp.construct_input_subspace(prior_preconditioned=False)
+            dj0, Vj0, _ = P.as_input_from_jacobians(J, 16, OmJ, ranks=world)
+            k = int(np.sum(dj0 / dj0[0] > 1e-5))
+            np.testing.assert_allclose(dj[:k], dj0[:k], rtol=1e-10)
+            assert P.principal_angle(hf.mv_to_dense(Vj)[:, :k], Vj0[:, :k]) < 1e-8
+            # PODProjector: rank 0 draws Omega, everybody else starts from zeros, bcast (PODProjector.py:367-374)
+            M = syn.p1_mass_matrix(12)
+            n = M.shape[0]
+            u = syn.snapshots(n, 32 * world, r0=24, seed=11)
+            params = hf.PODParameterList()
+            params["rank"], params["oversampling"], params["verbose"], params["save_and_plot"] = 10, 6, False, False
+            pp = hf.PODProjector(hf.StoredSnapshots(u[rank * 32:(rank + 1) * 32].copy()), collective=coll, parameters=params,
+                                 device=dev)
+            d2, U2 = pp.construct_subspace()
+            Om_used = pp.Omega.to_dense()
+            Om0 = Om_used.copy()
+            coll.bcast(Om0, root=0)
+            assert np.array_equal(Om0, Om_used)                               # every rank ended up with rank 0's draw
+            d3, U3 = P.pod_randomized(u, 10, Om_used, ranks=world)
+            k = int(np.sum(d3 / d3[0] > 1e-5))
+            np.testing.assert_allclose(d2[:k], d3[:k], rtol=1e-10)
+            assert P.principal_angle(hf.mv_to_dense(U2)[:, :k], U3[:, :k]) < 1e-8
+            # KLE 'mass' from sharded draws
+            kp = hf.KLEParameterList()
+            kp["rank"], kp["oversampling"], kp["verbose"], kp["save_and_plot"] = 8, 6, False, False
+            Omk = syn.gaussian_omega(n, 14, seed=15)
+            kle = hf.KLEProjector(hf.SampleCovariancePrior(u[rank * 32:(rank + 1) * 32], M, device=dev), collective=coll,
+                                  parameters=kp)
+            dk, Vk, Ek = kle.construct_input_subspace("mass", Omega=Omk)
+            dk0, Vk0, _ = P.kle_from_samples(u, M, 8, Omk, "mass", ranks=world)
+            np.testing.assert_allclose(dk, dk0, rtol=1e-10)
+            assert P.principal_angle(hf.mv_to_dense(Vk), Vk0, M) < 1e-8
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_projectors_host_logic_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shim_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out == {0: "ok", 1: "ok"}
+
+
 def test_sharded_mean_shift_host_logic_gloo_world2():
     """The N > 1 host logic of the weighted randomized POD (per-rank provisional means, global mean allreduce, rank-one
     corrections, sketch allreduce) over a world_size-2 gloo group, kernels replaced by the CPU test double."""
