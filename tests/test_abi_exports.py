@@ -44,6 +44,19 @@ def test_argument_validation_without_gpu():
     assert L.hfb_dgemm(0, 4, 4, 4, 1.0, 16, 5, 32, 4, 64, 4, None, 0, 0, None) == -2   # odd lda
     assert L.hfb_dgemm(0, 4, 4, 4, 1.0, 24, 4, 32, 4, 64, 4, None, 0, 0, None) == -2   # misaligned A
     assert L.hfb_csr_spmm(0, 4, None, None, None, None, 4, None, 4, None) == -1
+    # the cluster SpMM entry points: null pointers, caps beyond the kernels' budgets, misaligned / too narrow operands
+    for fn in (L.hfb_csr_spmm_dmma_frag, L.hfb_csr_spmm_dmma_pipe):
+        assert fn(10, 266, None, 16, 32, 0, 16, 272, 32, 272, None) == -1                 # no records
+        assert fn(10, 266, 64, 16, 32, 0, 16, 272, 16, 272, None) == -1                   # B == C
+        assert fn(10, 266, 64, 16, 32, 0, 16, 272, 32, 200, None) == -1                   # ldc < m
+        assert fn(10, 267, 64, 16, 32, 0, 16, 267, 32, 272, None) == -1                   # ldb < m rounded up to even
+        assert fn(10, 266, 64, 16, 32, 0, 24, 272, 32, 272, None) == -2                   # B not 16-byte aligned
+        assert fn(10, 266, 64, 16, 32, 0, 16, 273, 32, 272, None) == -2                   # odd ldb
+        assert fn(10, 266, 64, 32, 64, 0, 16, 272, 32, 272, None) == -5                   # clusters too large for the A fragments
+    assert L.hfb_csr_spmm_dmma(10, 266, 64, 32, 64, 200, 16, 272, 32, 272, None) == -5
+    assert L.hfb_csr_spmm_regblock(10, 266, 64, 64, 128, 500, 16, 272, 32, 272, None) == -5
+    assert L.hfb_csr_frag_blob_stride(16, 32) == 4352 and L.hfb_csr_frag_blob_stride(8, 24) == 1792
+    assert L.hfb_csr_frag_blob_stride(17, 32) < 0 and L.hfb_csr_frag_blob_stride(16, 49) < 0
     assert L.hfb_dgemm_workspace_bytes(0, 128, 16, 4096, 4) == 4 * 128 * 16 * 8
     assert L.hfb_dgemm_auto_splits(0, 4096, 266, 263169) >= 2
 
@@ -55,3 +68,5 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                # ... nor through the CPU test double of tests/ (numbers produced under it say nothing about the kernels)
+                assert "cpu_device_shim" not in src and "emulated_device" not in src, f
