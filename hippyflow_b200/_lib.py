@@ -110,6 +110,9 @@ def _check(rc, what):
 
 
 def _stream():
+    """Current stream of the current device.  One process per GPU is the supported setup; ``_req`` refuses operands
+    that live on another device than the current one (the launch would go to the wrong stream, and the C side keeps
+    per-process caches of the SM count and kernel attributes)."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -121,6 +124,9 @@ def is_device_tensor(t):
 def _req(t, name):
     if not (is_device_tensor(t) and t.dtype == torch.float64 and t.dim() == 2 and t.stride(1) == 1):
         raise HfbError("%s must be a 2-D float64 CUDA tensor with unit inner stride" % name)
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise HfbError("%s lives on cuda:%d but the current device is cuda:%d: wrap the call in torch.cuda.device(...)"
+                       % (name, t.device.index, torch.cuda.current_device()))
     return t
 
 

@@ -64,9 +64,31 @@ class TorchCollective:
     def _allReduce_tensor(self, t, op):
         if op not in ("sum", "avg"):
             raise NotImplementedError("Unknown operation *{0}* in TorchCollective.allReduce".format(op))
+        if not t.is_contiguous():
+            # NCCL rejects strided views (a DeviceVector is an (n, 1) column view of a padded block): reduce a packed
+            # copy and write it back, so v is still updated in place
+            tmp = t.contiguous()
+            self._allReduce_tensor(tmp, op)
+            t.copy_(tmp)
+            return t
+        if op == "avg" and not t.is_floating_point():
+            # integer 'avg' truncates like the in-place assignment v[:] = (1/size) * receive (collective.py:65-68)
+            tmp = t.to(torch.float64)
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+            t.copy_((tmp * (1.0 / float(self.size()))).to(t.dtype))
+            return t
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         if op == "avg":
             t.mul_(1.0 / float(self.size()))
+        return t
+
+    def _bcast_tensor(self, t, src):
+        if t.is_contiguous():
+            dist.broadcast(t, src=src, group=self.group)
+            return t
+        tmp = t.contiguous()
+        dist.broadcast(tmp, src=src, group=self.group)
+        t.copy_(tmp)
         return t
 
     def allReduce_async(self, t, op="sum"):
@@ -80,7 +102,7 @@ class TorchCollective:
         if op not in ("sum", "avg"):
             raise NotImplementedError("Unknown operation *{0}* in TorchCollective.allReduce".format(op))
         t = torch.from_numpy(np.ascontiguousarray(v)).to(self._host_device())
-        self._allReduce_tensor(t, op)
+        self._allReduce_tensor(t, op)                       # integer 'avg' truncates there, as collective.py:65-68 does
         v[...] = t.cpu().numpy().reshape(v.shape)
         return v
 
@@ -103,12 +125,7 @@ class TorchCollective:
         elif isinstance(v, np.ndarray):
             return self._allReduce_array(v, op)
         elif isinstance(v, torch.Tensor):
-            if v.is_contiguous():
-                return self._allReduce_tensor(v, op)
-            tmp = v.contiguous()
-            self._allReduce_tensor(tmp, op)
-            v.copy_(tmp)
-            return v
+            return self._allReduce_tensor(v, op)
         elif hasattr(v, "storage_tensor"):
             # DeviceMultiVector / DeviceVector: reduce the whole padded block in one call
             self._allReduce_tensor(v.storage_tensor(), op)
@@ -144,15 +161,9 @@ class TorchCollective:
             v[...] = t.cpu().numpy().reshape(v.shape)
             return v
         if isinstance(v, torch.Tensor):
-            if v.is_contiguous():
-                dist.broadcast(v, src=src, group=self.group)
-                return v
-            tmp = v.contiguous()
-            dist.broadcast(tmp, src=src, group=self.group)
-            v.copy_(tmp)
-            return v
+            return self._bcast_tensor(v, src)
         if hasattr(v, "storage_tensor"):
-            dist.broadcast(v.storage_tensor(), src=src, group=self.group)
+            self._bcast_tensor(v.storage_tensor(), src)
             return v
         if hasattr(v, "get_local") and hasattr(v, "set_local"):
             a = v.get_local()

@@ -393,9 +393,15 @@ class CsrCGSolver:
     together (SpMM + per-column dots/axpys); each column has its own step lengths.  Intended for mass-matrix-like
     (well conditioned) B; PDE-operator priors keep their upstream solvers."""
 
-    def __init__(self, Bmat, rel_tol=1e-13, max_iter=1000, check_every=8):
+    def __init__(self, Bmat, rel_tol=1e-13, max_iter=1000, check_every=8, on_fail="raise"):
+        """``on_fail``: what to do when ``max_iter`` is reached with a column still above ``rel_tol``:
+        "raise" (HfbError; an inexact B^-1 silently degrades the eigenpairs of doublePassG) or "warn"
+        (RuntimeWarning).  ``final_rel_res`` holds the largest relative residual of the last solve either way."""
         self.B = Bmat
         self.rel_tol, self.max_iter, self.check_every = rel_tol, max_iter, check_every
+        assert on_fail in ("raise", "warn")
+        self.on_fail = on_fail
+        self.final_rel_res = None
         n = Bmat.shape[0]
         dev = Bmat.device
         # diagonal of B from the CSR arrays
@@ -426,9 +432,10 @@ class CsrCGSolver:
             K.axpby_cols_(alpha, P, None, X)
             K.axpby_cols_(-alpha, AP, None, R)
             if (it + 1) % self.check_every == 0:
-                rn = torch.sqrt(K.coldot(R, R))
-                if bool(((rn / r0) < self.rel_tol).all()):
+                rel = float((torch.sqrt(K.coldot(R, R)) / r0).max())
+                if rel < self.rel_tol:
                     self.iterations = it + 1
+                    self.final_rel_res = rel
                     break
             K.rowscale(self.dinv, R, out=Z)
             rz_new = K.coldot(R, Z)
@@ -437,6 +444,16 @@ class CsrCGSolver:
             K.axpby_cols_(None, Z, beta, P)
         else:
             self.iterations = self.max_iter
+            self.final_rel_res = float((torch.sqrt(K.coldot(R, R)) / r0).max())
+            if not self.final_rel_res < self.rel_tol:
+                msg = ("CsrCGSolver: %d iterations reached with relative residual %.3e > rel_tol %.1e; the Jacobi-"
+                       "preconditioned block CG is meant for mass-matrix-like (well conditioned) B -- pass a better "
+                       "solver (any object with solve_block) for an ill-conditioned precision matrix"
+                       % (self.max_iter, self.final_rel_res, self.rel_tol))
+                if self.on_fail == "raise":
+                    raise K.HfbError(msg)
+                import warnings
+                warnings.warn(msg, RuntimeWarning)
         return X
 
     def solve(self, x, b):

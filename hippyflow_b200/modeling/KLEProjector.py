@@ -92,7 +92,7 @@ class KLEProjector:
         if orthogonality.lower() == 'mass':
             KLE_Operator = MassPreconditionedCovarianceOperator(self.C, self.prior.M)
             self.d_KLE, self.V_KLE = doublePassG(KLE_Operator, self.prior.M, self.prior.Msolver, Omega, rank, s=1,
-                                                 faithful=False)
+                                                 faithful=faithful)
             self.M_orthogonal = True
             kle_decoder = self.V_KLE
             kle_encoder = DeviceMultiVector(self.prior.M.matmat(kle_decoder.tensor()))

@@ -57,11 +57,15 @@ class SparsePrior:
     """``prior`` stand-in exposing ``R`` (CSR precision-like SPD matrix on the device) and ``Rsolver`` (block CG),
     the two objects doublePassG receives at activeSubspaceProjector.py:449-450."""
 
-    def __init__(self, R, device=None, rel_tol=1e-13):
+    def __init__(self, R, device=None, rel_tol=1e-13, max_iter=1000, Rsolver=None, on_fail="raise"):
+        """``Rsolver``: any object with ``solve_block(Y) -> R^-1 Y`` on device blocks (default: Jacobi-preconditioned
+        block CG, which raises when it does not reach ``rel_tol`` within ``max_iter`` iterations -- an unconverged
+        R^-1 silently degrades the eigenpairs of doublePassG)."""
         self.device = device if device is not None else _default_device()
         self.R_csr = _to_scipy_csr(R)
         self.R = CsrMatrix(self.R_csr, self.device)
-        self.Rsolver = CsrCGSolver(self.R, rel_tol=rel_tol)
+        self.Rsolver = Rsolver if Rsolver is not None else CsrCGSolver(self.R, rel_tol=rel_tol, max_iter=max_iter,
+                                                                       on_fail=on_fail)
 
 
 class ActiveSubspaceProjector:

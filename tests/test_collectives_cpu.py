@@ -28,9 +28,43 @@ def _worker(rank, world, port, q):
     try:
         from hippyflow_b200.collectives import (CollectiveOperator, MultipleSamePartitioningPDEsCollective,
                                                 MultipleSerialPDEsCollective)
+        # NCCL rejects strided tensors, gloo does not: make gloo as strict so that the contiguity handling is exercised here
+        _ar, _bc = dist.all_reduce, dist.broadcast
+
+        def strict_all_reduce(t, *a, **k):
+            assert t.is_contiguous(), "Tensors must be contiguous"
+            return _ar(t, *a, **k)
+
+        def strict_broadcast(t, *a, **k):
+            assert t.is_contiguous(), "Tensors must be contiguous"
+            return _bc(t, *a, **k)
+
+        dist.all_reduce, dist.broadcast = strict_all_reduce, strict_broadcast
         c = MultipleSerialPDEsCollective()
         res = {}
         assert c.size() == world and c.rank() == rank
+
+        class ColumnVector:                         # a DeviceVector: (n, 1) column view of a padded block (stride (2, 1))
+            def __init__(self, n, val):
+                self.block = torch.zeros(n, 2, dtype=torch.float64)
+                self.block[:, 0] = val
+
+            def storage_tensor(self):
+                return self.block[:, :1]
+
+        cv = ColumnVector(5, float(rank + 1))
+        assert not cv.storage_tensor().is_contiguous()
+        assert c.allReduce(cv, "avg") is cv
+        res["colvec"] = cv.block.numpy().copy()
+        cb = ColumnVector(5, float(rank + 7))
+        c.bcast(cb, root=1)
+        res["colvec_bcast"] = cb.block.numpy().copy()
+        ti = torch.full((3,), 3 * rank + 2, dtype=torch.int64)            # 2 and 5 -> sum 7, 'avg' truncates to 3
+        c.allReduce(ti, "avg")
+        res["int_avg_tensor"] = ti.numpy().copy()
+        ai = np.full(3, 3 * rank + 2, dtype=np.int32)
+        c.allReduce(ai, "avg")
+        res["int_avg_array"] = ai.copy()
         res["sum_f"] = c.allReduce(float(rank + 1), "sum")
         res["avg_f"] = c.allReduce(float(rank + 1), "AVG")                 # case-insensitive (collective.py:82)
         res["sum_i"] = int(c.allReduce(int(rank + 1), "sum"))
@@ -263,6 +297,10 @@ def test_torch_collective_gloo_world2():
         np.testing.assert_allclose(r["arr"], np.arange(6).reshape(2, 3) * 1.5)
         np.testing.assert_allclose(r["ten"], 3.0)
         np.testing.assert_allclose(r["nc"], 1.5)
+        np.testing.assert_allclose(r["colvec"][:, 0], 1.5)
+        np.testing.assert_allclose(r["colvec"][:, 1], 0.0)                    # the padding column is not touched
+        np.testing.assert_allclose(r["colvec_bcast"][:, 0], 8.0)
+        assert r["int_avg_tensor"].tolist() == [3, 3, 3] and r["int_avg_array"].tolist() == [3, 3, 3]
         np.testing.assert_allclose(r["bcast"], 1.0)
         assert r["bcast_scalar"] == 0.5
         assert r["bad_op"] and r["bad_type"]
