@@ -50,6 +50,8 @@ def lib():
         "hfb_dgemm": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, vp, i64, vp, sz, i32, vp]),
         "hfb_dgemm_ex_workspace_bytes": (sz, [i32, i64, i64, i64, i32, i32]),
         "hfb_dgemm_ex": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, vp, i64, vp, sz, i32, i32, vp]),
+        "hfb_dgemm_batched_workspace_bytes": (sz, [i32, i64, i64, i64, i64, i32]),
+        "hfb_dgemm_batched": (i32, [i32, i64, i64, i64, dbl, vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i32, i32, vp, sz, vp]),
         "hfb_dgemm_batched_small": (i32, [i32, i64, i64, i64, dbl, vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, vp]),
         "hfb_csr_spmm": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_ordered": (i32, [i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp]),
@@ -91,6 +93,7 @@ def lib():
 
 EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm", "hfb_dgemm_ex",
             "hfb_dgemm_ex_workspace_bytes",
+            "hfb_dgemm_batched_workspace_bytes", "hfb_dgemm_batched",
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
             "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
             "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma", "hfb_csr_spmm_regblock", "hfb_csr_spmm_dmma",
@@ -211,6 +214,78 @@ def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumula
         e1.record()
         TIMING.append(((layout, M, N, K), e0, e1))
     _check(rc, "hfb_dgemm")
+    return out
+
+
+def _batch_operand(t, name):
+    """(rows, cols, ld, batch stride, batch) of a 2-D (shared) or 3-D (batch, rows, cols) float64 CUDA operand."""
+    if not (is_device_tensor(t) and t.dtype == torch.float64 and t.dim() in (2, 3) and t.stride(-1) == 1):
+        raise HfbError("%s must be a 2-D or 3-D float64 CUDA tensor with unit inner stride" % name)
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], _ld(t), 0, 1
+    ld = t.stride(1) if t.shape[1] > 1 else max(t.stride(1), t.shape[2])
+    return t.shape[1], t.shape[2], ld, (t.stride(0) if t.shape[0] > 1 else 0), t.shape[0]
+
+
+def batched_empty(batch, rows, cols, device, pad=16):
+    """(batch, rows, cols) float64 view whose row pitch is a multiple of ``pad`` elements (TMA-conforming batch operand)."""
+    ld = ((cols + pad - 1) // pad) * pad
+    return torch.empty((batch, rows, ld), dtype=torch.float64, device=device)[:, :, :cols]
+
+
+def dgemm_batched(layout, A, B, out=None, alpha=1.0, reduce=False, accumulate=False):
+    """Strided-batch DMMA GEMM over the sample axis (hfb_dgemm_batched).  A, B: (batch, rows, cols) stacks, or 2-D =
+    shared by every sample.  reduce=False: out (batch, M, N), out[b] = alpha op(A[b]) op(B[b]) in ONE launch;
+    reduce=True: out (M, N) = alpha * sum_b op(A[b]) op(B[b]) (the K loop runs over the samples, deterministic split-K)."""
+    L = lib()
+    ra, ca, lda, sa, ba = _batch_operand(A, "A")
+    rb, cb, ldb, sb, bb = _batch_operand(B, "B")
+    batch = max(ba, bb)
+    if (ba not in (1, batch)) or (bb not in (1, batch)):
+        raise HfbError("dgemm_batched: batch sizes differ (%d vs %d)" % (ba, bb))
+    if layout == HFB_NN:
+        M, K, K2, N = ra, ca, rb, cb
+    elif layout == HFB_TN:
+        K, M, K2, N = ra, ca, rb, cb
+    elif layout == HFB_NT:
+        M, K, N, K2 = ra, ca, rb, cb
+    else:
+        raise HfbError("unknown layout")
+    if K != K2:
+        raise HfbError("dgemm_batched: inner dimensions differ (%d vs %d)" % (K, K2))
+    dev = A.device
+    if reduce:
+        if out is None:
+            if accumulate:
+                raise HfbError("dgemm_batched: accumulate needs an existing out")
+            out = padded_empty(M, N, dev)
+        _req(out, "out")
+        if tuple(out.shape) != (M, N):
+            raise HfbError("dgemm_batched: out has shape %s, expected %s" % (tuple(out.shape), (M, N)))
+        ldc, sc = _ld(out), 0
+    else:
+        if out is None:
+            if accumulate:
+                raise HfbError("dgemm_batched: accumulate needs an existing out")
+            out = batched_empty(batch, M, N, dev)
+        if not (is_device_tensor(out) and out.dtype == torch.float64 and out.dim() == 3 and out.stride(2) == 1) or \
+                tuple(out.shape) != (batch, M, N):
+            raise HfbError("dgemm_batched: out must be a (batch, M, N) float64 CUDA tensor with unit inner stride")
+        ldc = out.stride(1) if M > 1 else max(out.stride(1), N)
+        sc = out.stride(0) if batch > 1 else ldc * M
+    mode = 1 if reduce else 0
+    nbytes = L.hfb_dgemm_batched_workspace_bytes(layout, M, N, K, batch, mode)
+    ws = workspace(nbytes, dev) if nbytes else None
+    if TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = L.hfb_dgemm_batched(layout, M, N, K, float(alpha), A.data_ptr(), lda, sa, B.data_ptr(), ldb, sb, out.data_ptr(), ldc, sc,
+                             batch, mode, 2 if accumulate else 0, ws.data_ptr() if ws is not None else None,
+                             ws.numel() if ws is not None else 0, _stream())
+    if TIMING is not None:
+        e1.record()
+        TIMING.append((("batched", layout, M, N, K, batch, mode), e0, e1))
+    _check(rc, "hfb_dgemm_batched")
     return out
 
 

@@ -27,17 +27,23 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// 2-D fp64 tensor map over a row-major array: `inner` contiguous elements per row, `outer` rows, leading
-// dimension ld (elements); box = {16, box_rows}; 128-byte swizzle; out-of-bounds reads give zeros.
+// 3-D fp64 tensor map over `nbatch` row-major arrays `batch_stride` elements apart: `inner` contiguous elements per
+// row, `outer` rows, leading dimension ld (elements); box = {16, box_rows, 1}; 128-byte swizzle; out-of-bounds reads
+// give zeros (also for the rows past `outer` of ONE sample: a K or M tail never reads the next sample).  A plain
+// (non-batched) operand is the nbatch = 1 case.
 static int make_map(CUtensorMap* map, const double* base, long long inner, long long outer, long long ld,
-                    int box_rows) {
+                    int box_rows, long long nbatch = 1, long long batch_stride = 0) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return HFB_E_NODRIVER;
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
-    cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+    if (nbatch <= 1 || batch_stride <= 0) {
+        nbatch = 1;
+        batch_stride = ld * outer;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nbatch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)batch_stride * 8};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
@@ -64,13 +70,15 @@ static int choose_nt(long long N) {
 }
 
 static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static int cache[64] = {0};  // keyed by the current device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cache[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
     }
-    return n;
+    return cache[dev];
 }
 
 static int auto_splits(long long M, long long N, long long K, int symmetric = 0) {
@@ -175,26 +183,43 @@ extern "C" size_t hfb_dgemm_ex_workspace_bytes(int layout, int64_t M, int64_t N,
     return (size_t)splits * (size_t)M * (size_t)ldw * 8;
 }
 
-extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
-                            const double* B, int64_t ldb, double* C, int64_t ldc, void* workspace,
-                            size_t workspace_bytes, int splits, int flags, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// Common implementation of hfb_dgemm_ex and hfb_dgemm_batched.
+//   mode 0: `batch` independent products C_b = alpha op(A_b) op(B_b) (+ C_b); a stride of 0 shares the operand.
+//   mode 1: one product with the K loop folded over the samples, C = alpha sum_b op(A_b) op(B_b) (split-K over the folded
+//           range, summed in fixed order).
+static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t strideA,
+                     const double* B, int64_t ldb, int64_t strideB, double* C, int64_t ldc, int64_t strideC, int64_t batch,
+                     int mode, void* workspace, size_t workspace_bytes, int splits, int flags, cudaStream_t stream) {
     const int symmetric = ((flags & HFB_GEMM_SYMMETRIC) && M == N) ? 1 : 0;
     const int accumulate = (flags & HFB_GEMM_ACCUMULATE) ? 1 : 0;
     if ((flags & HFB_GEMM_SYMMETRIC) && M != N) return HFB_E_BADARG;
     if (symmetric && accumulate) return HFB_E_UNSUPPORTED;  // the mirror pass would overwrite the accumulated half
-    if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || splits < 0) return HFB_E_BADARG;
-    if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) return HFB_E_BADARG;
+    if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || splits < 0 || batch < 1) return HFB_E_BADARG;
+    if (mode != 0 && mode != 1) return HFB_E_BADARG;
+    if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL || batch > 0x7fffffffLL) return HFB_E_BADARG;
+    if (strideA < 0 || strideB < 0 || strideC < 0) return HFB_E_BADARG;
     const long long a_inner = (layout == HFB_TN) ? M : K, a_outer = (layout == HFB_TN) ? K : M;
     const long long b_inner = (layout == HFB_NT) ? K : N, b_outer = (layout == HFB_NT) ? N : K;
     if (lda < a_inner || ldb < b_inner || ldc < N) return HFB_E_BADARG;
-    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 1) || (ldb & 1))
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda & 1) || (ldb & 1) ||
+        (strideA & 1) || (strideB & 1))
         return HFB_E_ALIGN;
     if (reinterpret_cast<uintptr_t>(C) & 7) return HFB_E_ALIGN;
+    const bool batched = batch > 1;
+    if (batched) {
+        if (symmetric) return HFB_E_UNSUPPORTED;
+        if (mode == 0 && strideC < ldc * (M - 1) + N) return HFB_E_BADARG;  // outputs must not overlap
+        if (mode == 1 && (strideA == 0 && strideB == 0)) return HFB_E_BADARG;
+    }
+    const int kfold = (batched && mode == 1) ? (int)batch : 1;
+    const int nbat = (batched && mode == 0) ? (int)batch : 1;
 
     const int nt = choose_nt(N);
-    const long long kb_total = (K + GEMM_BK - 1) / GEMM_BK;
-    if (splits == 0) splits = auto_splits(M, N, K, symmetric);
+    const long long kb_per = (K + GEMM_BK - 1) / GEMM_BK;
+    const long long kb_total = kb_per * kfold;
+    if (kb_total > 0x7fffffffLL) return HFB_E_BADARG;
+    if (nbat > 1) splits = 1;  // the sample axis already fills the GPU; outputs are written directly
+    if (splits == 0) splits = auto_splits(M, N, kb_total * GEMM_BK, symmetric);
     if (splits > kb_total) splits = (int)kb_total;
     if (splits < 1) splits = 1;
 
@@ -207,6 +232,12 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
     p.splits = splits;
     p.kb_total = (int)kb_total;
     p.alpha = alpha;
+    p.batch = nbat;
+    p.kfold = kfold;
+    p.kb_per = (int)kb_per;
+    p.a_batched = (batched && strideA > 0) ? 1 : 0;
+    p.b_batched = (batched && strideB > 0) ? 1 : 0;
+    p.strideC = nbat > 1 ? strideC : 0;
     const long long ldw = (N + 1) & ~1LL;
     if (splits > 1) {
         const size_t need = (size_t)splits * (size_t)M * (size_t)ldw * 8;
@@ -220,18 +251,19 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
         p.ldc = ldc;
         p.split_stride = 0;
     }
-    p.vec_store = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 1) == 0) ? 1 : 0;
+    p.vec_store = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 1) == 0 && (p.strideC & 1) == 0) ? 1 : 0;
     p.symmetric = symmetric;
     p.accumulate = accumulate;
-    if ((long long)p.m_tiles * p.n_tiles * p.splits > 0x7fffffffLL) return HFB_E_BADARG;
+    if ((long long)p.m_tiles * p.n_tiles * p.splits * nbat > 0x7fffffffLL) return HFB_E_BADARG;
 
     CUtensorMap mapA, mapB;
     int rc;
-    if (layout == HFB_TN) rc = make_map(&mapA, A, M, K, lda, 16);
-    else rc = make_map(&mapA, A, K, M, lda, GEMM_BM);
+    const long long nA = p.a_batched ? batch : 1, nB = p.b_batched ? batch : 1;
+    if (layout == HFB_TN) rc = make_map(&mapA, A, M, K, lda, 16, nA, strideA);
+    else rc = make_map(&mapA, A, K, M, lda, GEMM_BM, nA, strideA);
     if (rc) return rc;
-    if (layout == HFB_NT) rc = make_map(&mapB, B, K, N, ldb, 8 * nt);
-    else rc = make_map(&mapB, B, N, K, ldb, 16);
+    if (layout == HFB_NT) rc = make_map(&mapB, B, K, N, ldb, 8 * nt, nB, strideB);
+    else rc = make_map(&mapB, B, N, K, ldb, 16, nB, strideB);
     if (rc) return rc;
 
     if (layout == HFB_NN) rc = dgemm_launch_nn(nt, mapA, mapB, p, stream);
@@ -255,4 +287,31 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
         rc = (int)cudaGetLastError();
     }
     return rc;
+}
+
+extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                            const double* B, int64_t ldb, double* C, int64_t ldc, void* workspace,
+                            size_t workspace_bytes, int splits, int flags, void* stream_) {
+    return gemm_impl(layout, M, N, K, alpha, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, 0, workspace, workspace_bytes, splits, flags,
+                     (cudaStream_t)stream_);
+}
+
+extern "C" size_t hfb_dgemm_batched_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int64_t batch, int mode) {
+    if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0 || batch < 1) return 0;
+    if (mode != 1 || batch == 1) return mode == 1 ? hfb_dgemm_ex_workspace_bytes(layout, M, N, K, 0, 0) : 0;
+    const long long kb_total = ((K + GEMM_BK - 1) / GEMM_BK) * batch;
+    if (kb_total > 0x7fffffffLL) return 0;
+    const int splits = auto_splits(M, N, kb_total * GEMM_BK, 0);
+    if (splits <= 1) return 0;
+    const long long ldw = (N + 1) & ~1LL;
+    return (size_t)splits * (size_t)M * (size_t)ldw * 8;
+}
+
+extern "C" int hfb_dgemm_batched(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                                 int64_t strideA, const double* B, int64_t ldb, int64_t strideB, double* C, int64_t ldc,
+                                 int64_t strideC, int64_t batch, int mode, int flags, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+    if (flags & HFB_GEMM_SYMMETRIC) return HFB_E_UNSUPPORTED;
+    return gemm_impl(layout, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, mode, workspace,
+                     workspace_bytes, 0, flags, (cudaStream_t)stream_);
 }

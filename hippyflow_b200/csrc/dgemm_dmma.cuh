@@ -45,6 +45,12 @@ struct GemmParams {
     int vec_store;         // 1 if C base is 16-byte aligned and ldc even (16-byte stores allowed)
     int symmetric;         // 1: the result is symmetric (M == N); tiles strictly below the diagonal are skipped
     int accumulate;        // 1: C += alpha * op(A) op(B)  (applied here when splits == 1, else by the split-K reduce)
+    // strided-batch extension (hfb_dgemm_batched); the operands are 3-D tensor maps whose third coordinate is the sample
+    int batch;             // independent outputs C_b = alpha op(A_b) op(B_b), b < batch (1 for a plain GEMM)
+    int kfold;             // samples folded into the K loop: C = alpha sum_z op(A_z) op(B_z), z < kfold (1 for a plain GEMM)
+    int kb_per;            // k-blocks per sample; kb_total = kb_per * kfold
+    int a_batched, b_batched;  // operand has a sample axis (third coordinate = sample) or is shared (third coordinate 0)
+    long long strideC;     // elements between consecutive C_b
 };
 
 template <int LAYOUT, int NT>
@@ -84,7 +90,9 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int n_tile = bid % p.n_tiles;
     bid /= p.n_tiles;
     const int m_tile = bid % p.m_tiles;
-    const int split = bid / p.m_tiles;
+    bid /= p.m_tiles;
+    const int split = bid % p.splits;
+    const int bat = bid / p.splits;  // sample of an independent-output batch (0 for a plain GEMM)
     const int kb_base = p.kb_total / p.splits, kb_rem = p.kb_total % p.splits;
     const int kb_begin = split * kb_base + (split < kb_rem ? split : kb_rem);
     const int kb_count = kb_base + (split < kb_rem ? 1 : 0);
@@ -114,20 +122,27 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
                 uint8_t* sB = sA + Cfg::A_BYTES;
                 mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                const int k0 = (kb_begin + it) * GEMM_BK;
+                // k-block -> (sample, k offset): with kfold > 1 the K loop runs over the samples as well
+                int kbg = kb_begin + it, z = bat;
+                if (p.kfold > 1) {
+                    z = kbg / p.kb_per;
+                    kbg -= z * p.kb_per;
+                }
+                const int k0 = kbg * GEMM_BK;
+                const int zA = p.a_batched ? z : 0, zB = p.b_batched ? z : 0;
                 if (Cfg::A_KC) {
-                    tma_load_2d(sA, &mapA, &full_bar[stage], k0, m0);  // box {16 k, 128 rows}
+                    tma_load_3d(sA, &mapA, &full_bar[stage], k0, m0, zA);  // box {16 k, 128 rows, 1}
                 } else {
 #pragma unroll
-                    for (int pnl = 0; pnl < GEMM_BM / 16; ++pnl)  // box {16 m, 16 k-rows}
-                        tma_load_2d(sA + pnl * (GEMM_BK * 128), &mapA, &full_bar[stage], m0 + 16 * pnl, k0);
+                    for (int pnl = 0; pnl < GEMM_BM / 16; ++pnl)  // box {16 m, 16 k-rows, 1}
+                        tma_load_3d(sA + pnl * (GEMM_BK * 128), &mapA, &full_bar[stage], m0 + 16 * pnl, k0, zA);
                 }
                 if (Cfg::B_KC) {
-                    tma_load_2d(sB, &mapB, &full_bar[stage], k0, n0);  // box {16 k, BN rows}
+                    tma_load_3d(sB, &mapB, &full_bar[stage], k0, n0, zB);  // box {16 k, BN rows, 1}
                 } else {
 #pragma unroll
-                    for (int pnl = 0; pnl < Cfg::NPB; ++pnl)  // box {16 n, 16 k-rows}
-                        tma_load_2d(sB + pnl * (GEMM_BK * 128), &mapB, &full_bar[stage], n0 + 16 * pnl, k0);
+                    for (int pnl = 0; pnl < Cfg::NPB; ++pnl)  // box {16 n, 16 k-rows, 1}
+                        tma_load_3d(sB + pnl * (GEMM_BK * 128), &mapB, &full_bar[stage], n0 + 16 * pnl, k0, zB);
                 }
             }
         }
@@ -244,7 +259,7 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
 
     // ---------------------------------------------------------------------- epilogue
-    double* Cout = p.C + (long long)split * p.split_stride;
+    double* Cout = p.C + (long long)split * p.split_stride + (long long)bat * p.strideC;
     const double alpha = (p.splits == 1) ? p.alpha : 1.0;
     const bool accum = (p.splits == 1) && p.accumulate;
     auto put1 = [&](double* dst, double v) { *dst = accum ? (*dst + v) : v; };

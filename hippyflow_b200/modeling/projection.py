@@ -17,6 +17,15 @@ def _dev(a, device):
     return K.to_padded(np.asarray(a, dtype=np.float64), device)
 
 
+def stacked_jacobians(J, device):
+    """Stored Jacobians (N, dQ, dM) as (J2, J3): the (N dQ, dM) row-major device matrix (TMA-conforming leading dimension,
+    zero-copy when the input already conforms) and its (N, dQ, dM) strided-batch view."""
+    N, dQ, dM = J.shape
+    J2 = _as_device_rows(J.reshape(N * dQ, dM), device)
+    ld = K._ld(J2)
+    return J2, J2.as_strided((N, dQ, dM), (dQ * ld, ld, 1))
+
+
 def project_data(data, encoder, device=None, out=None):
     """(N, r) reduced coordinates: row i = encoder^T data_i, with encoder = M decoder
     (KLEProjector.py:167-168, PODProjector.py:769,830).  ``data`` (N, n) host array or device block."""
@@ -40,14 +49,9 @@ def jacobian_action(J, Psi, device=None):
 def jacobian_transpose_action(J, MPhi, device=None):
     """JstarPhi (N, dM, rQ): JstarPhi_i = J_i^T (M Phi) (dataGenerator.py:170,339, stacked as at :582)."""
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    N, dQ, dM = J.shape
-    Jd = _as_device_rows(J.reshape(N * dQ, dM), device)
-    E = _dev(MPhi, device)
-    rQ = E.shape[1]
-    out = torch.empty((N, dM, ((rQ + 15) // 16) * 16), dtype=torch.float64, device=device)[:, :, :rQ]
-    for i in range(N):                                              # one TN GEMM (K = dQ) per sample
-        K.dgemm(K.HFB_TN, Jd[i * dQ:(i + 1) * dQ], E, out=out[i])
-    return out
+    _, J3 = stacked_jacobians(J, device)
+    E = _dev(MPhi, device)                                          # (dQ, rQ), shared by every sample
+    return K.dgemm_batched(K.HFB_TN, J3, E)                         # ONE strided-batch launch: grid = samples x tiles
 
 
 def reduced_jacobians(J, PhiEnc, V, device=None):

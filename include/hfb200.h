@@ -75,6 +75,28 @@ int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha,
 int hfb_dgemm_auto_splits(int layout, int64_t M, int64_t N, int64_t K);
 
 /*
+ * Strided-batch form of the same DMMA/TMA kernel over the sample axis of stored Jacobians J (N, dQ, dM) and of per-sample
+ * blocks: the operands are 3-D tensor maps (third coordinate = sample; rows past one sample's extent read as zeros, never
+ * the next sample), `batch` samples `strideA` / `strideB` / `strideC` elements apart (even; 0 = operand shared by all samples).
+ *   mode HFB_BATCH_INDEPENDENT: C_b = alpha op(A_b) op(B_b) [+ C_b with HFB_GEMM_ACCUMULATE], one launch for all samples:
+ *       JstarPhi_i = J_i^T (M Phi)   hp.MatMvTranspmult(J, MPhi, JstarPhi)   (hippyflow/modeling/dataGenerator.py:170,339)
+ *       G_i = J_i J_i^T, V_i = J_i^T U_i, B_i^T = J_i^T Q_i of the per-sample randomized SVD
+ *                                    hp.accuracyEnhancedSVD(J, Omega, r, s=1) (activeSubspaceProjector.py:816,1026, dataGenerator.py:187)
+ *   mode HFB_BATCH_REDUCE:      C = alpha sum_b op(A_b) op(B_b): the K loop runs over (sample, k), deterministic split-K:
+ *       E[J J^T] = (1/N) sum_i J_i J_i^T and its operator form sum_i J_i (J_i^T X)
+ *                                    JJT / SummedListOperator(average=True) (activeSubspaceProjector.py:625-673, jacobian.py:169-193)
+ * workspace: hfb_dgemm_batched_workspace_bytes (0 for HFB_BATCH_INDEPENDENT).  HFB_GEMM_SYMMETRIC is not supported here.
+ */
+#define HFB_BATCH_INDEPENDENT 0
+#define HFB_BATCH_REDUCE 1
+size_t hfb_dgemm_batched_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int64_t batch, int mode);
+int hfb_dgemm_batched(int layout, int64_t M, int64_t N, int64_t K, double alpha,
+                      const double* A, int64_t lda, int64_t strideA,
+                      const double* B, int64_t ldb, int64_t strideB,
+                      double* C, int64_t ldc, int64_t strideC, int64_t batch, int mode, int flags,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Batched small GEMM over the sample axis:  C_i[M x N] = alpha * op(A_i) * B_i  for i < batch,
  * with element strides between consecutive samples (stride 0 = shared operand).
  * layout is HFB_NN or HFB_TN.  One CTA per (sample, tile); CUDA-core DFMA (operands are tiny).

@@ -243,6 +243,55 @@ def as_input_from_jacobians(J, rank, Omega, noise_cov_inv=None, B_csr=None, rank
     return d, V.to_dense(), enc.to_dense()
 
 
+def _b_orthonormalize_blocked(Q, B_csr=None):
+    """Two eigen-based Cholesky-QR sweeps in the B inner product (B = I when None) -- the blocked stand-in for
+    hIPPYlib's MGS Borthogonalize; directions at round-off level are dropped, not amplified."""
+    for _ in range(2):
+        G = Q.T @ (Q if B_csr is None else B_csr @ Q)
+        w, V = np.linalg.eigh(0.5 * (G + G.T))
+        keep = w > w.max() * Q.shape[1] * np.finfo(float).eps
+        Q = Q @ (V * np.where(keep, 1.0 / np.sqrt(np.where(keep, w, 1.0)), 0.0))
+    return Q
+
+
+def as_input_from_jacobians_blocked(J, rank, Omega, noise_cov_inv=None, B_csr=None):
+    """Blocked (BLAS-3) evaluation of ``as_input_from_jacobians``: the operator mean_i J_i^T [G] J_i
+    (operatorWrappers.py:95-114) applied to all columns at once through the stacked (N dQ, dM) matrix, the same
+    doublePass / doublePassG structure (activeSubspaceProjector.py:447-463), T = Q^T A Q as a Gram matrix.  d and
+    span(V) agree with the column-by-column port (checked in tests/test_oracle_golden.py); used at benchmark shapes
+    where the column-by-column port would take hours."""
+    N, dQ, dM = J.shape
+    J2 = J.reshape(N * dQ, dM)
+
+    def weighted(W):                                        # blockdiag(Gamma^-1) W, sample by sample
+        if noise_cov_inv is None:
+            return W
+        G = np.asarray(noise_cov_inv)
+        return np.einsum("ab,ibm->iam", G, W.reshape(N, dQ, -1)).reshape(N * dQ, -1)
+
+    Y = J2.T @ weighted(J2 @ Omega) / N                     # A Omega
+    if B_csr is not None:
+        lu = spla.splu(B_csr.tocsc())
+        Y = lu.solve(Y)                                     # B^-1 A Omega
+    Q = _b_orthonormalize_blocked(Y, B_csr)
+    W = J2 @ Q
+    T = W.T @ weighted(W) / N                               # Q^T A Q
+    dd, VV = np.linalg.eigh(0.5 * (T + T.T))
+    d = dd[::-1][:rank]
+    V = Q @ VV[:, ::-1][:, :rank]
+    return d, V, (B_csr @ V if B_csr is not None else V.copy())
+
+
+def pod_randomized_blocked(u_data, rank, Omega):
+    """Blocked evaluation of ``pod_randomized`` (PODProjector.py:359-376 / KLE 'identity', KLEProjector.py:175-180):
+    doublePass on C = X^T X / N, no weighting, no shift."""
+    N = u_data.shape[0]
+    Q = _b_orthonormalize_blocked(u_data.T @ (u_data @ Omega) / N)
+    W = u_data @ Q
+    dd, VV = np.linalg.eigh(W.T @ W / N)
+    return dd[::-1][:rank], Q @ VV[:, ::-1][:, :rank]
+
+
 def as_output_from_jacobians(J, rank, Omega):
     """Output subspace E[J J^T] (activeSubspaceProjector.py:625-673: JJT operators, 'avg', doublePass)."""
     N = J.shape[0]
