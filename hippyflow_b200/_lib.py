@@ -81,6 +81,10 @@ def lib():
         "hfb_axpby_cols": (i32, [i64, i64, vp, vp, i64, vp, vp, i64, vp]),
         "hfb_rowscale": (i32, [i64, i64, vp, vp, i64, vp, i64, vp]),
         "hfb_measure_dmma_peak": (i32, [vp, sz, ctypes.POINTER(ctypes.c_double), vp]),
+        "hfb_chol_inverse_workspace_bytes": (sz, [i64]),
+        "hfb_chol_inverse": (i32, [i64, vp, i64, vp, i64, vp, i32, vp, sz, vp]),
+        "hfb_jacobi_svd_max_elems": (i64, []),
+        "hfb_jacobi_svd_batched": (i32, [i64, i64, vp, i64, i64, i64, vp, i64, vp, i32, i32, vp]),
         "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -101,7 +105,8 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
-            "hfb_measure_dmma_peak"]
+            "hfb_measure_dmma_peak", "hfb_chol_inverse_workspace_bytes", "hfb_chol_inverse", "hfb_jacobi_svd_max_elems",
+            "hfb_jacobi_svd_batched"]
 
 
 def _check(rc, what):
@@ -597,6 +602,49 @@ def measure_dmma_peak(device):
     rc = L.hfb_measure_dmma_peak(ws.data_ptr(), ws.numel(), ctypes.byref(out), _stream())
     _check(rc, "hfb_measure_dmma_peak")
     return out.value
+
+
+CHOL_INVERSE_MAX = 1024
+
+
+def chol_inverse(G, scale_columns=True):
+    """Device Cholesky-QR factor of the (m x m) Gram matrix G (hfb_chol_inverse): returns (S, stat) with S = D^-1 R^-1
+    (upper triangular, padded device block) and stat a DEVICE vector of 8 doubles {fail, shift, cond, attempts,
+    max |Gs - I|, max |d - 1|, zero columns, m}.  Asynchronous: nothing is copied to the host."""
+    L = lib()
+    _req(G, "G")
+    m = G.shape[0]
+    if G.shape[1] != m or m > CHOL_INVERSE_MAX:
+        raise HfbError("chol_inverse: G must be square with m <= %d" % CHOL_INVERSE_MAX)
+    S = padded_empty(m, m, G.device)
+    stat = torch.empty(8, dtype=torch.float64, device=G.device)
+    nbytes = L.hfb_chol_inverse_workspace_bytes(m)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=G.device)      # own scratch: the shared workspace may be in use by a GEMM queued behind
+    rc = L.hfb_chol_inverse(m, G.data_ptr(), _ld(G), S.data_ptr(), _ld(S), stat.data_ptr(), 1 if scale_columns else 0,
+                            ws.data_ptr(), ws.numel(), _stream())
+    _check(rc, "hfb_chol_inverse")
+    return S, stat
+
+
+def jacobi_svd_fits(rows, cols):
+    """True when a (rows x cols) block fits the shared-memory resident batched Jacobi SVD."""
+    return cols * (rows | 1) + cols + 2 + (cols + 1) // 2 <= int(lib().hfb_jacobi_svd_max_elems())
+
+
+def jacobi_svd_batched_(A, keep_scaled=False, max_sweeps=40):
+    """In-place batched one-sided Jacobi SVD (hfb_jacobi_svd_batched): A (batch, rows, cols) -> U (unit columns sorted by
+    descending singular value; ``keep_scaled``: U diag(sigma)).  Returns (sigma (batch, cols), info (batch,) int32 device)."""
+    L = lib()
+    if not (is_device_tensor(A) and A.dtype == torch.float64 and A.dim() == 3 and A.stride(2) == 1):
+        raise HfbError("jacobi_svd_batched_: A must be a (batch, rows, cols) float64 CUDA tensor with unit inner stride")
+    batch, rows, cols = A.shape
+    sigma = torch.empty((batch, cols), dtype=torch.float64, device=A.device)
+    info = torch.empty(batch, dtype=torch.int32, device=A.device)
+    lda = A.stride(1) if rows > 1 else max(A.stride(1), cols)
+    rc = L.hfb_jacobi_svd_batched(rows, cols, A.data_ptr(), lda, A.stride(0) if batch > 1 else lda * rows, batch, sigma.data_ptr(),
+                                  cols, info.data_ptr(), int(max_sweeps), 1 if keep_scaled else 0, _stream())
+    _check(rc, "hfb_jacobi_svd_batched")
+    return sigma, info
 
 
 # optional per-call CUDA-event timing of the GEMM launches (bench.py's roofline leg)

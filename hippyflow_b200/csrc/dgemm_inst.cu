@@ -19,7 +19,7 @@ static int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmPa
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    const long long grid = (long long)p.m_tiles * p.n_tiles * p.splits;
+    const long long grid = (long long)p.m_tiles * p.n_tiles * p.splits * p.batch;
     dgemm_dmma_kernel<LAYOUT, NT><<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
     ++g_launch_count;
     return (int)cudaGetLastError();

@@ -287,7 +287,45 @@ def sym_gram(Y, Z, alpha=1.0):
     return G
 
 
-def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=False):
+def _device_chol_enabled():
+    import os
+    return os.environ.get("HFB_DEVICE_CHOL", "1") != "0"
+
+
+def b_orthonormalize_device(Y, Bmat=None, return_BQ=True):
+    """Optimistic, host-free form of the two-pass Cholesky-QR for a well-conditioned sketch (the common case): every step
+    is queued on the stream and NOTHING is read back --
+        Z = B Y, G = Y^T Z, S1 = D^-1 chol(D^-1 G D^-1)^-1 (hfb_chol_inverse), Q1 = Y S1,
+        Z1 = B Q1, G1 = Q1^T Z1, S2 = chol(G1)^-1 (hfb_chol_inverse, no scaling),
+    and the clean-up factor S2 stays on the device for the caller to fold into the small matrices (T = S2^T T1 S2,
+    U = Q1 (S2 V)).  ``info["pending"]`` carries the two device status vectors; the caller checks them when it fetches T
+    (one synchronisation for everything) and falls back to the host-controlled ``b_orthonormalize`` on the untouched sketch
+    ``Y`` when pass 1 needed a shift or was too ill-conditioned for a folded clean-up (cond * eps * m >= 1e-4)."""
+    Z = Bmat.matmat(Y) if Bmat is not None else Y
+    G = sym_gram(Y, Z)
+    S1, stat1 = K.chol_inverse(G, scale_columns=True)
+    Q1 = K.dgemm(K.HFB_NN, Y, S1)
+    if Bmat is not None:
+        Z1 = Bmat.matmat(Q1, out=Z)
+    else:
+        Z1 = Q1
+    G1 = sym_gram(Q1, Z1)
+    S2, stat2 = K.chol_inverse(G1, scale_columns=False)
+    info = {"passes": 1, "shifted": 0, "cond": [], "route": "device",
+            "pending": {"stat1": stat1, "stat2": stat2, "S2": S2, "sketch": Y}}
+    return Q1, (Z1 if return_BQ else None), info
+
+
+def pending_ok(stats, m):
+    """Host check of the device status vectors of ``b_orthonormalize_device`` (stats: (2, 8) NumPy array)."""
+    eps = np.finfo(np.float64).eps
+    s1, s2 = stats
+    ok1 = s1[0] == 0.0 and s1[1] == 0.0 and np.isfinite(s1[2]) and s1[2] * eps * m < 1e-4
+    ok2 = s2[0] == 0.0 and s2[1] == 0.0 and np.isfinite(s2[2]) and s2[2] < 4.0
+    return bool(ok1 and ok2)
+
+
+def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=False, device_chol=None):
     """Orthonormalise the columns of the sketch Y (n, m) in the inner product of the sparse SPD matrix
     ``Bmat`` (None = Euclidean): the role of MultiVector.Borthogonalize / orthogonalize inside hIPPYlib's
     doublePassG / doublePass.
@@ -309,9 +347,13 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=Fals
     which is the same algebra as Q = Q1 S2 without the (n x m) update GEMM, one SpMM and one host round trip on
     the critical path."""
     n, m = Y.shape
+    if device_chol is None:
+        device_chol = _device_chol_enabled()
+    if defer_last and device_chol and m <= K.CHOL_INVERSE_MAX and n >= m:
+        return b_orthonormalize_device(Y, Bmat, return_BQ)
     spare = None
     eps = np.finfo(np.float64).eps
-    info = {"passes": 0, "shifted": 0, "cond": []}
+    info = {"passes": 0, "shifted": 0, "cond": [], "route": "host"}
     Z = None
     eye = np.eye(m)
     for it in range(max_passes):

@@ -74,6 +74,25 @@ def _copy_stream(dev):
     return st
 
 
+_staging = {}
+
+
+def _staging_ring(dev, n, nbuf=3, target_bytes=96 << 20):
+    """Ring of pinned staging buffers (rows x n) for uploads from pageable host memory, cached per device and row length."""
+    key = (dev.index, n)
+    ring = _staging.get(key)
+    if ring is None:
+        rows = int(max(1, target_bytes // (8 * n)))
+        ring = []
+        for _ in range(nbuf):
+            ev = torch.cuda.Event()
+            ev.record()
+            ring.append((torch.empty((rows, n), dtype=torch.float64, pin_memory=True), ev))
+        _staging.clear()                                                     # one row length at a time: do not hoard pinned memory
+        _staging[key] = ring
+    return ring
+
+
 def to_host(t):
     """Device block -> NumPy array through a pinned staging tensor (torch's caching host allocator reuses the
     pinned blocks once earlier results are garbage-collected)."""
@@ -258,16 +277,12 @@ class PODProjectorFromData:
         main = torch.cuda.current_stream(dev)
         copy_stream = _copy_stream(dev)
         copy_stream.wait_stream(main)
-        events = []
-        with torch.cuda.stream(copy_stream):
-            for lo, hi in bounds:
-                Xt[lo:hi].copy_(src[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                events.append(ev)
         colsum = None
         prov = None
-        for i, ((lo, hi), ev) in enumerate(zip(bounds, events)):
+
+        def consume(i, lo, hi, ev):
+            """Main-stream work on rows lo..hi once their copy (event ev) has landed."""
+            nonlocal colsum, prov
             main.wait_event(ev)
             Xc = Xt[lo:hi]
             if shifted:
@@ -278,6 +293,38 @@ class PODProjectorFromData:
                 colsum = part if colsum is None else colsum.add_(part)
             K.dgemm(K.HFB_NN, Xc, B, out=W[lo:hi])
             K.dgemm(K.HFB_TN, Xc, W[lo:hi], out=Y, alpha=1.0 / N, accumulate=(i > 0))
+
+        if src.is_pinned():
+            events = []
+            with torch.cuda.stream(copy_stream):
+                for lo, hi in bounds:
+                    Xt[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    events.append(ev)
+            for i, ((lo, hi), ev) in enumerate(zip(bounds, events)):
+                consume(i, lo, hi, ev)
+        else:
+            # pageable input (a plain NumPy array, the documented drop-in call): a cudaMemcpy from pageable memory is staged
+            # by the driver at ~10 GB/s.  Instead the rows go through a small ring of pinned buffers filled by torch's
+            # multi-threaded host copy, so the host copy of piece j+1 overlaps the DMA of piece j and the GEMMs of the
+            # previous chunk.
+            ring = _staging_ring(dev, n)
+            rows_per = ring[0][0].shape[0]
+            j = 0
+            for i, (lo, hi) in enumerate(bounds):
+                for s0 in range(lo, hi, rows_per):
+                    s1 = min(hi, s0 + rows_per)
+                    buf, free = ring[j % len(ring)]
+                    free.synchronize()                                       # its previous DMA has finished
+                    buf[:s1 - s0].copy_(src[s0:s1])
+                    with torch.cuda.stream(copy_stream):
+                        Xt[s0:s1].copy_(buf[:s1 - s0], non_blocking=True)
+                        free.record(copy_stream)
+                    j += 1
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                consume(i, lo, hi, ev)
         Xt.record_stream(copy_stream)
         if not shifted:
             return Xt, torch.zeros(n, dtype=torch.float64, device=dev), None, (W, Y)

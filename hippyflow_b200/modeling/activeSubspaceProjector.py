@@ -13,7 +13,7 @@ from ..linalg import CsrMatrix, CsrCGSolver, SampleCovariance
 from ..multivector import DeviceMultiVector, mv_to_dense
 from ..parameterList import ParameterList
 from ..randomized import doublePass, doublePassG
-from .operators import MeanJTJfromDataOperator, SampleCovarianceOperator
+from .operators import MeanJJTfromDataOperator, MeanJTJfromDataOperator, SampleCovarianceOperator
 from .PODProjector import _default_device, _to_scipy_csr, gaussian_omega
 
 
@@ -68,7 +68,54 @@ class SparsePrior:
                                                                        on_fail=on_fail)
 
 
+class LowRankHessian:
+    """hIPPYlib ``LowRankHessian`` (the object behind ``prior.Hlr``, used as B and as its own solver at
+    activeSubspaceProjector.py:455-459,562-566): H = R + R U diag(d) U^T R with U^T R U = I, and by Sherman-Morrison-
+    Woodbury H^-1 = R^-1 - U diag(d / (1 + d)) U^T.  R is a device CSR matrix with a block solver (``SparsePrior``); U a
+    (n, r) device block, d (r,).  Exposes the block protocol doublePassG uses (``matmat`` / ``solve_block``) and the
+    vector protocol of the reference (``mult`` / ``solve`` / ``init_vector``)."""
+
+    def __init__(self, prior, d, U):
+        self.prior = prior
+        self.device = prior.device
+        self.shape = prior.R.shape
+        self.U = U.tensor() if hasattr(U, "tensor") else K.to_padded(np.asarray(U, dtype=np.float64), self.device)
+        self.d = torch.as_tensor(np.asarray(d, dtype=np.float64), device=self.device)
+        self.RU = prior.R.matmat(self.U)                                   # R U (n, r)
+
+    def init_vector(self, x, dim):
+        x.init(self.shape[0])
+
+    def matmat(self, X, out=None):
+        Y = self.prior.R.matmat(X, out=out)                                # R X
+        coef = K.rowscale(self.d, K.dgemm(K.HFB_TN, self.RU, X))           # diag(d) (R U)^T X   (r, m)
+        K.axpby_(1.0, K.dgemm(K.HFB_NN, self.RU, coef), 1.0, Y)            # + R U diag(d) U^T R X
+        return Y
+
+    def solve_block(self, Y):
+        X = self.prior.Rsolver.solve_block(Y)                              # R^-1 Y
+        coef = K.rowscale(self.d / (1.0 + self.d), K.dgemm(K.HFB_TN, self.U, Y))
+        K.axpby_(-1.0, K.dgemm(K.HFB_NN, self.U, coef), 1.0, X)            # - U diag(d/(1+d)) U^T Y
+        return X
+
+    def mult(self, x, y):
+        y.storage_tensor().copy_(self.matmat(_aligned_block(x.storage_tensor())))
+
+    def solve(self, sol, rhs):
+        sol.storage_tensor().copy_(self.solve_block(_aligned_block(rhs.storage_tensor())))
+
+
+def _aligned_block(t):
+    if t.data_ptr() % 16 or K._ld(t) % 2:
+        return K.to_padded(t, t.device, pad=2 if t.shape[1] == 1 else 16)
+    return t
+
+
 class ActiveSubspaceProjector:
+    # largest output dimension for which E[J J^T] is formed as a dense (dQ x dQ) matrix; above it (full-state observable,
+    # dQ = n_u) the operator form MeanJJTfromDataOperator is handed to doublePass
+    DENSE_OUTPUT_MAX = 4096
+
     def __init__(self, observable, prior=None, control_distribution=None, mesh_constructor_comm=None,
                  collective=NullCollective(), parameters=None, device=None):
         self.observable = observable
@@ -86,6 +133,7 @@ class ActiveSubspaceProjector:
         self.Omega_NG = None
         self.prior_preconditioned = None
         self._JTJ = None
+        self._JJT = None
 
     def _operator(self):
         if self._JTJ is None:
@@ -113,11 +161,17 @@ class ActiveSubspaceProjector:
             self.Omega_GN = Omega
         rank = self.parameters['rank']
         if prior_preconditioned:
-            if self.prior is None or not hasattr(self.prior, "R"):
-                raise ValueError("prior_preconditioned=True needs a prior exposing R and Rsolver")
-            self.d_GN, self.V_GN = doublePassG(A, self.prior.R, self.prior.Rsolver, Omega, rank, s=1, faithful=faithful)
-            as_decoder = self.V_GN
-            as_encoder = DeviceMultiVector(self.prior.R.matmat(as_decoder.tensor()))   # hp.MatMvMult(prior.R, ...) :452-453
+            if self.prior is not None and hasattr(self.prior, "R"):
+                self.d_GN, self.V_GN = doublePassG(A, self.prior.R, self.prior.Rsolver, Omega, rank, s=1, faithful=faithful)
+                as_decoder = self.V_GN
+                as_encoder = DeviceMultiVector(self.prior.R.matmat(as_decoder.tensor()))   # hp.MatMvMult(prior.R, ...) :452-453
+            elif self.prior is not None and hasattr(self.prior, "Hlr"):
+                # doublePassG(A, prior.Hlr, prior.Hlr, ...) :455-459 -- Hlr is the operator and its own solver
+                self.d_GN, self.V_GN = doublePassG(A, self.prior.Hlr, self.prior.Hlr, Omega, rank, s=1, faithful=faithful)
+                as_decoder = self.V_GN
+                as_encoder = DeviceMultiVector(self.prior.Hlr.matmat(as_decoder.tensor()))
+            else:
+                raise ValueError("prior_preconditioned=True needs a prior exposing R and Rsolver, or Hlr")
         else:
             self.d_GN, self.V_GN = doublePass(A, Omega, rank, s=1, faithful=faithful)
             as_decoder = self.V_GN
@@ -136,31 +190,40 @@ class ActiveSubspaceProjector:
             np.save(self.parameters['output_directory'] + name + '_d_GN', self.d_GN)
         return self.d_GN, as_decoder, as_encoder
 
-    def construct_output_subspace(self, name_suffix=None):
-        """E[J J^T] (activeSubspaceProjector.py:618-673): a (dQ x dQ) problem.  J J^T averaged over samples is
-        accumulated as one NT GEMM per sample block and handed to doublePass through a dense operator."""
+    def construct_output_subspace(self, name_suffix=None, operator_form=None):
+        """E[J J^T] (activeSubspaceProjector.py:618-673): doublePass on the sample-averaged J J^T.  For a small output space
+        (pointwise observations) the (dQ x dQ) matrix is formed by ONE strided-batch GEMM whose K loop runs over
+        (sample, dM); for a large one (full-state observable, dQ = n_u > DENSE_OUTPUT_MAX, or ``operator_form=True``) the
+        operator mean_i J_i (J_i^T X) is applied block-wise without ever forming the matrix."""
         t0 = time.time()
         J = self.observable.J
         N, dQ, dM = J.shape
-        Jd = self._operator()._cov.Xt                                        # (N*dQ, dM) on the device
-        C = torch.zeros((dQ, dQ), dtype=torch.float64, device=self.device)
-        tmp = K.padded_empty(dQ, dQ, self.device)
-        for i in range(N):
-            Ji = Jd[i * dQ:(i + 1) * dQ]
-            K.dgemm(K.HFB_NT, Ji, Ji, out=tmp)
-            C += tmp
-        C /= N
-        self.collective.allReduce(C, 'avg')
-        Cd = K.to_padded(C, self.device)
+        if getattr(self, "_JJT", None) is None:
+            stacked = None
+            if self._JTJ is not None:                                            # reuse the device copy of the input subspace
+                J2 = self._JTJ._cov.Xt
+                stacked = (J2, J2.as_strided((N, dQ, dM), (dQ * K._ld(J2), K._ld(J2), 1)))
+            self._JJT = MeanJJTfromDataOperator(J, device=self.device, collective=self.collective, mpi_op='avg',
+                                                stacked=stacked)
+        if operator_form is None:
+            operator_form = dQ > self.DENSE_OUTPUT_MAX
+        if operator_form:
+            A = self._JJT
+        else:
+            Cd = self._JJT.dense()
 
-        class _Dense:
-            def matMvMult(self_, X, Y):
-                K.dgemm(K.HFB_NN, Cd, X.tensor(), out=Y.tensor())
+            class _Dense:
+                overwrites = True
+
+                def matMvMult(self_, X, Y):
+                    K.dgemm(K.HFB_NN, Cd, X.tensor(), out=Y.tensor())
+
+            A = _Dense()
 
         Omega = self._omega(self.Omega_NG, dQ)
         if self.parameters['store_Omega']:
             self.Omega_NG = Omega
-        self.d_NG, self.U_NG = doublePass(_Dense(), Omega, min(self.parameters['rank'], dQ), s=1)
+        self.d_NG, self.U_NG = doublePass(A, Omega, min(self.parameters['rank'], dQ), s=1)
         output_decoder = self.U_NG
         output_encoder = DeviceMultiVector(output_decoder)
         torch.cuda.synchronize(self.device)

@@ -7,8 +7,7 @@
   collective the way the reference does (allReduce 'avg' of the mean and of the variance).
 * ``jacobian_truncated_svd``: (U, sigma, V) of every stored Jacobian, the arrays ``Jsvd_data.npz`` holds
   (dataGenerator.py:187,643-655; the reference obtains them with hIPPYlib's accuracyEnhancedSVD on the
-  matrix-free Jacobian).  On stored data the small side dQ makes the exact route cheap: G_i = J_i J_i^T
-  (DMMA GEMM, K = dM), eigh on the host, V_i = J_i^T U_i / sigma_i (DMMA GEMM).
+  matrix-free Jacobian): the same randomized algorithm, batched over all samples (``randomizedSVD.py``).
 """
 import numpy as np
 import torch
@@ -70,25 +69,18 @@ def projection_errors(test_data, decoder, encoder, ranks, collective=None, devic
     return np.array(avg), np.array(std)
 
 
-def jacobian_truncated_svd(J, rank, device=None):
-    """U (N, dQ, r), sigma (N, r), V (N, dM, r) with J_i ~ U_i diag(sigma_i) V_i^T, sigma descending."""
+def jacobian_truncated_svd(J, rank, device=None, oversampling=10, Omega=None, s=1, seed=1):
+    """U (N, dQ, r), sigma (N, r), V (N, dM, r) with J_i ~ U_i diag(sigma_i) V_i^T, sigma descending: the arrays of
+    ``Jsvd_data.npz`` (dataGenerator.py:643-655), computed the way the reference does -- hIPPYlib's
+    accuracyEnhancedSVD(J, Omega, r, s=1) with r + oversampling Gaussian columns (activeSubspaceProjector.py:1004-1026) --
+    for all samples at once (``randomizedSVD.accuracyEnhancedSVD_batched``: strided-batch DMMA GEMMs + batched Jacobi
+    kernels, no loop over samples, no host LAPACK)."""
+    from .randomizedSVD import accuracyEnhancedSVD_batched
+    from .PODProjector import gaussian_omega
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     N, dQ, dM = J.shape
     r = int(rank)
     assert r <= min(dQ, dM)
-    Jd = _as_device_rows(J.reshape(N * dQ, dM), device)
-    G = torch.empty((N, dQ, dQ), dtype=torch.float64, device=device)
-    tmp = K.padded_empty(dQ, dQ, device)
-    for i in range(N):                                               # G_i = J_i J_i^T  (NT, K = dM, split-K)
-        Ji = Jd[i * dQ:(i + 1) * dQ]
-        K.dgemm(K.HFB_NT, Ji, Ji, out=tmp)
-        G[i].copy_(tmp)
-    w, Uh = np.linalg.eigh(G.cpu().numpy())                          # ascending, (N, dQ), (N, dQ, dQ)
-    w = np.maximum(w[:, ::-1][:, :r], 0.0)
-    U = np.ascontiguousarray(Uh[:, :, ::-1][:, :, :r])
-    sigma = np.sqrt(w)
-    inv = np.where(sigma > 0, 1.0 / np.where(sigma > 0, sigma, 1.0), 0.0)
-    V = torch.empty((N, dM, ((r + 15) // 16) * 16), dtype=torch.float64, device=device)[:, :, :r]
-    for i in range(N):                                               # V_i = J_i^T (U_i / sigma_i)   (TN, K = dQ)
-        K.dgemm(K.HFB_TN, Jd[i * dQ:(i + 1) * dQ], K.to_padded(U[i] * inv[i][None, :], device), out=V[i])
-    return torch.as_tensor(U, device=device), torch.as_tensor(sigma, device=device), V
+    if Omega is None:
+        Omega = gaussian_omega(dM, min(r + int(oversampling), max(r, min(dQ, dM))), seed, device)
+    return accuracyEnhancedSVD_batched(J, Omega, r, s=s, device=device)

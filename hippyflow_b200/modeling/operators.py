@@ -191,6 +191,71 @@ class MeanJTJfromDataOperator:
         return self._op.rayleigh_device(Q, BQ)
 
 
+class MeanJJTfromDataOperator:
+    """y = mean_i J_i J_i^T x on the OUTPUT space from a stored (ndata, dQ, dM) array: the operator
+    ``CollectiveOperator(SummedListOperator([JJT(J_i)], average=True), collective, 'avg')`` of the output active subspace
+    (activeSubspaceProjector.py:625-673, jacobian.py:169-193) in stored-data form.  It never forms the (dQ x dQ) matrix, so it
+    also serves the full-state observable where dQ = n_u (fullStateObservable.py:18).  A block of m columns costs two
+    strided-batch DMMA launches per chunk of samples:
+        T_i = J_i^T X          (dM x m) for every sample of the chunk      hfb_dgemm_batched, independent outputs
+        Y  += sum_i J_i T_i    (dQ x m), K loop folded over (sample, dM)   hfb_dgemm_batched, HFB_BATCH_REDUCE
+    (the chunk bounds the (chunk, dM, m) workspace; it is not a per-sample loop)."""
+
+    overwrites = True
+
+    def __init__(self, J, device=None, collective=None, mpi_op="avg", chunk_bytes=4 << 30, stacked=None):
+        """``stacked``: an existing (J2, J3) pair from ``projection.stacked_jacobians`` (shares the device copy another
+        operator already made)."""
+        from .projection import stacked_jacobians
+        assert len(J.shape) == 3
+        self.ndata, self.dQ, self.dM = J.shape
+        if device is None:
+            device = J.device if K.is_device_tensor(J) else torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self._J2, self._J3 = stacked if stacked is not None else stacked_jacobians(J, device)
+        self.collective = collective if collective is not None else NullCollective()
+        self.mpi_op = mpi_op
+        self.chunk_bytes = int(chunk_bytes)
+
+    def init_vector(self, x, dim=None):
+        x.init(self.dQ)
+
+    def _apply_local(self, Xt, Yt):
+        m = Xt.shape[1]
+        ldm = ((m + 15) // 16) * 16
+        chunk = int(max(1, min(self.ndata, self.chunk_bytes // max(1, self.dM * ldm * 8))))
+        T = K.batched_empty(chunk, self.dM, m, self.device)
+        for i0 in range(0, self.ndata, chunk):
+            i1 = min(self.ndata, i0 + chunk)
+            Jc = self._J3[i0:i1]
+            Tc = T[:i1 - i0]
+            K.dgemm_batched(K.HFB_TN, Jc, Xt, out=Tc)                                        # T_i = J_i^T X
+            K.dgemm_batched(K.HFB_NN, Jc, Tc, out=Yt, alpha=1.0 / self.ndata, reduce=True, accumulate=(i0 > 0))
+        return Yt
+
+    def matMvMult(self, X, Y):
+        self._apply_local(_tma_operand(X.tensor()), Y.tensor())
+        self.collective.allReduce(Y, self.mpi_op)
+
+    matMvTranspmult = matMvMult
+
+    def mult(self, x, y):
+        xt = _tma_operand(x.storage_tensor())
+        yt = K.padded_empty(self.dQ, 1, self.device, pad=2)
+        self._apply_local(xt, yt)
+        y.storage_tensor().copy_(yt)
+        self.collective.allReduce(y, self.mpi_op)
+
+    transpmult = mult
+
+    def dense(self):
+        """C = mean_i J_i J_i^T as a (dQ x dQ) device matrix: ONE strided-batch launch with the K loop folded over
+        (sample, dM) -- the cheap route when dQ is small (pointwise observations)."""
+        C = K.dgemm_batched(K.HFB_NT, self._J3, self._J3, alpha=1.0 / self.ndata, reduce=True)
+        self.collective.allReduce(C, self.mpi_op)
+        return C
+
+
 class JTJ:
     """Gauss-Newton Hessian J^T J of ONE stored Jacobian (dQ, dM): the stored-data form of
     hippyflow/modeling/jacobian.py:142-166 (there every apply is an incremental forward and adjoint PDE solve)."""

@@ -58,24 +58,48 @@ def _fetch_async(t):
     return host, done
 
 
-def _rayleigh_ritz(A, Q, BQ, k, gram, faithful):
-    """T = Q^T A Q, top-k eigenpairs, and the (m x k) DEVICE coefficient matrix C with U = Q C.  ``gram`` is the device
-    Gram matrix of a basis whose clean-up pass was deferred (see linalg.b_orthonormalize).  The only host arithmetic is
-    the Cholesky factor of ``gram`` (in the shadow of the pass-2 GEMM) and eigh(T), as in hIPPYlib; the small products
-    with the clean-up factor S2 run on the device (a 266^3 product costs ~20 us there, milliseconds on the host)."""
+def _rayleigh_matrix(A, Q, BQ, faithful):
+    """T = Q^T A Q as (device matrix or None, host matrix or None); the big GEMM(s) are only queued here."""
+    if hasattr(A, "rayleigh_device") and not faithful:
+        return A.rayleigh_device(Q, BQ), None
+    if hasattr(A, "rayleigh") and not faithful:
+        return None, A.rayleigh(Q, BQ)
+    AQ = _block_apply(A, Q)
+    return None, AQ.dot_mv(Q)
+
+
+def _rayleigh_ritz(A, Q, BQ, k, oinfo, faithful):
+    """T = Q^T A Q, top-k eigenpairs, and the (m x k) DEVICE coefficient matrix C with U = Q C.
+
+    ``oinfo`` is the info dict of ``b_orthonormalize``.  Three cases:
+      * ``oinfo["pending"]`` (device Cholesky-QR, nothing read back so far): T1 is formed, the clean-up factor S2 is folded
+        in on the device (T = S2^T T1 S2), and T travels to the host together with the two status vectors -- ONE
+        synchronisation for the whole orthonormalisation + Rayleigh-Ritz phase.  Returns None when the status vectors say
+        the optimistic path was not valid (the caller then redoes the orthonormalisation under host control).
+      * ``oinfo["gram"]`` (host path with deferred clean-up): G1 is fetched on a side stream while the pass-2 GEMM runs and
+        the host computes S2 = chol(G1)^-1 in its shadow.
+      * neither: Q is B-orthonormal to round-off.
+    The only host arithmetic is eigh(T) (hIPPYlib: np.linalg.eigh), plus the Cholesky factor of G1 in the second case."""
     dev = Q.tensor().device
+    m = Q.nvec()
+    pending = oinfo.pop("pending", None)
+    gram = oinfo.pop("gram", None)
     if gram is not None:
         G1h, done = _fetch_async(gram)
-    Td = None
-    if hasattr(A, "rayleigh_device") and not faithful:
-        Td = A.rayleigh_device(Q, BQ)                          # big GEMM(s) queued: overlaps with the host work below
-    elif hasattr(A, "rayleigh") and not faithful:
-        T = A.rayleigh(Q, BQ)
-    else:
-        AQ = _block_apply(A, Q)
-        T = AQ.dot_mv(Q)
+    Td, T = _rayleigh_matrix(A, Q, BQ, faithful)
     S2d = None
-    if gram is not None:
+    if pending is not None:
+        S2d = pending["S2"]
+        if Td is None:
+            Td = K.to_padded(np.ascontiguousarray(T), dev)
+        Td = K.dgemm(K.HFB_TN, S2d, K.dgemm(K.HFB_NN, Td, S2d))          # S2^T T S2
+        stats = torch.stack([pending["stat1"], pending["stat2"]]).cpu().numpy()   # the one synchronisation of this phase
+        from .linalg import pending_ok
+        if not pending_ok(stats, m):
+            return None
+        oinfo["cond"] = [float(stats[0][2]), float(stats[1][2])]
+        oinfo["passes"] = 2                                              # pass 2 folded into the small matrices
+    elif gram is not None:
         done.synchronize()
         S2d = K.to_padded(cleanup_factor(G1h.numpy()), dev)
         if Td is None:
@@ -88,6 +112,25 @@ def _rayleigh_ritz(A, Q, BQ, k, gram, faithful):
     return d, (Vd if S2d is None else K.dgemm(K.HFB_NN, S2d, Vd))
 
 
+def _orthonormalize_and_ritz(A, Y, B, k, faithful, return_BQ):
+    """(B-)orthonormalise the sketch Y and solve the projected problem; the optimistic device path is tried first and
+    replaced by the host-controlled passes (on the untouched sketch) when its status check fails."""
+    Qt, BQt, oinfo = b_orthonormalize(Y, B, return_BQ=return_BQ, defer_last=True)
+    optimistic = "pending" in oinfo
+    Q = DeviceMultiVector(Qt)
+    BQ = DeviceMultiVector(BQt) if return_BQ else Q
+    res = _rayleigh_ritz(A, Q, BQ, k, oinfo, faithful)
+    if res is None:
+        assert optimistic
+        Qt, BQt, oinfo = b_orthonormalize(Y, B, return_BQ=return_BQ, defer_last=True, device_chol=False)
+        Q = DeviceMultiVector(Qt)
+        BQ = DeviceMultiVector(BQt) if return_BQ else Q
+        res = _rayleigh_ritz(A, Q, BQ, k, oinfo, faithful)
+        oinfo["route"] = "host (device status rejected)"
+    d, C = res
+    return d, Q, C, oinfo
+
+
 def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     """d (k,) descending, U DeviceMultiVector (n, k) with U^T U = I."""
     nvec = Omega.nvec()
@@ -95,9 +138,7 @@ def doublePass(A, Omega, k, s=1, faithful=False, info=None):
     Q = Omega                                   # not modified: every apply writes a fresh block
     for _ in range(s):
         Q = _block_apply(A, Q)
-    Qt, _, oinfo = b_orthonormalize(Q.tensor(), None, return_BQ=False, defer_last=True)
-    Q = DeviceMultiVector(Qt)
-    d, C = _rayleigh_ritz(A, Q, Q, k, oinfo.pop("gram", None), faithful)
+    d, Q, C, oinfo = _orthonormalize_and_ritz(A, Q.tensor(), None, k, faithful, return_BQ=False)
     U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), C))
     if info is not None:
         info.update(oinfo)
@@ -123,9 +164,7 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None, Q0=None):
             Q = DeviceMultiVector(Binv.solve_block(Ybar.tensor()))
     if Q0 is not None:
         Q = Q0                                  # range-finder block B^-1 A Omega supplied by the caller (pipelined upload)
-    Qt, BQt, oinfo = b_orthonormalize(Q.tensor(), B, return_BQ=True, defer_last=True)
-    Q, BQ = DeviceMultiVector(Qt), DeviceMultiVector(BQt)
-    d, C = _rayleigh_ritz(A, Q, BQ, k, oinfo.pop("gram", None), faithful)
+    d, Q, C, oinfo = _orthonormalize_and_ritz(A, Q.tensor(), B, k, faithful, return_BQ=True)
     U = DeviceMultiVector(K.dgemm(K.HFB_NN, Q.tensor(), C))
     if info is not None:
         info.update(oinfo)

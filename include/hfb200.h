@@ -241,6 +241,35 @@ int hfb_rowscale(int64_t n, int64_t m, const double* s, const double* X, int64_t
 int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64_t seed, int64_t row_offset,
                     int kind, void* stream);
 
+/*
+ * Device Cholesky-QR factor: for the symmetric (m x m) Gram matrix G = Y^T B Y of a sketch (m <= 1024), one CTA computes
+ *   d_j = sqrt(G_jj) (scale_columns != 0; a zero column keeps d_j^-1 = 0), Gs = D^-1 G D^-1, R = chol(Gs + shift I) upper,
+ *   S = D^-1 R^-1 (upper triangular, strictly lower part zeroed), so that Q = Y S is B-orthonormal:
+ * the role of hIPPYlib's MultiVector.Borthogonalize inside doublePassG / doublePass (call sites PODProjector.py:376,
+ * activeSubspaceProjector.py:449-461, KLEProjector.py:163,177), done as Cholesky-QR.  The shift starts at 0 and is raised
+ * (100 m eps, x100 per attempt, <= 8 attempts) until the factorisation succeeds with cond(R)^2 < 1e13 -- the same policy the
+ * host path applied with LAPACK dpotrf/dtrtri, without the device -> host -> device round trip.
+ * stat (DEVICE, 8 doubles): {fail, shift, cond = (max r_jj / min r_jj)^2, attempts, max |Gs - I|, max |d_j - 1|, zero columns, m}.
+ * workspace >= hfb_chol_inverse_workspace_bytes(m) (two m x m scratch matrices).
+ */
+size_t hfb_chol_inverse_workspace_bytes(int64_t m);
+int hfb_chol_inverse(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat, int scale_columns,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Batched one-sided Jacobi SVD of small blocks, one CTA per sample, block resident in shared memory
+ * (rows * cols <= ~hfb_jacobi_svd_max_elems()): A_b (rows x cols, row-major, lda, strideA between samples) is overwritten
+ * by its left singular vectors U_b (unit columns sorted by descending singular value; keep_scaled != 0: U_b diag(sigma_b)),
+ * sigma (batch x cols, ldsig) receives the singular values, info[b] the sweeps used (negative = not converged).
+ * Used by the batched randomized SVD of stored Jacobians -- hp.accuracyEnhancedSVD(J, Omega, r, s=1)
+ * (activeSubspaceProjector.py:816,1026, dataGenerator.py:187): orthonormalisation Q_i of the sketches J_i Omega
+ * (hIPPYlib: MultiVector.orthogonalize) and the eigen decomposition of the (l x l) matrices (Q_i^T J_i)(Q_i^T J_i)^T
+ * (hIPPYlib: np.linalg.svd of the small factor).
+ */
+int64_t hfb_jacobi_svd_max_elems(void);
+int hfb_jacobi_svd_batched(int64_t rows, int64_t cols, double* A, int64_t lda, int64_t strideA, int64_t batch,
+                           double* sigma, int64_t ldsig, int32_t* info, int32_t max_sweeps, int keep_scaled, void* stream);
+
 /* Measure the FP64 tensor-pipe ceiling of the current device (register-resident DMMA.8x8x4 loop, 8 warps/SM,
  * best of 5): the roofline denominator bench.py reports the GEMM against.  Synchronises the stream.
  * scratch: >= SMs*256*8 bytes of device memory; *tflops_out is a HOST double. */

@@ -162,6 +162,9 @@ def emulated_device():
                    "stream": torch.cuda.stream, "synchronize": torch.cuda.synchronize,
                    "current_device": torch.cuda.current_device}
     saved_empty = torch.empty
+    import os
+    saved_env = os.environ.get("HFB_DEVICE_CHOL")
+    os.environ["HFB_DEVICE_CHOL"] = "0"      # the test double covers the host-controlled orthonormalisation route only
     had_record = "record_stream" in torch.Tensor.__dict__
     saved_record = torch.Tensor.__dict__.get("record_stream")
     counter = {"n": 0}
@@ -327,6 +330,10 @@ def emulated_device():
         for k, v in saved_torch.items():
             setattr(torch.cuda, k, v)
         torch.empty = saved_empty
+        if saved_env is None:
+            os.environ.pop("HFB_DEVICE_CHOL", None)
+        else:
+            os.environ["HFB_DEVICE_CHOL"] = saved_env
         if had_record:
             torch.Tensor.record_stream = saved_record
         else:

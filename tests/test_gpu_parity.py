@@ -405,19 +405,6 @@ def test_projection_error_sweep_vs_numpy(hf, cuda_device):
     assert np.linalg.norm(Y.to_dense() - ref) / np.linalg.norm(ref) < PROJ_RTOL
 
 
-def test_jacobian_truncated_svd_vs_numpy(hf, cuda_device, golden_jtj):
-    J = golden_jtj["J"][:6]                                          # (6, 100, 121)
-    U, s, V = hf.jacobian_truncated_svd(J, 10, cuda_device)
-    U, s, V = U.cpu().numpy(), s.cpu().numpy(), V.cpu().numpy()
-    for i in range(6):
-        u0, s0, vt0 = np.linalg.svd(J[i], full_matrices=False)
-        np.testing.assert_allclose(s[i], s0[:10], rtol=1e-9)
-        rec = (U[i] * s[i]) @ V[i].T
-        ref = (u0[:, :10] * s0[:10]) @ vt0[:10]
-        assert np.linalg.norm(rec - ref) / np.linalg.norm(ref) < 1e-8
-        np.testing.assert_allclose(V[i].T @ V[i], np.eye(10), atol=1e-8)
-
-
 # ------------------------------------------------------------------ mean shift: implicit / pipelined / explicit routes
 def _blocked_weighted_pod(u, M, Om, rank):
     """Blocked NumPy evaluation of the M-weighted double pass on explicitly shifted data (the reference's
