@@ -55,18 +55,13 @@ def lib():
         "hfb_dgemm_batched_small": (i32, [i32, i64, i64, i64, dbl, vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, vp]),
         "hfb_csr_spmm": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_ordered": (i32, [i64, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp]),
-        "hfb_csr_cluster_rows": (i32, [i64, vp, vp, i32, vp]),
         "hfb_csr_cluster_rows_capped": (i32, [i64, vp, vp, i32, i32, vp, vp, ctypes.POINTER(ctypes.c_int64)]),
-        "hfb_csr_spmm_staged": (i32, [i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_cluster_blob_stride": (i64, [i32, i32, i32]),
         "hfb_csr_pack_clusters": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
-        "hfb_csr_spmm_tma": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
-        "hfb_csr_spmm_regblock": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_dmma": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_frag_blob_stride": (i64, [i32, i32]),
         "hfb_csr_pack_clusters_frag": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
         "hfb_csr_spmm_dmma_frag": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
-        "hfb_csr_spmm_dmma_pipe": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -98,10 +93,10 @@ def lib():
 EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb_dgemm_auto_splits", "hfb_dgemm", "hfb_dgemm_ex",
             "hfb_dgemm_ex_workspace_bytes",
             "hfb_dgemm_batched_workspace_bytes", "hfb_dgemm_batched",
-            "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", "hfb_csr_cluster_rows",
-            "hfb_csr_cluster_rows_capped", "hfb_csr_spmm_staged",
-            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_tma", "hfb_csr_spmm_regblock", "hfb_csr_spmm_dmma",
-            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", "hfb_csr_spmm_dmma_pipe",
+            "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", 
+            "hfb_csr_cluster_rows_capped", 
+            "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_dmma",
+            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", 
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -334,7 +329,7 @@ def csr_spmm(rowptr, colind, val, B, out=None, order=None):
 
 
 def csr_cluster_rows_capped(indptr, indices, max_rows=64, max_cols=128):
-    """Host preprocessing for the staged SpMM: (order, cluster_ptr) as NumPy int32 arrays."""
+    """Host preprocessing for the cluster SpMM kernels: (order, cluster_ptr) as NumPy int32 arrays."""
     import numpy as np
     L = lib()
     indptr = np.ascontiguousarray(indptr, dtype=np.int32)
@@ -349,23 +344,8 @@ def csr_cluster_rows_capped(indptr, indices, max_rows=64, max_cols=128):
     return order, cptr[:ncl.value + 1].copy()
 
 
-def csr_spmm_staged(plan, B, out=None):
-    """C = M @ B with the cluster-staged kernel; ``plan`` is the dict built by linalg.CsrMatrix._build_plan."""
-    L = lib()
-    _req(B, "B")
-    n, m = B.shape
-    if out is None:
-        out = padded_empty(n, m, B.device)
-    rc = L.hfb_csr_spmm_staged(plan["nclusters"], m, plan["cl_rowptr"].data_ptr(), plan["order"].data_ptr(),
-                               plan["s_rowptr"].data_ptr(), plan["entries"].data_ptr(), plan["cl_colptr"].data_ptr(),
-                               plan["cl_cols"].data_ptr(), plan["max_cols"], plan["max_entries"], B.data_ptr(), _ld(B),
-                               out.data_ptr(), _ld(out), _stream())
-    _check(rc, "hfb_csr_spmm_staged")
-    return out
-
-
 def csr_pack_clusters(indptr, indices, data, order, cptr, max_rows, max_cols, max_entries):
-    """Host preprocessing for the TMA SpMM: uint8 NumPy buffer of per-cluster blobs (hfb_csr_pack_clusters)."""
+    """Host preprocessing for the panel DMMA SpMM: uint8 NumPy buffer of per-cluster records (hfb_csr_pack_clusters)."""
     import numpy as np
     L = lib()
     indptr = np.ascontiguousarray(indptr, dtype=np.int32)
@@ -382,33 +362,6 @@ def csr_pack_clusters(indptr, indices, data, order, cptr, max_rows, max_cols, ma
                                  cptr.ctypes.data, ncl, int(max_rows), int(max_cols), int(max_entries), blobs.ctypes.data)
     _check(rc, "hfb_csr_pack_clusters")
     return blobs
-
-
-def csr_spmm_tma(plan, B, out=None):
-    """C = M @ B with the persistent TMA-fed kernel; ``plan`` is the dict built by linalg.CsrMatrix._build_plan."""
-    L = lib()
-    _req(B, "B")
-    n, m = B.shape
-    if out is None:
-        out = padded_empty(n, m, B.device)
-    rc = L.hfb_csr_spmm_tma(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
-                            plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
-    _check(rc, "hfb_csr_spmm_tma")
-    return out
-
-
-def csr_spmm_regblock(plan, B, out=None):
-    """C = M @ B with the register-blocked kernel (dense per-cluster block in shared memory, B rows straight from global
-    memory into registers); ``plan`` is the dict built by linalg.CsrMatrix._build_plan with its blobs packed."""
-    L = lib()
-    _req(B, "B")
-    n, m = B.shape
-    if out is None:
-        out = padded_empty(n, m, B.device)
-    rc = L.hfb_csr_spmm_regblock(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
-                                 plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
-    _check(rc, "hfb_csr_spmm_regblock")
-    return out
 
 
 def csr_spmm_dmma(plan, B, out=None):
@@ -446,33 +399,18 @@ def csr_pack_clusters_frag(indptr, indices, data, order, cptr, max_rows, max_col
     return blobs
 
 
-def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0, pipelined=False):
-    """C = M @ B with the fragment-blob DMMA kernel; ``plan`` carries ``fblobs`` (linalg.CsrMatrix._frag_blobs).
-    ``chunk_cols`` = columns staged per CTA (0: whole rows up to 320 columns); ``pipelined`` = resident CTAs walking the
-    clusters with double-buffered rows (hfb_csr_spmm_dmma_pipe)."""
+def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0):
+    """C = M @ B with the fragment-record DMMA kernel; ``plan`` carries ``fblobs`` (linalg.CsrMatrix._frag_blobs).
+    ``chunk_cols`` = columns staged per CTA (0: whole rows up to 320 columns)."""
     L = lib()
     _req(B, "B")
     n, m = B.shape
     if out is None:
         out = padded_empty(n, m, B.device)
-    fn = L.hfb_csr_spmm_dmma_pipe if pipelined else L.hfb_csr_spmm_dmma_frag
-    rc = fn(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+    rc = L.hfb_csr_spmm_dmma_frag(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
             int(chunk_cols), B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
-    _check(rc, "hfb_csr_spmm_dmma_pipe" if pipelined else "hfb_csr_spmm_dmma_frag")
+    _check(rc, "hfb_csr_spmm_dmma_frag")
     return out
-
-
-def csr_cluster_rows(indptr, indices, cluster=64):
-    """Host preprocessing: NumPy int32 CSR arrays -> int32 permutation grouping neighbouring rows (hfb_csr_cluster_rows)."""
-    import numpy as np
-    L = lib()
-    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
-    indices = np.ascontiguousarray(indices, dtype=np.int32)
-    n = indptr.size - 1
-    order = np.empty(n, dtype=np.int32)
-    rc = L.hfb_csr_cluster_rows(n, indptr.ctypes.data, indices.ctypes.data, int(cluster), order.ctypes.data)
-    _check(rc, "hfb_csr_cluster_rows")
-    return order
 
 
 def csr_spmm_rows(rowptr, colind, val, X, out=None):

@@ -20,52 +20,7 @@ static inline int num_sms() {
 }
 
 // ------------------------------------------------------------------------------------------ CSR SpMM
-// One warp per matrix row; lane l owns columns {2l, 2l+1} + 64*i (16-byte loads, a warp reads 512
-// contiguous bytes of a B row per chunk).  CH = ceil(m/64) chunks live in registers.
-template <int CH>
-__global__ void __launch_bounds__(256) csr_spmm_kernel(long long nrows, int m, const int* __restrict__ rowptr,
-                                                       const int* __restrict__ colind, const double* __restrict__ val,
-                                                       const double* __restrict__ B, long long ldb,
-                                                       double* __restrict__ C, long long ldc, int vec_ok) {
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long row = warp0; row < nrows; row += nwarps) {
-        double2 acc[CH];
-#pragma unroll
-        for (int i = 0; i < CH; ++i) acc[i] = make_double2(0.0, 0.0);
-        const int beg = rowptr[row], end = rowptr[row + 1];
-        for (int j = beg; j < end; ++j) {
-            const double v = __ldg(val + j);
-            const double* brow = B + (long long)__ldg(colind + j) * ldb;
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-                const int c = 2 * lane + 64 * i;
-                if (vec_ok && c + 1 < m) {
-                    const double2 b = *reinterpret_cast<const double2*>(brow + c);
-                    acc[i].x = fma(v, b.x, acc[i].x);
-                    acc[i].y = fma(v, b.y, acc[i].y);
-                } else {
-                    if (c < m) acc[i].x = fma(v, brow[c], acc[i].x);
-                    if (c + 1 < m) acc[i].y = fma(v, brow[c + 1], acc[i].y);
-                }
-            }
-        }
-        double* crow = C + row * ldc;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            const int c = 2 * lane + 64 * i;
-            if (vec_ok && c + 1 < m) {
-                *reinterpret_cast<double2*>(crow + c) = acc[i];
-            } else {
-                if (c < m) crow[c] = acc[i].x;
-                if (c + 1 < m) crow[c + 1] = acc[i].y;
-            }
-        }
-    }
-}
-
-// v2: (row block) x (64-column panel) decomposition.  A CTA of 16 warps walks 64 consecutive rows (16 at a time) of one
+// (row block) x (64-column panel) decomposition.  A CTA of 16 warps walks 64 consecutive rows (16 at a time) of one
 // 64-column panel, so the B-row segments shared by neighbouring rows (FEM stencils) are re-used out of L1 instead of
 // being re-fetched from L2; the CSR entries of a row are fetched by one coalesced load and broadcast by shuffles,
 // which leaves three dependent memory latencies per row instead of 2*nnz.
@@ -85,7 +40,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) csr_spmm_panel_kernel(long lo
     for (int i = 0; i < SPMM_ROWS_PER_CTA / SPMM_WARPS; ++i) {
         const long long slot = row_base + i * SPMM_WARPS + warp;
         if (slot >= nrows) break;
-        // `order` groups mesh-neighbouring rows into one CTA (hfb_csr_cluster_rows) so their B rows overlap in L1
+        // `order` groups mesh-neighbouring rows into one CTA (hfb_csr_cluster_rows_capped) so their B rows overlap in L1
         const long long row = order ? (long long)__ldg(order + slot) : slot;
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
         double2 acc[CH];
@@ -150,89 +105,6 @@ static int launch_spmm_panel(long long nrows, int m, const int* rowptr, const in
     }
     ++g_launch_count;
     return (int)cudaGetLastError();
-}
-
-// v3: cluster-staged SpMM.  A CTA owns one cluster of <= 64 mesh-neighbouring rows (hfb_csr_cluster_rows_capped) and one
-// 64-column panel: the <= max_cols DISTINCT rows of B the cluster touches are copied once into shared memory with
-// cp.async (512 contiguous bytes per row), then every row of the cluster is a sequence of conflict-free LDS.128 + DFMA
-// against cluster-local column indices.  B is read ~1.7x from L2 (halo overlap between clusters) instead of ~7x.
-constexpr int SPMM_STAGED_WARPS = 8;
-struct __align__(16) SpmmEntry {  // one matrix entry in cluster order: value + cluster-local column index
-    double v;
-    long long l;
-};
-__global__ void __launch_bounds__(SPMM_STAGED_WARPS * 32) csr_spmm_staged_kernel(
-    int m, int max_cols, int max_entries, const int* __restrict__ cl_rowptr, const int* __restrict__ order,
-    const int* __restrict__ s_rowptr, const SpmmEntry* __restrict__ ent, const int* __restrict__ cl_colptr,
-    const int* __restrict__ cl_cols, const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc) {
-    // shared memory: two B-panel buffers [max_cols][64] (double-buffered over the column panels), the cluster's matrix
-    // entries, its distinct-column list and the entry offsets of its rows
-    extern __shared__ __align__(16) unsigned char smem_spmm[];
-    double* sB0 = reinterpret_cast<double*>(smem_spmm);
-    double* sB1 = sB0 + (size_t)max_cols * 64;
-    SpmmEntry* sE = reinterpret_cast<SpmmEntry*>(sB1 + (size_t)max_cols * 64);
-    int* sCols = reinterpret_cast<int*>(sE + max_entries);
-    int* sRow = sCols + max_cols;  // [rows + 1] offsets relative to the cluster's first entry
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cluster = blockIdx.x;
-    const int col_beg = __ldg(cl_colptr + cluster), ncol = __ldg(cl_colptr + cluster + 1) - col_beg;
-    const int slot_beg = __ldg(cl_rowptr + cluster), nrow = __ldg(cl_rowptr + cluster + 1) - slot_beg;
-    const int e_beg = __ldg(s_rowptr + slot_beg);
-    const int nent = __ldg(s_rowptr + slot_beg + nrow) - e_beg;
-    for (int e = threadIdx.x; e < nent; e += SPMM_STAGED_WARPS * 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sE + e)), "l"(ent + e_beg + e) : "memory");
-    for (int j = threadIdx.x; j < ncol; j += SPMM_STAGED_WARPS * 32) sCols[j] = __ldg(cl_cols + col_beg + j);
-    for (int r = threadIdx.x; r <= nrow; r += SPMM_STAGED_WARPS * 32) sRow[r] = __ldg(s_rowptr + slot_beg + r) - e_beg;
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    __syncthreads();  // sCols visible before the first panel is staged
-
-    const int npanel = (m + 63) / 64;
-    auto stage = [&](int panel, double* buf) {
-        const int c = panel * 64 + 2 * lane;
-#pragma unroll 4
-        for (int j = warp; j < ncol; j += SPMM_STAGED_WARPS) {
-            const double* src = B + (long long)sCols[j] * ldb + c;
-            double* dst = buf + j * 64 + 2 * lane;
-            if (c + 1 < m) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-            } else if (c < m) {
-                dst[0] = src[0];
-                dst[1] = 0.0;
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage(0, sB0);
-    for (int panel = 0; panel < npanel; ++panel) {
-        double* cur = (panel & 1) ? sB1 : sB0;
-        if (panel + 1 < npanel) {
-            stage(panel + 1, (panel & 1) ? sB0 : sB1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const int c = panel * 64 + 2 * lane;
-        const double* sBl = cur + 2 * lane;
-        for (int r = warp; r < nrow; r += SPMM_STAGED_WARPS) {
-            const int beg = sRow[r], end = sRow[r + 1];
-            double2 acc = make_double2(0.0, 0.0);
-#pragma unroll 4
-            for (int j = beg; j < end; ++j) {
-                const SpmmEntry en = sE[j];  // same address in all lanes: one broadcast LDS.128
-                const double2 b = *reinterpret_cast<const double2*>(sBl + en.l * 64);
-                acc.x = fma(en.v, b.x, acc.x);
-                acc.y = fma(en.v, b.y, acc.y);
-            }
-            double* cp = C + (long long)__ldg(order + slot_beg + r) * ldc + c;
-            if (c + 1 < m) {
-                *reinterpret_cast<double2*>(cp) = acc;
-            } else if (c < m) {
-                cp[0] = acc.x;
-            }
-        }
-        __syncthreads();  // everyone is done with `cur` before it is refilled two panels later
-    }
 }
 
 // Sparse matrix applied to sample-major data: C[s, r] = sum_j val[j] X[s, col[j]], j in row r.
@@ -592,26 +464,7 @@ extern "C" int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, con
                         (ldb & 1) == 0 && (ldc & 1) == 0)
                            ? 1
                            : 0;
-    static const bool use_v1 = (getenv("HFB_SPMM_V1") != nullptr);
-    if (!use_v1) {
-        return launch_spmm_panel(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, nullptr, stream);
-    }
-    const int ch = (int)((m + 63) / 64);
-    long long blocks = (nrows + 7) / 8;  // 8 warps (rows) per CTA
-    const long long cap = 16LL * num_sms();
-    if (blocks > cap) blocks = cap;
-#define SPMM_CASE(CH)                                                                                               \
-    case CH:                                                                                                        \
-        csr_spmm_kernel<CH><<<(unsigned)blocks, 256, 0, stream>>>(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, \
-                                                                  vec_ok);                                          \
-        break;
-    switch (ch) {
-        SPMM_CASE(1) SPMM_CASE(2) SPMM_CASE(3) SPMM_CASE(4) SPMM_CASE(5) SPMM_CASE(6) SPMM_CASE(7) SPMM_CASE(8)
-        default: return HFB_E_UNSUPPORTED;
-    }
-#undef SPMM_CASE
-    HFB_LAUNCHED();
-    return (int)cudaGetLastError();
+    return launch_spmm_panel(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, nullptr, stream);
 }
 
 extern "C" int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind,
@@ -625,77 +478,6 @@ extern "C" int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* row
                            ? 1
                            : 0;
     return launch_spmm_panel(nrows, (int)m, rowptr, colind, val, B, ldb, C, ldc, vec_ok, order, stream);
-}
-
-// Host-side preprocessing (HOST pointers): group the rows of a sparse matrix with symmetric pattern into clusters of
-// `cluster` graph-neighbouring rows by greedy breadth-first growth; order_out is a permutation of 0..n-1 whose
-// consecutive runs of `cluster` entries are the clusters.  O(nnz).
-extern "C" int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t cluster,
-                                    int32_t* order_out) {
-    if (n <= 0 || !rowptr || !colind || !order_out || cluster <= 0) return HFB_E_BADARG;
-    int32_t* queue = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
-    unsigned char* state = (unsigned char*)calloc((size_t)n, 1);  // 0 free, 1 queued in the current cluster, 2 assigned
-    if (!queue || !state) {
-        free(queue);
-        free(state);
-        return HFB_E_WORKSPACE;
-    }
-    int64_t out = 0, seed_scan = 0;
-    // frontier carried over between clusters so that the next cluster starts next to the previous one
-    int64_t carry_head = 0, carry_tail = 0;
-    int32_t* carry = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
-    if (!carry) {
-        free(queue);
-        free(state);
-        return HFB_E_WORKSPACE;
-    }
-    while (out < n) {
-        int32_t seed = -1;
-        while (carry_head < carry_tail) {
-            const int32_t cnd = carry[carry_head++];
-            if (state[cnd] != 2) {
-                seed = cnd;
-                break;
-            }
-        }
-        if (seed < 0) {
-            while (seed_scan < n && state[seed_scan] == 2) ++seed_scan;
-            if (seed_scan >= n) break;
-            seed = (int32_t)seed_scan;
-        }
-        int64_t head = 0, tail = 0, taken = 0;
-        queue[tail++] = seed;
-        state[seed] = 1;
-        while (head < tail && taken < cluster) {
-            const int32_t r = queue[head++];
-            state[r] = 2;
-            order_out[out++] = r;
-            ++taken;
-            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
-                const int32_t c = colind[j];
-                if (c >= 0 && c < n && state[c] == 0) {
-                    state[c] = 1;
-                    queue[tail++] = c;
-                }
-            }
-        }
-        // rows queued but not taken go back to "free" and seed the following clusters
-        for (int64_t q = head; q < tail; ++q) {
-            state[queue[q]] = 0;
-            if (carry_tail < n) carry[carry_tail++] = queue[q];
-        }
-        if (carry_tail >= n - 1 && carry_head > 0) {  // compact the carry list
-            int64_t w = 0;
-            for (int64_t q = carry_head; q < carry_tail; ++q)
-                if (state[carry[q]] != 2) carry[w++] = carry[q];
-            carry_head = 0;
-            carry_tail = w;
-        }
-    }
-    free(queue);
-    free(state);
-    free(carry);
-    return out == n ? 0 : HFB_E_BADARG;
 }
 
 // Same greedy growth with a cap on the number of DISTINCT columns a cluster may touch (the shared-memory budget of
@@ -771,31 +553,6 @@ extern "C" int hfb_csr_cluster_rows_capped(int64_t n, const int32_t* rowptr, con
 done:
     free(queue); free(carry); free(stamp); free(state);
     return rc;
-}
-
-extern "C" int hfb_csr_spmm_staged(int64_t nclusters, int64_t m, const int32_t* cl_rowptr, const int32_t* order,
-                                   const int32_t* s_rowptr, const void* entries, const int32_t* cl_colptr,
-                                   const int32_t* cl_cols, int32_t max_cols, int32_t max_entries, const double* B,
-                                   int64_t ldb, double* C, int64_t ldc, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (nclusters <= 0 || m <= 0 || !cl_rowptr || !order || !s_rowptr || !entries || !cl_colptr || !cl_cols || !B || !C ||
-        ldb < m || ldc < m || B == C || max_cols <= 0 || max_cols > 256 || max_entries <= 0 || max_entries > 4096)
-        return HFB_E_BADARG;
-    if (reinterpret_cast<uintptr_t>(entries) & 15) return HFB_E_ALIGN;
-    if ((reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15) || (ldb & 1) || (ldc & 1)) return HFB_E_ALIGN;
-    if (nclusters > 0x7fffffffLL) return HFB_E_UNSUPPORTED;
-    const size_t smem = 2 * (size_t)max_cols * 64 * 8 + (size_t)max_entries * sizeof(SpmmEntry) + (size_t)max_cols * 4 + 65 * 4 + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(csr_spmm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
-    csr_spmm_staged_kernel<<<(unsigned)nclusters, SPMM_STAGED_WARPS * 32, smem, stream>>>((int)m, (int)max_cols, (int)max_entries, cl_rowptr, order, s_rowptr,
-                                                                           (const SpmmEntry*)entries, cl_colptr, cl_cols, B,
-                                                                           ldb, C, ldc);
-    HFB_LAUNCHED();
-    return (int)cudaGetLastError();
 }
 
 extern "C" int hfb_csr_spmm_rows(int64_t nsamples, int64_t n, const int32_t* rowptr, const int32_t* colind,

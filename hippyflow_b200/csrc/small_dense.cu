@@ -83,32 +83,36 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
     __syncthreads();
     for (int i0 = 0; i0 < m; i0 += CI_NB) {
         const int nb = min(CI_NB, m - i0), i1 = i0 + nb, w = m - i0;
-        for (int idx = tid; idx < CI_NB * w; idx += T) {
-            const int r = idx / w, cc = idx - r * w;
-            P[r * PW + cc] = (r < nb && cc >= r) ? W[(long long)(i0 + r) * ldw + i0 + cc] : 0.0;
+        for (int idx = tid; idx < CI_NB * (w + 8); idx += T) {
+            const int r = idx / (w + 8), cc = idx - r * (w + 8);
+            P[r * PW + cc] = (r < nb && cc >= r && cc < w) ? W[(long long)(i0 + r) * ldw + i0 + cc] : 0.0;
         }
         __syncthreads();
-        if (tid == 0) {  // diagonal block: R11^T R11 = A11, 8 x 8, sequential
+        if (tid < 32) {  // diagonal block R11^T R11 = A11 (8 x 8) by warp 0: lane c owns column c in registers
+            const int c = tid;
+            double d[CI_NB];
+#pragma unroll
+            for (int r = 0; r < CI_NB; ++r) d[r] = (c < nb && r <= c) ? P[r * PW + c] : (r == c ? 1.0 : 0.0);
             int bad = 0;
-            for (int j = 0; j < CI_NB; ++j)
-                for (int c = 0; c < CI_NB; ++c) Dblk[j * CI_NB + c] = 0.0;
-            for (int j = 0; j < nb && !bad; ++j) {
-                double piv = P[j * PW + j];
-                for (int q = 0; q < j; ++q) piv -= Dblk[q * CI_NB + j] * Dblk[q * CI_NB + j];
-                if (!(piv > 0.0) || !(piv < DBL_MAX)) {
-                    bad = 1;
-                    break;
-                }
-                const double rjj = sqrt(piv);
-                Dblk[j * CI_NB + j] = rjj;
-                rdiag[i0 + j] = rjj;
-                for (int c = j + 1; c < nb; ++c) {
-                    double v = P[j * PW + c];
-                    for (int q = 0; q < j; ++q) v -= Dblk[q * CI_NB + j] * Dblk[q * CI_NB + c];
-                    Dblk[j * CI_NB + c] = v / rjj;
+#pragma unroll
+            for (int j = 0; j < CI_NB; ++j) {
+                const double piv = __shfl_sync(0xffffffffu, d[j], j);
+                if (j < nb && (!(piv > 0.0) || !(piv < DBL_MAX))) bad = 1;
+                const double rjj = sqrt(bad ? 1.0 : piv);
+                if (c == j) d[j] = rjj;
+                else if (c > j) d[j] = d[j] / rjj;
+#pragma unroll
+                for (int r = j + 1; r < CI_NB; ++r) {
+                    const double vr = __shfl_sync(0xffffffffu, d[j], r);      // D[j][r]
+                    if (c >= r) d[r] = fma(-vr, d[j], d[r]);
                 }
             }
-            if (bad) *s_fail = 1;
+            if (c < CI_NB) {
+#pragma unroll
+                for (int r = 0; r < CI_NB; ++r) Dblk[r * CI_NB + c] = (c < nb && r <= c) ? d[r] : 0.0;
+                if (c < nb) rdiag[i0 + c] = d[c];
+            }
+            if (bad && c == 0) *s_fail = 1;
         }
         __syncthreads();
         if (*s_fail) return 1;
@@ -134,32 +138,41 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
             const int r = idx / w, cc = idx - r * w;
             if (cc >= r) W[(long long)(i0 + r) * ldw + i0 + cc] = P[r * PW + cc];
         }
-        // trailing update: W[i][c] -= sum_r P[r][i - i0] P[r][c - i0] for i >= i1, c >= i
-        const int wt = m - i1;
-        for (int base = tid; base < wt * wt; base += T * CI_U) {
-            double v[CI_U];
-            long long off[CI_U];
+        // trailing update W[i][c] -= sum_r P[r][i - i0] P[r][c - i0] (i >= i1, c >= i) as a rank-CI_NB SYRK on the FP64 tensor
+        // pipe: one warp per 8 x 8 tile, A[g][t] = P[k][a0 + g], B[t][g] = P[k][b0 + g] straight from the shared-memory panel
+        // (2 LDS per DMMA instead of 16 LDS per element), C read-modify-written in place as 16-byte pairs.
+        const int wt = m - i1, nt8 = (wt + 7) >> 3;
+        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5, g = lane >> 2, t = lane & 3;
+        for (int tile0 = warp; tile0 < nt8 * nt8; tile0 += nwarps * CI_U) {  // CI_U tiles per trip: their loads overlap
+            double c0[CI_U], c1[CI_U];
+            double* cp[CI_U];
+            int ca[CI_U], cb[CI_U];
+            bool ok0[CI_U], ok1[CI_U];
 #pragma unroll
             for (int u = 0; u < CI_U; ++u) {
-                const int idx = base + u * T;
-                const int ii = idx / wt, c2 = idx - ii * wt;
-                off[u] = (idx < wt * wt && c2 >= ii) ? (long long)(i1 + ii) * ldw + i1 + c2 : -1;
-                v[u] = off[u] >= 0 ? W[off[u]] : 0.0;
+                const int tile = tile0 + u * nwarps;
+                const int ti = tile / nt8, tj = tile - ti * nt8;
+                const int i = i1 + 8 * ti + g, c = i1 + 8 * tj + 2 * t;
+                const bool live = tile < nt8 * nt8 && tj >= ti;
+                ok0[u] = live && i < m && c < m && c >= i;
+                ok1[u] = live && i < m && c + 1 < m && c + 1 >= i;
+                cp[u] = W + (long long)i * ldw + c;
+                ca[u] = live ? nb + 8 * ti + g : 0;
+                cb[u] = live ? nb + 8 * tj + g : 0;
+                c0[u] = ok0[u] ? cp[u][0] : 0.0;
+                c1[u] = ok1[u] ? cp[u][1] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < CI_U; ++u) {
-                if (off[u] < 0) continue;
-                const int idx = base + u * T;
-                const int ii = idx / wt, c2 = idx - ii * wt;
-                const int a = nb + ii, b = nb + c2;  // panel-local column indices of row i and column c
-                double sum = 0.0;
 #pragma unroll
-                for (int r = 0; r < CI_NB; ++r) sum = fma(P[r * PW + a], P[r * PW + b], sum);   // rows r >= nb of P are zero
-                v[u] -= sum;
+                for (int ks = 0; ks < CI_NB / 4; ++ks)
+                    dmma884(c0[u], c1[u], -P[(4 * ks + t) * PW + ca[u]], P[(4 * ks + t) * PW + cb[u]]);
             }
 #pragma unroll
-            for (int u = 0; u < CI_U; ++u)
-                if (off[u] >= 0) W[off[u]] = v[u];
+            for (int u = 0; u < CI_U; ++u) {
+                if (ok0[u]) cp[u][0] = c0[u];
+                if (ok1[u]) cp[u][1] = c1[u];
+            }
         }
         __syncthreads();
     }
@@ -177,9 +190,9 @@ __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S
     __syncthreads();
     for (int i0 = ((m - 1) / CI_NB) * CI_NB; i0 >= 0; i0 -= CI_NB) {
         const int nb = min(CI_NB, m - i0), w = m - i0;
-        for (int idx = tid; idx < CI_NB * w; idx += T) {
-            const int r = idx / w, cc = idx - r * w;
-            P[r * PW + cc] = (r < nb && cc >= r) ? S[(long long)(i0 + r) * lds + i0 + cc] : 0.0;
+        for (int idx = tid; idx < CI_NB * (w + 8); idx += T) {
+            const int r = idx / (w + 8), cc = idx - r * (w + 8);
+            P[r * PW + cc] = (r < nb && cc >= r && cc < w) ? S[(long long)(i0 + r) * lds + i0 + cc] : 0.0;
         }
         if (tid < CI_NB * CI_NB) {
             const int r = tid / CI_NB, q = tid % CI_NB;
@@ -198,39 +211,49 @@ __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S
 #pragma unroll
             for (int jj = 0; jj < CI_NB; ++jj) P[jj * PW + cc] = t[jj];
         }
-        for (int idx = tid; idx < i0 * CI_NB; idx += T) {  // block column R[0:i0][i0:i0+nb] for the eager update
+        for (int idx = tid; idx < (i0 + 8) * CI_NB; idx += T) {  // block column R[0:i0][i0:i0+nb] for the eager update (+ zero tail)
             const int i = idx / CI_NB, q = idx - i * CI_NB;
-            Rcol[idx] = q < nb ? W[(long long)i * ldw + i0 + q] : 0.0;
+            Rcol[idx] = (i < i0 && q < nb) ? W[(long long)i * ldw + i0 + q] : 0.0;
         }
         __syncthreads();
         for (int idx = tid; idx < nb * w; idx += T) {
             const int r = idx / w, cc = idx - r * w;
             if (cc >= r) S[(long long)(i0 + r) * lds + i0 + cc] = P[r * PW + cc];
         }
-        // rows above: S[i][c] += sum_q R[i][i0 + q] S[i0 + q][c], i < i0, c >= i0   (P[q][cc] = 0 for cc < q)
-        for (int base = tid; base < i0 * w; base += T * CI_U) {
-            double v[CI_U];
-            long long off[CI_U];
+        // rows above: S[i][c] += sum_q R[i][i0 + q] S[i0 + q][c], i < i0, c >= i0, again as 8 x 8 DMMA tiles:
+        // A[g][t] = Rcol[i][k], B[t][g] = P[k][cc]  (P[q][cc] = 0 for cc < q, so no triangle test is needed)
+        const int nti = (i0 + 7) >> 3, ntj = (w + 7) >> 3;
+        const int lane = tid & 31, warp = tid >> 5, nwarps = T >> 5, g = lane >> 2, t = lane & 3;
+        for (int tile0 = warp; tile0 < nti * ntj; tile0 += nwarps * CI_U) {
+            double c0[CI_U], c1[CI_U];
+            double* cp[CI_U];
+            int ra[CI_U], cb[CI_U];
+            bool ok0[CI_U], ok1[CI_U];
 #pragma unroll
             for (int u = 0; u < CI_U; ++u) {
-                const int idx = base + u * T;
-                const int i = idx / w, cc = idx - i * w;
-                off[u] = idx < i0 * w ? (long long)i * lds + i0 + cc : -1;
-                v[u] = off[u] >= 0 ? S[off[u]] : 0.0;
+                const int tile = tile0 + u * nwarps;
+                const int ti = tile / ntj, tj = tile - ti * ntj;
+                const int i = 8 * ti + g, cc = 8 * tj + 2 * t;
+                const bool live = tile < nti * ntj;
+                ok0[u] = live && i < i0 && cc < w;
+                ok1[u] = live && i < i0 && cc + 1 < w;
+                cp[u] = S + (long long)i * lds + i0 + cc;
+                ra[u] = live ? (8 * ti + g) * CI_NB : 0;
+                cb[u] = live ? 8 * tj + g : 0;
+                c0[u] = ok0[u] ? cp[u][0] : 0.0;
+                c1[u] = ok1[u] ? cp[u][1] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < CI_U; ++u) {
-                if (off[u] < 0) continue;
-                const int idx = base + u * T;
-                const int i = idx / w, cc = idx - i * w;
-                double sum = 0.0;
 #pragma unroll
-                for (int q = 0; q < CI_NB; ++q) sum = fma(Rcol[i * CI_NB + q], P[q * PW + cc], sum);
-                v[u] += sum;
+                for (int ks = 0; ks < CI_NB / 4; ++ks)
+                    dmma884(c0[u], c1[u], Rcol[ra[u] + 4 * ks + t], P[(4 * ks + t) * PW + cb[u]]);
             }
 #pragma unroll
-            for (int u = 0; u < CI_U; ++u)
-                if (off[u] >= 0) S[off[u]] = v[u];
+            for (int u = 0; u < CI_U; ++u) {
+                if (ok0[u]) cp[u][0] = c0[u];
+                if (ok1[u]) cp[u][1] = c1[u];
+            }
         }
         __syncthreads();
     }
@@ -242,13 +265,13 @@ chol_inverse_kernel(int m, const double* __restrict__ G, long long ldg, double* 
                     double* W0, double* W, long long ldw, double* __restrict__ stat,
                     int scale_columns, double cond_max) {
     extern __shared__ double sm[];
-    const int PW = (m + 1) & ~1;
+    const int PW = (m + 9) & ~1;          // + 8 zero columns: partial DMMA tiles read past the panel width
     double* P = sm;                       // CI_NB x PW
     double* dinv = P + CI_NB * PW;        // m
     double* rdiag = dinv + PW;            // m
     double* Dblk = rdiag + PW;            // CI_NB x CI_NB
     double* red = Dblk + CI_NB * CI_NB;   // 40
-    double* Rcol = red + 40;              // m x CI_NB
+    double* Rcol = red + 40;              // (m + 8) x CI_NB
     const int tid = threadIdx.x, T = blockDim.x;
     const double eps = DBL_EPSILON;
     __shared__ int s_fail;
@@ -487,7 +510,7 @@ extern "C" int hfb_chol_inverse(int64_t m, const double* G, int64_t ldg, double*
     const long long ldw = (m + 1) & ~1LL;
     double* W0 = (double*)workspace;
     double* W = W0 + (size_t)m * ldw;
-    const int PW = (int)ldw;
+    const int PW = (int)((m + 9) & ~1LL);
     const size_t smem = ((size_t)CI_NB * PW + 2 * (size_t)PW + CI_NB * CI_NB + 40 + (size_t)CI_NB * PW) * 8;
     static bool configured[64] = {false};
     int dev = 0;

@@ -192,195 +192,12 @@ __global__ void __launch_bounds__(DM_WARPS * 32)
     }
 }
 
-// ---------------------------------------------------------------------------------------------------- row-slab variant
-// Same arithmetic, different staging: a CTA owns (cluster, column chunk of W <= 320 columns; one chunk at m = 266) and
-// stages the WHOLE chunk of every distinct B row at once -- one warp issues the consecutive 16-byte pieces of a row back to
-// back, so global memory sees contiguous reads of W*8 bytes (2 KB) instead of 512-byte panel slices, and a CTA has its
-// entire input (50-70 KB) in flight while it builds the A fragments.  The k-steps are the OUTER loop of the product (a warp
-// keeps the accumulators of all its column groups, <= 5 x 4 doubles per lane, in registers), so the DMMAs of k-steps 2i,
-// 2i+1 start as soon as the i-th cp.async group (rows 8i .. 8i+7) has landed while the later rows are still in flight.
-// Across CTAs the copy of one overlaps the DMMA phase of the others resident on the SM.
+// column groups per warp of the fragment kernel (W <= 64 * SLAB_NG) and the cp.async group wait it uses
 constexpr int SLAB_NG = 5;          // column groups per warp: W <= 64 * SLAB_NG
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <int RH, int MAXKS>
-__global__ void __launch_bounds__(DM_WARPS * 32, RH == 2 ? 2 : 3)
-    csr_spmm_dmma_slab_kernel(int m, int W, int st256, SpmmBlobLayout L, const unsigned char* __restrict__ blobs,
-                              const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc) {
-    constexpr int ROWS = 8 * RH, COLS = 4 * MAXKS;
-    constexpr int CP = (COLS + 11) / 16 * 16 + 4;
-    constexpr int TILEW = 8 * RH;                   // columns a warp handles per group: one n-tile (RH = 1) or an interleaved pair
-    constexpr int JW = (COLS + DM_WARPS - 1) / DM_WARPS;   // staged rows per warp = cp.async groups
-    constexpr int NA = 2 * RH;                      // accumulator doubles per group and lane
-    extern __shared__ __align__(16) unsigned char smem_dm[];
-    unsigned char* sBlob = smem_dm;
-    double* sD = reinterpret_cast<double*>(smem_dm + L.stride);              // [ROWS][CP]
-    double* sB = sD + ROWS * CP;                                             // [COLS][pitch]
-    const int pitch = W + 4;                                                 // W % 16 == 0 -> pitch % 16 == 4: conflict-free
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int c0 = blockIdx.y * W;                                           // first column of this chunk
-    const int wcur = min(W, m - c0);                                         // columns of this chunk that exist
-    {
-        const int4* src = reinterpret_cast<const int4*>(blobs + (size_t)blockIdx.x * L.stride);
-        int4* dst = reinterpret_cast<int4*>(sBlob);
-        for (int i = tid; i < (L.stride >> 4); i += DM_WARPS * 32) dst[i] = __ldg(src + i);
-        double2* z = reinterpret_cast<double2*>(sD);
-        for (int i = tid; i < (ROWS * CP) >> 1; i += DM_WARPS * 32) z[i] = make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-    const int* hdr = reinterpret_cast<const int*>(sBlob);
-    const int nrow = hdr[0], ncol = hdr[1], nent = hdr[2];
-    const int* sCols = reinterpret_cast<const int*>(sBlob + L.off_cols);
-    const int* sOut = reinterpret_cast<const int*>(sBlob + L.off_outrow);
-    const int KS = (ncol + 3) >> 2;
-    const int width = m + (m & 1);                                           // readable columns of a B row
-    const int npiece = (min(W, width - c0) + 1) >> 1;                        // 16-byte pieces per row with real data
-    const int npiece_all = (((wcur + TILEW - 1) / TILEW) * TILEW) >> 1;      // pieces the fragment reads touch
-    // stage: warp w copies rows w, w + 8, ... (one cp.async group each); consecutive lanes take consecutive pieces.
-    // Rows >= ncol inside the k padding and pieces past the readable width are zero-filled (src-size 0).
-#pragma unroll
-    for (int i = 0; i < JW; ++i) {
-        const int j = warp + DM_WARPS * i;
-        if (j < (KS << 2)) {
-            const bool real = j < ncol;
-            const double* src = B + (real ? (long long)sCols[j] * ldb + c0 : 0);
-            const uint32_t dst = smem_u32(sB + j * pitch);
-            for (int p = lane; p < npiece_all; p += 32) {
-                const bool valid = real && p < npiece;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u * p),
-                             "l"(src + (valid ? 2 * p : 0)), "r"(valid ? 16 : 0)
-                             : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    {
-        const int4* ent = reinterpret_cast<const int4*>(sBlob + L.off_ent);
-        for (int e = tid; e < nent; e += DM_WARPS * 32) {
-            const int4 en = ent[e];
-            sD[en.w * CP + en.z] = __hiloint2double(en.y, en.x);
-        }
-    }
-    __syncthreads();
-    const int h = warp % RH, cg = warp / RH;
-    double a[MAXKS];
-    unsigned nz = 0;
-#pragma unroll
-    for (int ks = 0; ks < MAXKS; ++ks) {
-        a[ks] = sD[(g + 8 * h) * CP + 4 * ks + t];
-        nz |= (__ballot_sync(0xffffffffu, a[ks] != 0.0) ? 1u : 0u) << ks;
-    }
-    // this warp's column groups: n0 = (cg + (8/RH) i) * TILEW, i < ngrp
-    constexpr int GSTRIDE = (DM_WARPS / RH) * TILEW;                         // 64 columns
-    const int ngrp = (wcur > cg * TILEW) ? (wcur - cg * TILEW + GSTRIDE - 1) / GSTRIDE : 0;
-    double acc[SLAB_NG][NA];
-#pragma unroll
-    for (int i = 0; i < SLAB_NG; ++i)
-#pragma unroll
-        for (int q = 0; q < NA; ++q) acc[i][q] = 0.0;
-    uint32_t bfrag;
-    asm volatile("mov.u32 %0, %1;" : "=r"(bfrag) : "r"(smem_u32(sB + t * pitch + cg * TILEW + (RH == 2 ? 2 * g : g))));
-    const uint32_t kstep_bytes = (uint32_t)(4 * pitch) * 8u;
-
-    auto ksteps = [&](int ks) {                    // one k-step over all column groups of this warp
-        if (nz >> ks & 1u) {
-            const uint32_t bk = bfrag + ks * kstep_bytes;
-#pragma unroll
-            for (int i = 0; i < SLAB_NG; ++i) {
-                if (i < ngrp) {
-                    if (RH == 2) {
-                        const double2 b = lds128(bk + (uint32_t)(i * GSTRIDE) * 8u);
-                        dmma884(acc[i][0], acc[i][1], a[ks], b.x);
-                        dmma884(acc[i][NA - 2], acc[i][NA - 1], a[ks], b.y);
-                    } else {
-                        const double b = lds64(bk + (uint32_t)(i * GSTRIDE) * 8u);
-                        dmma884(acc[i][0], acc[i][1], a[ks], b);
-                    }
-                }
-            }
-        }
-    };
-    // rows 8i .. 8i+7 = cp.async group i of every warp -> k-steps 2i, 2i+1
-#pragma unroll
-    for (int i = 0; i < JW; ++i) {
-        switch (JW - 1 - i) {
-            case 0: cp_async_wait_group<0>(); break;
-            case 1: cp_async_wait_group<1>(); break;
-            case 2: cp_async_wait_group<2>(); break;
-            case 3: cp_async_wait_group<3>(); break;
-            case 4: cp_async_wait_group<4>(); break;
-            default: cp_async_wait_group<5>(); break;
-        }
-        __syncthreads();
-        if (2 * i < MAXKS) ksteps(2 * i);
-        if (2 * i + 1 < MAXKS) ksteps(2 * i + 1);
-    }
-
-    const int r = g + 8 * h;
-    if (r < nrow) {
-        double* outp = C + (long long)sOut[r] * ldc + c0 + cg * TILEW + (RH == 2 ? 4 * t : 2 * t);
-#pragma unroll
-        for (int i = 0; i < SLAB_NG; ++i) {
-            if (i < ngrp) {
-                double* cp = outp + i * GSTRIDE;
-                const int cc = c0 + cg * TILEW + i * GSTRIDE + (RH == 2 ? 4 * t : 2 * t);   // first column of this lane
-                if (RH == 2) {
-                    // lane holds four consecutive columns: A.c0, B.c0, A.c1, B.c1
-                    if (st256 && cc + 3 < m) {
-                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(cp)), "d"(acc[i][0]), "d"(acc[i][NA - 2]),
-                                     "d"(acc[i][1]), "d"(acc[i][NA - 1])
-                                     : "memory");
-                    } else {
-                        if (cc + 1 < m) {
-                            *reinterpret_cast<double2*>(cp) = make_double2(acc[i][0], acc[i][NA - 2]);
-                        } else if (cc < m) {
-                            cp[0] = acc[i][0];
-                        }
-                        if (cc + 3 < m) {
-                            *reinterpret_cast<double2*>(cp + 2) = make_double2(acc[i][1], acc[i][NA - 1]);
-                        } else if (cc + 2 < m) {
-                            cp[2] = acc[i][1];
-                        }
-                    }
-                } else {
-                    if (cc + 1 < m) {
-                        *reinterpret_cast<double2*>(cp) = make_double2(acc[i][0], acc[i][1]);
-                    } else if (cc < m) {
-                        cp[0] = acc[i][0];
-                    }
-                }
-            }
-        }
-    }
-}
-
-template <int RH, int MAXKS>
-static int launch_dmma_slab(int64_t nclusters, int m, int W, const SpmmBlobLayout& L, const void* blobs, const double* B,
-                            int64_t ldb, double* C, int64_t ldc, cudaStream_t stream) {
-    constexpr int ROWS = 8 * RH, COLS = 4 * MAXKS, CP = (COLS + 11) / 16 * 16 + 4;
-    const size_t smem = (size_t)L.stride + sizeof(double) * ((size_t)ROWS * CP + (size_t)COLS * (W + 4));
-    if (smem > 227 * 1024 || W > 64 * SLAB_NG) return HFB_E_UNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_slab_kernel<RH, MAXKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
-    const int nchunk = (m + W - 1) / W;
-    if (nchunk > 65535) return HFB_E_UNSUPPORTED;
-    // 256-bit result stores need 32-byte aligned rows (true for the padded blocks of this package; checked, not assumed)
-    const int st256 = ((reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc & 3) == 0) ? 1 : 0;
-    dim3 grid((unsigned)nclusters, (unsigned)nchunk);
-    csr_spmm_dmma_slab_kernel<RH, MAXKS><<<grid, DM_WARPS * 32, smem, stream>>>(
-        m, W, st256, L, static_cast<const unsigned char*>(blobs), B, ldb, C, ldc);
-    ++g_launch_count;
-    return (int)cudaGetLastError();
 }
 
 template <int RH, int MAXKS, int NT>
@@ -578,218 +395,87 @@ static int launch_dmma_frag(int64_t nclusters, int m, int W, const FragBlobLayou
     return (int)cudaGetLastError();
 }
 
-// ---------------------------------------------------------------------------------------------------- cluster-pipelined variant
-// The fragment-record kernel with the per-CTA latency chain taken off the critical path: a CTA walks clusters
-// c = blockIdx.x, blockIdx.x + gridDim.x, ... (grid = resident CTAs only) with two row buffers.  While the DMMAs of cluster c
-// run from buffer b, the cp.asyncs of cluster c' = c + gridDim.x fill buffer b^1, its A fragments / masks / result row
-// arrive in a second register set, and the column list of the cluster after that is already being fetched -- so every
-// global-memory round trip of a cluster overlaps the arithmetic of its predecessor inside the same CTA.
-template <int RH, int MAXKS>
-__global__ void __launch_bounds__(DM_WARPS * 32, 1)
-    csr_spmm_dmma_pipe_kernel(int m, int W, int st256, int nclusters, FragBlobLayout F, const unsigned char* __restrict__ blobs,
-                              const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc) {
-    constexpr int COLS = 4 * MAXKS;
-    constexpr int TILEW = 8 * RH;
-    constexpr int JW = (COLS + DM_WARPS - 1) / DM_WARPS;
-    constexpr int NA = 2 * RH;
-    constexpr int GSTRIDE = (DM_WARPS / RH) * TILEW;
-    extern __shared__ __align__(16) unsigned char smem_dm[];
-    double* sB = reinterpret_cast<double*>(smem_dm);                         // [2][COLS][pitch]
-    const int pitch = W + 4;
-    const uint32_t buf_bytes = (uint32_t)(COLS * pitch) * 8u;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int h = warp % RH, cg = warp / RH;
-    const int c0 = blockIdx.y * W;
-    const int wcur = min(W, m - c0);
-    const int width = m + (m & 1);
-    const int npiece = (min(W, width - c0) + 1) >> 1;
-    const int npiece_all = (((wcur + TILEW - 1) / TILEW) * TILEW) >> 1;
-    const int ngrp = (wcur > cg * TILEW) ? (wcur - cg * TILEW + GSTRIDE - 1) / GSTRIDE : 0;
-    const uint32_t kstep_bytes = (uint32_t)(4 * pitch) * 8u;
-    uint32_t bfrag0, stage0;
-    asm volatile("mov.u32 %0, %1;" : "=r"(bfrag0) : "r"(smem_u32(sB + t * pitch + cg * TILEW + (RH == 2 ? 2 * g : g))));
-    asm volatile("mov.u32 %0, %1;" : "=r"(stage0) : "r"(smem_u32(sB + warp * pitch)));
-
-    int mycol[JW];
-    int ncol_s = 0;                                                         // columns of the cluster whose list is in mycol
-    auto load_cols = [&](int c) {
-        const unsigned char* blob = blobs + (size_t)c * F.stride;
-        ncol_s = __ldg(reinterpret_cast<const int*>(blob) + 1);
-        const int* gcols = reinterpret_cast<const int*>(blob + F.off_cols);
-#pragma unroll
-        for (int i = 0; i < JW; ++i) mycol[i] = __ldg(gcols + warp + DM_WARPS * i);
-    };
-    auto stage = [&](int which) {                                           // rows of the cluster described by mycol / ncol_s
-        const int kpad = ((ncol_s + 3) >> 2) << 2;
-#pragma unroll
-        for (int i = 0; i < JW; ++i) {
-            const int j = warp + DM_WARPS * i;
-            if (j < kpad) {
-                const bool real = j < ncol_s;
-                const double* src = B + (real ? (long long)mycol[i] * ldb + c0 : 0);
-                const uint32_t dst = stage0 + which * buf_bytes + (uint32_t)(i * DM_WARPS * pitch) * 8u;
-                for (int p = lane; p < npiece_all; p += 32) {
-                    const bool valid = real && p < npiece;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16u * p),
-                                 "l"(src + (valid ? 2 * p : 0)), "r"(valid ? 16 : 0)
-                                 : "memory");
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto load_frags = [&](int c, double (&af)[MAXKS], unsigned& nzf, int& orowf) {
-        const unsigned char* blob = blobs + (size_t)c * F.stride;
-        const int* hdr = reinterpret_cast<const int*>(blob);
-        const int nrow = __ldg(hdr);
-        nzf = (unsigned)__ldg(hdr + 2 + h);
-        const double* afrag = reinterpret_cast<const double*>(blob + F.off_afrag) + h * 32 + lane;
-#pragma unroll
-        for (int ks = 0; ks < MAXKS; ++ks) af[ks] = __ldg(afrag + ks * RH * 32);   // zero blocks are stored as zeros
-        const int r = g + 8 * h;
-        orowf = r < nrow ? __ldg(reinterpret_cast<const int*>(blob + F.off_outrow) + r) : -1;
-    };
-
-    int c = blockIdx.x;
-    if (c >= nclusters) return;
-    load_cols(c);
-    stage(0);
-    double a[MAXKS];
-    unsigned nz;
-    int orow;
-    load_frags(c, a, nz, orow);
-    int cn = c + gridDim.x;
-    if (cn < nclusters) load_cols(cn);
-    int buf = 0;
-    while (true) {
-        const bool has_next = cn < nclusters;
-        double an[MAXKS];
-        unsigned nzn = 0;
-        int orown = -1;
-#pragma unroll
-        for (int ks = 0; ks < MAXKS; ++ks) an[ks] = 0.0;
-        if (has_next) {
-            stage(buf ^ 1);                                  // free since the closing barrier of the previous iteration
-            load_frags(cn, an, nzn, orown);
-            if (cn + (int)gridDim.x < nclusters) load_cols(cn + gridDim.x);
-            cp_async_wait_group<1>();
-        } else {
-            cp_async_wait_group<0>();
-        }
-        __syncthreads();
-        double acc[SLAB_NG][NA];
-#pragma unroll
-        for (int i = 0; i < SLAB_NG; ++i)
-#pragma unroll
-            for (int q = 0; q < NA; ++q) acc[i][q] = 0.0;
-        const uint32_t bcur = bfrag0 + buf * buf_bytes;
-#pragma unroll
-        for (int ks = 0; ks < MAXKS; ++ks) {
-            if (nz >> ks & 1u) {
-                const uint32_t bk = bcur + ks * kstep_bytes;
-#pragma unroll
-                for (int i = 0; i < SLAB_NG; ++i) {
-                    if (i < ngrp) {
-                        if (RH == 2) {
-                            const double2 b = lds128(bk + (uint32_t)(i * GSTRIDE) * 8u);
-                            dmma884(acc[i][0], acc[i][1], a[ks], b.x);
-                            dmma884(acc[i][NA - 2], acc[i][NA - 1], a[ks], b.y);
-                        } else {
-                            const double b = lds64(bk + (uint32_t)(i * GSTRIDE) * 8u);
-                            dmma884(acc[i][0], acc[i][1], a[ks], b);
-                        }
-                    }
-                }
-            }
-        }
-        if (orow >= 0) {
-            double* outp = C + (long long)orow * ldc + c0 + cg * TILEW + (RH == 2 ? 4 * t : 2 * t);
-#pragma unroll
-            for (int i = 0; i < SLAB_NG; ++i) {
-                if (i < ngrp) {
-                    double* cp = outp + i * GSTRIDE;
-                    const int cc = c0 + cg * TILEW + i * GSTRIDE + (RH == 2 ? 4 * t : 2 * t);
-                    if (RH == 2) {
-                        if (st256 && cc + 3 < m) {
-                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(cp)),
-                                         "d"(acc[i][0]), "d"(acc[i][NA - 2]), "d"(acc[i][1]), "d"(acc[i][NA - 1])
-                                         : "memory");
-                        } else {
-                            if (cc + 1 < m) {
-                                *reinterpret_cast<double2*>(cp) = make_double2(acc[i][0], acc[i][NA - 2]);
-                            } else if (cc < m) {
-                                cp[0] = acc[i][0];
-                            }
-                            if (cc + 3 < m) {
-                                *reinterpret_cast<double2*>(cp + 2) = make_double2(acc[i][1], acc[i][NA - 1]);
-                            } else if (cc + 2 < m) {
-                                cp[2] = acc[i][1];
-                            }
-                        }
-                    } else {
-                        if (cc + 1 < m) {
-                            *reinterpret_cast<double2*>(cp) = make_double2(acc[i][0], acc[i][1]);
-                        } else if (cc < m) {
-                            cp[0] = acc[i][0];
-                        }
-                    }
-                }
-            }
-        }
-        if (!has_next) break;
-        __syncthreads();                                     // everyone is done reading `buf` before the next stage refills it
-#pragma unroll
-        for (int ks = 0; ks < MAXKS; ++ks) a[ks] = an[ks];
-        nz = nzn;
-        orow = orown;
-        cn += gridDim.x;
-        buf ^= 1;
-    }
-}
-
-template <int RH, int MAXKS>
-static int launch_dmma_pipe(int64_t nclusters, int m, int W, const FragBlobLayout& F, const void* blobs, const double* B,
-                            int64_t ldb, double* C, int64_t ldc, cudaStream_t stream) {
-    constexpr int COLS = 4 * MAXKS;
-    const size_t smem = 2 * sizeof(double) * (size_t)COLS * (W + 4);
-    if (smem > 227 * 1024 || W > 64 * SLAB_NG) return HFB_E_UNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_pipe_kernel<RH, MAXKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
-    const int nchunk = (m + W - 1) / W;
-    if (nchunk > 65535) return HFB_E_UNSUPPORTED;
-    static int sms = 0, per_sm = 0;
-    static size_t per_sm_for = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            sms <= 0)
-            sms = 148;
-    }
-    if (!per_sm || per_sm_for != smem) {           // resident CTAs per SM for this shared-memory size (cached)
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_dmma_pipe_kernel<RH, MAXKS>, DM_WARPS * 32, smem) !=
-                cudaSuccess || per_sm < 1)
-            per_sm = 1;
-        per_sm_for = smem;
-    }
-    long long gx = (long long)sms * per_sm;
-    if (gx > nclusters) gx = nclusters;
-    const int st256 = ((reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc & 3) == 0) ? 1 : 0;
-    dim3 grid((unsigned)gx, (unsigned)nchunk);
-    csr_spmm_dmma_pipe_kernel<RH, MAXKS><<<grid, DM_WARPS * 32, smem, stream>>>(
-        m, W, st256, (int)nclusters, F, static_cast<const unsigned char*>(blobs), B, ldb, C, ldc);
-    ++g_launch_count;
-    return (int)cudaGetLastError();
-}
-
 }  // namespace hfb
 
 using namespace hfb;
+
+extern "C" int64_t hfb_csr_cluster_blob_stride(int32_t max_rows, int32_t max_cols, int32_t max_entries) {
+    if (max_rows <= 0 || max_cols <= 0 || max_entries <= 0) return HFB_E_BADARG;
+    return blob_layout(max_rows, max_cols, max_entries).stride;
+}
+
+// HOST function: packs the clusters of (order, cluster_ptr) into the blob format above.  O(nnz).
+extern "C" int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int32_t* colind, const double* val,
+                                     const int32_t* order, const int32_t* cluster_ptr, int64_t nclusters, int32_t max_rows,
+                                     int32_t max_cols, int32_t max_entries, void* blobs_out) {
+    if (n <= 0 || !rowptr || !colind || !val || !order || !cluster_ptr || nclusters <= 0 || max_rows <= 0 || max_cols <= 0 ||
+        max_cols > 128 || max_entries <= 0 || !blobs_out)
+        return HFB_E_BADARG;
+    const SpmmBlobLayout L = blob_layout(max_rows, max_cols, max_entries);
+    std::vector<int32_t> stamp((size_t)n, -1), local((size_t)n, 0);
+    std::vector<int32_t> touched;                 // distinct columns of the current cluster, first-touch order
+    std::vector<unsigned char> half((size_t)n, 0);  // bit 0: touched by cluster rows 0..7, bit 1: by rows >= 8
+    unsigned char* out = static_cast<unsigned char*>(blobs_out);
+    for (int64_t c = 0; c < nclusters; ++c) {
+        unsigned char* blob = out + (size_t)c * L.stride;
+        memset(blob, 0, (size_t)L.stride);
+        int32_t* hdr = reinterpret_cast<int32_t*>(blob);
+        int32_t* rowoff = reinterpret_cast<int32_t*>(blob + L.off_rowoff);
+        int32_t* outrow = reinterpret_cast<int32_t*>(blob + L.off_outrow);
+        int32_t* cols = reinterpret_cast<int32_t*>(blob + L.off_cols);
+        unsigned char* ent = blob + L.off_ent;
+        const int32_t s0 = cluster_ptr[c], s1 = cluster_ptr[c + 1];
+        const int32_t nrow = s1 - s0;
+        if (nrow <= 0 || nrow > max_rows) return HFB_E_BADARG;
+        // pass 1: the distinct columns and which 8-row half of the cluster touches them
+        touched.clear();
+        for (int32_t r = 0; r < nrow; ++r) {
+            const int32_t row = order[s0 + r];
+            if (row < 0 || row >= n) return HFB_E_BADARG;
+            for (int32_t j = rowptr[row]; j < rowptr[row + 1]; ++j) {
+                const int32_t col = colind[j];
+                if (col < 0 || col >= n) return HFB_E_BADARG;
+                if (stamp[col] != (int32_t)c) {
+                    if ((int32_t)touched.size() >= max_cols) return HFB_E_UNSUPPORTED;
+                    stamp[col] = (int32_t)c;
+                    half[col] = 0;
+                    touched.push_back(col);
+                }
+                half[col] |= (r < 8) ? 1 : 2;
+            }
+        }
+        // local numbering: columns only the upper half touches, then shared ones, then lower-half only (first-touch order
+        // within a class).  Each half's nonzeros then fill a contiguous range of local columns, so the DMMA kernel skips
+        // the 8 x 4 blocks of the dense cluster matrix outside that range; the other kernels do not care about the order.
+        int32_t ncol = 0;
+        for (unsigned char want : {(unsigned char)1, (unsigned char)3, (unsigned char)2})
+            for (int32_t col : touched)
+                if (half[col] == want) {
+                    local[col] = ncol;
+                    cols[ncol++] = col;
+                }
+        // pass 2: the entries
+        int32_t nent = 0;
+        for (int32_t r = 0; r < nrow; ++r) {
+            const int32_t row = order[s0 + r];
+            rowoff[r] = nent;
+            outrow[r] = row;
+            for (int32_t j = rowptr[row]; j < rowptr[row + 1]; ++j) {
+                if (nent >= max_entries) return HFB_E_UNSUPPORTED;
+                memcpy(ent + 16 * (size_t)nent, &val[j], 8);
+                const int32_t l = local[colind[j]];
+                memcpy(ent + 16 * (size_t)nent + 8, &l, 4);
+                memcpy(ent + 16 * (size_t)nent + 12, &r, 4);
+                ++nent;
+            }
+        }
+        rowoff[nrow] = nent;
+        hdr[0] = nrow;
+        hdr[1] = ncol;
+        hdr[2] = nent;
+    }
+    return 0;
+}
 
 extern "C" int hfb_csr_spmm_dmma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                                  int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
@@ -803,32 +489,6 @@ extern "C" int hfb_csr_spmm_dmma(int64_t nclusters, int64_t m, const void* blobs
     if (nclusters > 0x7fffffffLL || m > 0x3fffffffLL) return HFB_E_UNSUPPORTED;
     if (max_rows > 16 || max_cols > 48) return HFB_E_UNSUPPORTED;   // A fragments must fit in registers
     const SpmmBlobLayout L = blob_layout(max_rows, max_cols, max_entries);
-    // HFB_SPMM_DMMA_W = chunk width of the row-slab variant (multiple of 16; 0/unset = double-buffered 64-column panels)
-    const char* w_env = getenv("HFB_SPMM_DMMA_W");
-    int W = w_env ? atoi(w_env) : 0;
-    if (W > 0) {
-        W = (W + 15) / 16 * 16;
-        if (W > 64 * SLAB_NG) W = 64 * SLAB_NG;
-        const int64_t mp = (m + 15) / 16 * 16;
-        if (W > mp) W = (int)mp;
-        // equalise the chunks (same chunk count, smallest width that covers m); more chunks if the slab would not fit
-        const int rows_pad = max_cols <= 16 ? 16 : max_cols <= 24 ? 24 : max_cols <= 32 ? 32 : 48;
-        for (int nchunk = (int)((m + W - 1) / W);; ++nchunk) {
-            W = (int)(((m + nchunk - 1) / nchunk + 15) / 16 * 16);
-            if ((size_t)L.stride + 8u * ((size_t)16 * 52 + (size_t)rows_pad * (W + 4)) <= 200u * 1024u || W <= 16) break;
-        }
-#define HFB_DM_SLAB(RH_, KS_) launch_dmma_slab<RH_, KS_>(nclusters, (int)m, W, L, blobs, B, ldb, C, ldc, stream)
-        if (max_rows <= 8) {
-            if (max_cols <= 16) return HFB_DM_SLAB(1, 4);
-            if (max_cols <= 24) return HFB_DM_SLAB(1, 6);
-            if (max_cols <= 32) return HFB_DM_SLAB(1, 8);
-            return HFB_DM_SLAB(1, 12);
-        }
-        if (max_cols <= 24) return HFB_DM_SLAB(2, 6);
-        if (max_cols <= 32) return HFB_DM_SLAB(2, 8);
-        return HFB_DM_SLAB(2, 12);
-#undef HFB_DM_SLAB
-    }
     // panel width for clusters of <= 8 rows: HFB_SPMM_DMMA_NT = 1 (64 columns, default) / 2 (128 columns)
     const char* nt_env = getenv("HFB_SPMM_DMMA_NT");
     const int nt = nt_env ? atoi(nt_env) : 1;
@@ -920,7 +580,7 @@ extern "C" int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, cons
     return 0;
 }
 
-static int dmma_frag_dispatch(int pipelined, int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+static int dmma_frag_dispatch(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                               int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nclusters <= 0 || m <= 0 || !blobs || !B || !C || B == C || chunk_cols < 0) return HFB_E_BADARG;
@@ -939,9 +599,7 @@ static int dmma_frag_dispatch(int pipelined, int64_t nclusters, int64_t m, const
         W = (int)(((m + nchunk - 1) / nchunk + 15) / 16 * 16);
         if (8u * (size_t)(4 * maxks) * (W + 4) <= 100u * 1024u || W <= 16) break;
     }
-#define HFB_DM_FRAG(RH_, KS_)                                                                         \
-    (pipelined ? launch_dmma_pipe<RH_, KS_>(nclusters, (int)m, W, F, blobs, B, ldb, C, ldc, stream) \
-               : launch_dmma_frag<RH_, KS_>(nclusters, (int)m, W, F, blobs, B, ldb, C, ldc, stream))
+#define HFB_DM_FRAG(RH_, KS_) launch_dmma_frag<RH_, KS_>(nclusters, (int)m, W, F, blobs, B, ldb, C, ldc, stream)
     if (rh == 1) {
         if (maxks == 4) return HFB_DM_FRAG(1, 4);
         if (maxks == 6) return HFB_DM_FRAG(1, 6);
@@ -956,10 +614,5 @@ static int dmma_frag_dispatch(int pipelined, int64_t nclusters, int64_t m, const
 
 extern "C" int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                                       int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream) {
-    return dmma_frag_dispatch(0, nclusters, m, blobs, max_rows, max_cols, chunk_cols, B, ldb, C, ldc, stream);
-}
-
-extern "C" int hfb_csr_spmm_dmma_pipe(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
-                                      int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream) {
-    return dmma_frag_dispatch(1, nclusters, m, blobs, max_rows, max_cols, chunk_cols, B, ldb, C, ldc, stream);
+    return dmma_frag_dispatch(nclusters, m, blobs, max_rows, max_cols, chunk_cols, B, ldb, C, ldc, stream);
 }

@@ -22,7 +22,7 @@ class CsrMatrix:
     """Sparse SPD weight matrix (mass matrix M, prior precision R) resident on the device as int32 CSR,
     the format the reference exports (PODProjector.py:695-697)."""
 
-    WIDE_DEFAULT = "frag"       # kernel 'auto' uses for blocks of >= 192 columns ("frag"; "pipe" measured 2x slower, kept as an evaluated alternative)
+    WIDE_DEFAULT = "frag"       # kernel 'auto' uses for blocks of >= 192 columns
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
@@ -40,15 +40,11 @@ class CsrMatrix:
         self.order = None
         self.plan = None
         import os
-        # SpMM kernel for wide blocks (m >= 96) over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
-        #   "auto"     (default) "frag" for m >= 192, "dmma" for narrower blocks, "staged" when the clusters exceed the
-        #              DMMA kernels' register budget (16 rows x 48 distinct columns)
-        #   "frag"     dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
-        #   "pipe"     "frag" with resident CTAs walking the clusters, next cluster's rows in flight during the DMMAs
-        #   "dmma"     same arithmetic, records decoded in the kernel, double-buffered 64-column panels
-        #   "staged"   cp.async panels + one LDS.128 pair per matrix entry (round-1 default, LSU-bound)
-        #   "regblock" dense cluster block against B rows loaded straight into registers (scoreboard-bound)
-        #   "tma"      persistent CTAs fed by cp.async.bulk row copies (TMA small-copy rate bound)
+        # SpMM kernel for blocks of >= 96 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
+        #   "auto"  (default) "frag" for m >= 192, "dmma" for narrower blocks
+        #   "frag"  dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
+        #   "dmma"  same arithmetic, records decoded in the kernel, double-buffered 64-column panels
+        # (five further variants were measured and retired: profiles/r01_spmm_variants.md, tools/experiments/spmm_variants/)
         self.impl = os.environ.get("HFB_SPMM_IMPL", "auto")
         if cluster_rows and M.shape[0] == M.shape[1] and M.shape[0] >= 4096:
             try:
@@ -61,56 +57,46 @@ class CsrMatrix:
     def _build_plan(M, device, max_rows=None, max_cols=None):
         import os
         # (16, 32) measured best on B200 for the cluster kernels (cfg2, m = 266; profiles/r01_spmm_variants.md: DMMA
-        # fragment kernel 0.271 ms, (12, 32) 0.283, (8, 24) 0.286, (8, 20) 0.326; cp.async-panel kernel 0.343 ms, (24, 48)
-        # 0.358, (32, 64) 0.389): one cluster = two DMMA row halves x eight k-steps, 71 KB of staged rows, 3 CTAs per SM
+        # fragment kernel 0.271 ms, (12, 32) 0.283, (8, 24) 0.286, (8, 20) 0.326): one cluster = two DMMA row halves x
+        # eight k-steps, 71 KB of staged rows, 3 CTAs per SM
         max_rows = int(os.environ.get("HFB_SPMM_ROWS", 16)) if max_rows is None else max_rows
         if max_cols is None:
             # 7-point P1 stencils fill (16, 32) clusters; denser rows (9-point, P2: 9-20 entries) would shrink them to 2-3 rows
             # under 32 columns, so they get the DMMA kernels' largest column budget instead
             max_cols = int(os.environ.get("HFB_SPMM_COLS", 32 if M.nnz <= 8 * M.shape[0] else 48))
-        indptr, indices, data = np.asarray(M.indptr, dtype=np.int64), np.asarray(M.indices, dtype=np.int64), np.asarray(M.data)
         order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, max_rows, max_cols)
-        n = M.shape[0]
         ncl = cptr.size - 1
-        counts = (indptr[1:] - indptr[:-1])[order]                       # nnz per row, cluster order
-        s_rowptr = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(counts, out=s_rowptr[1:])
-        # gather the entries in cluster order
-        src = np.repeat(indptr[:-1][order], counts) + (np.arange(s_rowptr[-1]) - np.repeat(s_rowptr[:-1], counts))
-        cols, vals = indices[src], data[src]
-        cl_of_slot = np.repeat(np.arange(ncl), np.diff(cptr))            # cluster id of every slot
-        cl_of_nnz = np.repeat(cl_of_slot, counts)
-        key = cl_of_nnz * n + cols
-        ukey, inv = np.unique(key, return_inverse=True)
-        ucl = ukey // n
-        cl_colptr = np.searchsorted(ucl, np.arange(ncl + 1)).astype(np.int64)
-        lcol = inv - cl_colptr[cl_of_nnz]
-        assert lcol.max() < max_cols and np.diff(cl_colptr).max() <= max_cols
-        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a.astype(dt)), device=device)
-        ent = np.empty((vals.size, 2), dtype=np.float64)                 # 16-byte {double value; int64 local column}
-        ent[:, 0] = vals
-        ent[:, 1] = lcol.astype(np.int64).view(np.float64)
-        max_entries = int(np.diff(s_rowptr[cptr]).max())
-        plan = {"nclusters": int(ncl), "max_cols": int(np.diff(cl_colptr).max()), "max_entries": max_entries,
-                "cl_rowptr": t(cptr, np.int32), "order": t(order, np.int32), "s_rowptr": t(s_rowptr, np.int32),
-                "entries": torch.as_tensor(ent, device=device), "cl_colptr": t(cl_colptr, np.int32),
-                "cl_cols": t(ukey % n, np.int32)}
-        # the persistent TMA-fed kernel reads one fixed-stride record per cluster, packed on first use (_tma_blobs)
-        plan["max_rows"] = int(np.diff(cptr).max())
-        plan["max_cols_cap"] = plan["max_cols"]
-        plan["_host"] = (M.indptr, M.indices, M.data, order, cptr)
+        indptr = np.asarray(M.indptr, dtype=np.int64)
+        counts = (indptr[1:] - indptr[:-1])[order]                        # nnz per row, cluster order
+        ent_ptr = np.zeros(order.size + 1, dtype=np.int64)
+        np.cumsum(counts, out=ent_ptr[1:])
+        # largest number of distinct columns any cluster actually touches (selects the kernel instantiation)
+        indices = np.asarray(M.indices, dtype=np.int64)
+        src = np.repeat(indptr[:-1][order], counts) + (np.arange(ent_ptr[-1]) - np.repeat(ent_ptr[:-1], counts))
+        cl_of_nnz = np.repeat(np.repeat(np.arange(ncl), np.diff(cptr)), counts)
+        ukey = np.unique(cl_of_nnz * M.shape[0] + indices[src])
+        distinct = np.bincount(ukey // M.shape[0], minlength=ncl)
+        assert distinct.max() <= max_cols
+        plan = {"nclusters": int(ncl), "order": torch.as_tensor(np.ascontiguousarray(order.astype(np.int32)), device=device),
+                "max_rows": int(np.diff(cptr).max()), "max_cols_cap": int(distinct.max()),
+                "max_entries": int(np.diff(ent_ptr[cptr]).max()),
+                "_host": (M.indptr, M.indices, M.data, order, cptr)}
         return plan
 
     @staticmethod
-    def _tma_blobs(plan, device):
+    def _panel_blobs(plan, device):
+        """Per-cluster records of the panel DMMA kernel, packed on first use."""
         if "blobs" not in plan:
             indptr, indices, data, order, cptr = plan["_host"]
             plan["blobs"] = torch.as_tensor(K.csr_pack_clusters(indptr, indices, data, order, cptr, plan["max_rows"],
                                                                 plan["max_cols_cap"], plan["max_entries"]), device=device)
         return plan
 
+    _tma_blobs = _panel_blobs       # round-1 name
+
     @staticmethod
     def _frag_blobs(plan, device):
+        """Fragment records of the whole-row DMMA kernel, packed on first use."""
         if "fblobs" not in plan:
             indptr, indices, data, order, cptr = plan["_host"]
             plan["fblobs"] = torch.as_tensor(K.csr_pack_clusters_frag(indptr, indices, data, order, cptr, plan["max_rows"],
@@ -131,26 +117,21 @@ class CsrMatrix:
     def _matmat(self, B, out):
         m = B.shape[1]
         wide = K._ld(B) >= m + (m & 1)                      # the padding column of an odd width may be read
-        if self.plan is not None and m >= 96 and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
+        if self.plan is not None and m >= 96 and wide and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
+                self.plan["max_rows"] <= 16 and self.plan["max_cols_cap"] <= 48 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
             import os
             impl = self.impl
-            dmma_ok = wide and self.plan["max_rows"] <= 16 and self.plan["max_cols_cap"] <= 48
             if impl == "auto":
                 # measured on B200 (profiles/r01_spmm_variants.md): whole-row fragment-record kernel for wide blocks,
                 # double-buffered 64-column panels for narrow ones (a CTA's share is too small to amortise its latency chain)
-                impl = (os.environ.get("HFB_SPMM_WIDE", self.WIDE_DEFAULT) if m >= 192 else "dmma") if dmma_ok else "staged"
-            if impl in ("frag", "pipe") and dmma_ok:
+                impl = os.environ.get("HFB_SPMM_WIDE", self.WIDE_DEFAULT) if m >= 192 else "dmma"
+            if impl == "frag":
                 return K.csr_spmm_dmma_frag(self._frag_blobs(self.plan, self.device), B, out,
-                                            int(os.environ.get("HFB_SPMM_FRAG_W", 0)), pipelined=(impl == "pipe")), \
-                    ("csr_spmm_dmma_pipe_kernel" if impl == "pipe" else "csr_spmm_dmma_frag_kernel")
-            if impl == "dmma" and dmma_ok:
-                return K.csr_spmm_dmma(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_dmma_kernel"
-            if impl == "tma" and wide:
-                return K.csr_spmm_tma(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_tma_kernel"
-            if impl == "regblock" and wide and self.plan["max_rows"] <= 32:
-                return K.csr_spmm_regblock(self._tma_blobs(self.plan, self.device), B, out), "csr_spmm_regblock_kernel"
-            return K.csr_spmm_staged(self.plan, B, out), "csr_spmm_staged_kernel"
+                                            int(os.environ.get("HFB_SPMM_FRAG_W", 0))), "csr_spmm_dmma_frag_kernel"
+            if impl == "dmma":
+                return K.csr_spmm_dmma(self._panel_blobs(self.plan, self.device), B, out), "csr_spmm_dmma_kernel"
+            raise K.HfbError("unknown HFB_SPMM_IMPL '%s' (auto | frag | dmma)" % impl)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order), "csr_spmm_panel_kernel"
 
     def matmat_rows(self, X, out=None):
@@ -193,15 +174,33 @@ class SampleCovariance:
         self._W = None
         self.center = None
         self.center_ratio = None        # device scalar, set by the first ``project`` when a center is present
-        if center is not None:
+        # center="lazy": the sample mean is NOT known yet.  It is obtained for free from the first lift, which multiplies
+        # with [W | 1] instead of W (one more column inside the same GEMM tiles: X^T 1 = N * mean), and the first apply is
+        # centred afterwards through  (X - 1 c^T)^T (X - 1 c^T) B = X^T (X B) - c (1^T X B)  -- this removes the separate
+        # 8.6 GB column-sum sweep over the stored snapshots.  Round-off of that first apply grows like eps * |c|^2 / var
+        # (``center_ratio``), so callers redo it with a known center when the ratio is large (LAZY_MAX_RATIO).
+        self.lazy_center = False
+        self._lazy_B = None
+        if isinstance(center, str):
+            assert center == "lazy" and self.noise_cov_inv is None and self.block == 1
+            self.lazy_center = True
+        elif center is not None:
             assert self.noise_cov_inv is None and self.block == 1, "implicit centering is for snapshot rows"
             self.center = center.contiguous()
 
+    LAZY_MAX_RATIO = 1.0e3      # (|mean| / rms fluctuation)^2 above which the lazily centred first apply is redone
+
     def _wbuf(self, m):
         if self._W is None or self._W.shape[1] != m:
-            self._W = K.padded_empty(self.rows, m, self.Xt.device)
+            self._Wext = K.padded_empty(self.rows, m + 1, self.Xt.device)     # one spare column: the ones column of a lazy lift
+            self._Wext[:, m].fill_(1.0)
+            self._W = self._Wext[:, :m]
             self._W2 = K.padded_empty(self.rows, m, self.Xt.device) if self.noise_cov_inv is not None else None
         return self._W
+
+    def lazy_pending(self):
+        """True while the center of a lazily centred operator has not been determined yet."""
+        return self.lazy_center and self.center is None
 
     def project(self, B):
         """W (R, m) = Xt @ B  (and Gamma^-1 applied per sample block when present).  Returns (W, GW)
@@ -211,6 +210,9 @@ class SampleCovariance:
         if B.data_ptr() % 16 or K._ld(B) % 2:
             B = K.to_padded(B, B.device)      # e.g. one column of a multivector block: stage into a TMA-aligned buffer
         K.dgemm(K.HFB_NN, self.Xt, B, out=W)
+        if self.lazy_pending():
+            self._lazy_B = B                      # centring of this apply happens after the lift (finish_lazy)
+            return W, W
         if self.center is not None:
             sb = K.colsum(B, 1.0, weights=self.center)                                # c^T B  (m,), one sweep over B
             K.subtract_row_(W, sb)
@@ -227,6 +229,8 @@ class SampleCovariance:
     def apply(self, B, out=None, scale=None):
         """out (n, m) = scale * Xt^T G Xt B with scale = 1/nsamples by default (the local 'average'
         of SummedListOperator(average=True) / LowRankOperator(ones/N_loc))."""
+        if self.lazy_pending():            # a direct apply cannot carry the extra column: determine the mean the ordinary way
+            self.center = K.colsum(self.Xt, 1.0 / self.nsamples)
         _, GW = self.project(B)
         return self.lift(GW, out=out, scale=scale, weighted=True)
 
@@ -245,14 +249,48 @@ class SampleCovariance:
         if scale is None:
             scale = 1.0 / self.nsamples
         lo, hi = (0, self.n) if rows is None else rows
+        if self.lazy_pending():
+            # raw block scale * X^T [W | 1]: the extra column (scale * X^T 1 = local mean) lands in the padding of ``out``
+            m = GW.shape[1]
+            assert out is not None and K._ld(out) >= m + 1 and GW.data_ptr() == self._Wext.data_ptr()
+            ext = out.as_strided((out.shape[0], m + 1), (K._ld(out), 1))
+            K.dgemm(K.HFB_TN, self.Xt if rows is None else self.Xt[:, lo:hi], self._Wext, out=ext, alpha=scale)
+            return out
         out = K.dgemm(K.HFB_TN, self.Xt if rows is None else self.Xt[:, lo:hi], GW, out=out, alpha=scale)
         if self.center is not None:
             K.rank1_update_(out, -scale, self.center[lo:hi], K.colsum(GW, 1.0))       # - c (1^T W)
         return out
 
+    def can_lazy(self, Y, m):
+        """The lazy lift needs one spare column in the padding of the result block."""
+        return self.lazy_pending() and K._ld(Y) >= m + 1
+
+    def finish_lazy(self, Y, collective=None, mpi_op="avg"):
+        """After the (all-reduced) raw lift of a lazily centred operator: read the mean from the extra column of ``Y``,
+        apply the rank-one correction  Y -= c (1^T W / N)  and fix the center for all later products.  With a collective the
+        extra column has been averaged together with the block ('avg' over equal shards = global mean); the (m,) vector
+        1^T W / N is averaged here."""
+        m = self._W.shape[1]
+        ext = Y.as_strided((Y.shape[0], m + 1), (K._ld(Y), 1))
+        c = ext[:, m].contiguous()                                           # global mean of the stored rows
+        cw = K.colsum(self._W, 1.0 / self.nsamples)                          # 1^T W / N_loc
+        if collective is not None:
+            collective.allReduce(cw, mpi_op)
+        K.rank1_update_(Y, -1.0, c, cw)
+        self.center = c
+        # (|c| / rms |x_i - c|)^2 through this projection: sum |W - 1 sb^T|^2 = sum |W|^2 - 2 sb.(1^T W) + rows |sb|^2
+        sb = K.colsum(self._lazy_B, 1.0, weights=c)
+        ww = K.coldot(self._W, self._W).sum() - 2.0 * self.nsamples * torch.dot(sb, cw) + self.rows * torch.dot(sb, sb)
+        if collective is not None:
+            pass                                                             # local estimate; callers sum it over the ranks
+        self.center_ratio = self.rows * torch.dot(sb, sb) / torch.clamp_min(ww, 1e-300)
+        self._lazy_B = None
+        return c
+
     def gram_T(self, B, scale=None):
         """T_local (m, m) = scale * (Xt B)^T G (Xt B): the Rayleigh quotient B^T C B without forming C B
         (SURVEY.md 7 'T = Q^T A Q shortcut')."""
+        assert not self.lazy_pending(), "the Rayleigh quotient needs the center (apply the operator first)"
         W, GW = self.project(B)
         if scale is None:
             scale = 1.0 / self.nsamples
@@ -287,6 +325,16 @@ def sym_gram(Y, Z, alpha=1.0):
     return G
 
 
+_side_streams = {}
+
+
+def _side_stream(dev):
+    st = _side_streams.get(dev.index)
+    if st is None:
+        st = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def _device_chol_enabled():
     import os
     return os.environ.get("HFB_DEVICE_CHOL", "1") != "0"
@@ -310,9 +358,18 @@ def b_orthonormalize_device(Y, Bmat=None, return_BQ=True):
     else:
         Z1 = Q1
     G1 = sym_gram(Q1, Z1)
-    S2, stat2 = K.chol_inverse(G1, scale_columns=False)
+    # the clean-up factor is not needed before T1 exists: its one-CTA kernel runs on a side stream, on one SM, while the
+    # Rayleigh-quotient GEMM the caller queues next keeps the other 147 busy
+    main = torch.cuda.current_stream(Y.device)
+    side = _side_stream(Y.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        S2, stat2 = K.chol_inverse(G1, scale_columns=False)
+    for t in (S2, stat2):
+        t.record_stream(main)
+    G1.record_stream(side)
     info = {"passes": 1, "shifted": 0, "cond": [], "route": "device",
-            "pending": {"stat1": stat1, "stat2": stat2, "S2": S2, "sketch": Y}}
+            "pending": {"stat1": stat1, "stat2": stat2, "S2": S2, "sketch": Y, "side": side}}
     return Q1, (Z1 if return_BQ else None), info
 
 

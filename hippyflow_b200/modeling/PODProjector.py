@@ -136,7 +136,7 @@ class PODProjectorFromData:
 
     def construct_subspace(self, u_data, u_rank, shifted=True, method='hep', verify=False,
                            oversampling=10, Omega=None, collective=None, return_device=False, faithful=False,
-                           overwrite_data=False, pipelined_upload=True, implicit_shift=True):
+                           overwrite_data=False, pipelined_upload=True, implicit_shift=True, lazy_mean=True):
         """Same contract as PODProjector.py:699-852: returns (d, phi, Mphi, u_shift) as NumPy arrays of shape
         (r,), (n, r), (n, r), (n,).  ``u_data`` may be a NumPy array or a float64 CUDA tensor (rows = samples;
         with a collective, the local shard).  Extra keywords (randomized method only): ``oversampling``,
@@ -164,7 +164,14 @@ class PODProjectorFromData:
             self.shift_route = 'pipelined' if shifted else 'none'
         else:
             Xt = _as_device_rows(u_data, dev)
-            if shifted:
+            m_cols = u_rank + oversampling
+            if shifted and method == 'randomized' and implicit_shift and lazy_mean and m_cols % 16 != 0:
+                # the mean comes out of the range-finding pass itself (one extra column in the lift GEMM, see
+                # linalg.SampleCovariance): no separate sweep over the stored snapshots
+                center = "lazy"
+                u_shift_d = None
+                self.shift_route = 'implicit'
+            elif shifted:
                 # u_shift = mean over ALL samples (np.mean(u_data, axis=0), PODProjector.py:733), then X - shift
                 u_shift_d = K.colsum(Xt, 1.0 / n_data)
                 collective.allReduce(u_shift_d, 'avg')
@@ -182,6 +189,15 @@ class PODProjectorFromData:
         t1 = time.time()
         if method == 'randomized':
             d, phi_d, Mphi_d, ratio = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, center, pre)
+            if isinstance(center, str):
+                # lazily centred solve: the mean is known now; its first apply lost ~eps * ratio digits, so redo the solve
+                # with the known center when the mean is not small against the fluctuations
+                center = u_shift_d = self._last_cov.center
+                worst = ratio.reshape(1).clone()
+                collective.allReduce(worst, 'sum')
+                if float(worst) > SampleCovariance.LAZY_MAX_RATIO * collective.size():
+                    self.shift_route = 'implicit (lazy mean redone)'
+                    d, phi_d, Mphi_d, ratio = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, center, None)
             if ratio is not None:
                 worst = ratio.reshape(1).clone()
                 collective.allReduce(worst, 'sum')
@@ -345,6 +361,7 @@ class PODProjectorFromData:
         Omega = self._resolve_omega(Omega, n, m)
         assert Omega.nvec() >= u_rank
         cov = SampleCovariance(Xt, center=center)
+        self._last_cov = cov
         C = SampleCovarianceOperator(cov, collective, 'avg')
         A = SandwichedCovarianceOperator(C, Md)
         self.info = {}

@@ -52,9 +52,20 @@ class SampleCovarianceOperator:
         n = Yt.shape[0]
         scale = 1.0 / self.cov.nsamples
         size = self.collective.size()
+        lazy = self.cov.lazy_pending()
+        if lazy and (not self.cov.can_lazy(Yt, GW.shape[1]) or self.mpi_op.lower() != "avg"):
+            # no spare column in the result block: determine the mean the ordinary way first
+            c = K.colsum(self.cov.Xt, 1.0 / self.cov.nsamples)
+            self.collective.allReduce(c, "avg")
+            self.cov.center = c
+            W, GW = self.cov.project(self.cov._lazy_B)
+            self.cov._lazy_B = None
+            lazy = False
         if size == 1 or not hasattr(self.collective, "allReduce_async") or n < 4096:
             self.cov.lift(GW, out=Yt, scale=scale, weighted=True)
-            self.collective.allReduce(Y, self.mpi_op)
+            self.collective.allReduce(Y, self.mpi_op)       # reduces the whole padded block: the mean column travels along
+            if lazy:
+                self.cov.finish_lazy(Yt, self.collective if size > 1 else None, self.mpi_op)
             return
         if self.mpi_op.lower() == "avg":
             scale /= float(size)
@@ -69,6 +80,10 @@ class SampleCovarianceOperator:
             works.append(self.collective.allReduce_async(full[lo:hi], "sum"))
         for w in works:
             w.wait()
+        if lazy:
+            # the chunks carried scale / size and were summed: the extra column is the global mean already; 1^T W / N is
+            # averaged inside finish_lazy
+            self.cov.finish_lazy(Yt, self.collective, "avg")
 
     def mult(self, x, y):
         self.cov.apply(x.storage_tensor(), out=y.storage_tensor())

@@ -90,6 +90,8 @@ def _rayleigh_ritz(A, Q, BQ, k, oinfo, faithful):
     S2d = None
     if pending is not None:
         S2d = pending["S2"]
+        if pending.get("side") is not None:
+            torch.cuda.current_stream(dev).wait_stream(pending["side"])   # S2 was computed on a side stream
         if Td is None:
             Td = K.to_padded(np.ascontiguousarray(T), dev)
         Td = K.dgemm(K.HFB_TN, S2d, K.dgemm(K.HFB_NN, Td, S2d))          # S2^T T S2

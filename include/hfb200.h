@@ -118,71 +118,46 @@ int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t*
                  const double* val, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
 /* Same product with the rows visited in the order `order` (device int32 permutation of 0..nrows-1, from
- * hfb_csr_cluster_rows): a CTA then owns 64 mesh-neighbouring rows whose B rows overlap, so most B reads hit in L1. */
+ * hfb_csr_cluster_rows_capped): a CTA then owns 64 mesh-neighbouring rows whose B rows overlap, so most B reads hit in L1.
+ * Used for narrow blocks (m < 96) and for matrices whose rows are too dense for the cluster kernels below. */
 int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind, const double* val,
                          const int32_t* order, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
-/* HOST function (host pointers, no CUDA call): greedy breadth-first clustering of the rows of a CSR matrix with
- * symmetric pattern into groups of `cluster` neighbouring rows; writes a permutation of 0..n-1. O(nnz). */
-int hfb_csr_cluster_rows(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t cluster, int32_t* order_out);
 
-/* Cluster-staged SpMM (round-1 baseline of the cluster kernels; the default is hfb_csr_spmm_dmma_frag below): HOST preprocessing hfb_csr_cluster_rows_capped groups the rows into clusters of
- * <= max_rows rows touching <= max_cols distinct columns; the caller then builds, in cluster order, the row offsets
- * s_rowptr, the 16-byte entries {value, cluster-LOCAL column index} and the per-cluster distinct-column lists
- * (cl_colptr, cl_cols) -- see hippyflow_b200/linalg.py:CsrMatrix._build_plan.  The kernel stages each cluster's distinct
- * B rows in shared memory once (cp.async) and reads them with LDS.128.  B, C: 16-byte aligned, even ld. */
+/* HOST function (host pointers, no CUDA call): greedy breadth-first clustering of the rows of a CSR matrix with symmetric
+ * pattern into clusters of <= max_rows graph-neighbouring rows touching <= max_cols DISTINCT columns; writes a permutation
+ * of 0..n-1 (order_out), the slot boundaries of the clusters (cluster_ptr_out, n+1 entries allocated by the caller) and
+ * their number.  O(nnz).  One-time preprocessing per matrix (hippyflow_b200/linalg.py:CsrMatrix._build_plan). */
 int hfb_csr_cluster_rows_capped(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t max_rows, int32_t max_cols,
                                 int32_t* order_out, int32_t* cluster_ptr_out, int64_t* nclusters_out);
-int hfb_csr_spmm_staged(int64_t nclusters, int64_t m, const int32_t* cl_rowptr, const int32_t* order,
-                        const int32_t* s_rowptr, const void* entries /* {double value; int64 local column} per nnz */,
-                        const int32_t* cl_colptr, const int32_t* cl_cols, int32_t max_cols, int32_t max_entries,
-                        const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
-/* Persistent TMA-fed SpMM (evaluated alternative, HFB_SPMM_IMPL=tma).  HOST preprocessing hfb_csr_pack_clusters packs the clusters of
- * hfb_csr_cluster_rows_capped into fixed-stride blobs (layout in hippyflow_b200/csrc/spmm_tma.cu; stride from
- * hfb_csr_cluster_blob_stride; max_entries = largest number of matrix entries in one cluster); the caller uploads the
- * blob buffer.  One CTA per SM; a producer warp moves every blob and every distinct B row of a (cluster, column chunk)
- * work item with cp.async.bulk into an mbarrier-guarded shared-memory ring, consumer warps do LDS.128 + DFMA.
- * B, C, blobs: 16-byte aligned; ldb, ldc even; ldb >= m rounded up to even. */
+/* Cluster-dense DMMA SpMM, panel form (default for 96 <= m < 192).  HOST preprocessing hfb_csr_pack_clusters packs the
+ * clusters of hfb_csr_cluster_rows_capped into fixed-stride records (layout in hippyflow_b200/csrc/spmm_blob.cuh; stride from
+ * hfb_csr_cluster_blob_stride; max_entries = largest number of matrix entries in one cluster; max_rows <= 16, max_cols <= 48
+ * for this kernel); the caller uploads the buffer.  One CTA per cluster: the cluster's entries become a dense
+ * [rows][distinct columns] block whose DMMA A-fragments stay in registers; the distinct B rows are staged panel by panel into
+ * shared memory with cp.async (double-buffered) and multiplied as DMMA.8x8x4 tiles, so every staged B element is read from
+ * shared memory once and the matrix never is.  B, C, blobs: 16-byte aligned; ldb, ldc even; ldb >= m rounded up to even. */
 int64_t hfb_csr_cluster_blob_stride(int32_t max_rows, int32_t max_cols, int32_t max_entries);
 int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int32_t* colind, const double* val, const int32_t* order,
                           const int32_t* cluster_ptr, int64_t nclusters, int32_t max_rows, int32_t max_cols,
                           int32_t max_entries, void* blobs_out /* HOST, nclusters * stride bytes */);
-int hfb_csr_spmm_tma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols, int32_t max_entries,
-                     const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
-
-/* Register-blocked SpMM over the same blobs (max_rows <= 32).  One CTA per cluster, warp w owns the 64-column panel w of
- * the result: the cluster's entries are scattered into a dense [distinct columns][rows] block in shared memory, every
- * distinct B row is loaded once per cluster straight from global memory into registers (coalesced LDG.128, software ring),
- * and all rows of the cluster accumulate in registers from broadcast LDS.128 of the dense block -- B is never staged in
- * shared memory.  B, C, blobs: 16-byte aligned; ldb, ldc even. */
-int hfb_csr_spmm_regblock(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
-                          int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
-
-/* Cluster-dense DMMA SpMM over the same blobs (max_rows <= 16, max_cols <= 48).  One CTA per cluster: the cluster's entries
- * become a dense [rows][distinct columns] block whose DMMA A-fragments stay in registers; the distinct B rows are staged
- * panel by panel into shared memory with cp.async (double-buffered) and multiplied as DMMA.8x8x4 tiles, so every staged B
- * element is read from shared memory once and the matrix never is.  B, C, blobs: 16-byte aligned; ldb, ldc even;
- * ldb >= m rounded up to even. */
 int hfb_csr_spmm_dmma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                       int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
-/* The same product from "fragment blobs": HOST preprocessing hfb_csr_pack_clusters_frag stores each cluster's dense block
- * already in DMMA A-fragment order together with its nonzero-block masks, distinct columns and result rows (fixed stride
- * hfb_csr_frag_blob_stride; max_rows <= 16, max_cols <= 48).  The kernel needs no record staging or dense-block build:
- * it requests the whole chunk (chunk_cols columns, 0 = whole rows up to 320 columns) of every distinct B row with cp.async
- * right after reading the column list, keeps the accumulators of all its column groups in registers with the k-steps as
- * the outer loop, and starts the DMMAs of k-steps 2i, 2i+1 when rows 8i..8i+7 have landed.  256-bit result stores when C
- * rows are 32-byte aligned.  B, C, blobs: 16-byte aligned; ldb, ldc even; ldb >= m rounded up to even. */
+/* The same product from "fragment records" (default for m >= 192): HOST preprocessing hfb_csr_pack_clusters_frag stores each
+ * cluster's dense block already in DMMA A-fragment order together with its nonzero-block masks, distinct columns and result
+ * rows (fixed stride hfb_csr_frag_blob_stride; max_rows <= 16, max_cols <= 48).  The kernel needs no record staging or
+ * dense-block build: it requests the whole chunk (chunk_cols columns, 0 = whole rows up to 320 columns) of every distinct B
+ * row with cp.async right after reading the column list, keeps the accumulators of all its column groups in registers with
+ * the k-steps as the outer loop, and starts the DMMAs of k-steps 2i, 2i+1 when rows 8i..8i+7 have landed.  256-bit result
+ * stores when C rows are 32-byte aligned.  B, C, blobs: 16-byte aligned; ldb, ldc even; ldb >= m rounded up to even.
+ * (Five further variants were measured and retired -- profiles/r01_spmm_variants.md, sources under
+ * tools/experiments/spmm_variants/.) */
 int64_t hfb_csr_frag_blob_stride(int32_t max_rows, int32_t max_cols);
 int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, const int32_t* colind, const double* val, const int32_t* order,
                                const int32_t* cluster_ptr, int64_t nclusters, int32_t max_rows, int32_t max_cols,
                                void* blobs_out /* HOST, nclusters * stride bytes */);
 int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
-                           int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
-/* Cluster-pipelined form of the same kernel: only the resident CTAs are launched and each walks clusters blockIdx.x,
- * blockIdx.x + gridDim.x, ... with two row buffers, so the row copies, fragment loads and column list of the next clusters
- * overlap the DMMAs of the current one inside the CTA.  Same arguments and results (bitwise) as hfb_csr_spmm_dmma_frag. */
-int hfb_csr_spmm_dmma_pipe(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                            int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
 /*

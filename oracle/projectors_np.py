@@ -332,17 +332,17 @@ def project_data(data, encoder):
 
 def jstar_phi(J, MPhi):
     """JstarPhi_i = J_i^T (M Phi), stacked (N, dM, rQ)  (dataGenerator.py:170,339,582)."""
-    return np.einsum("iqm,qr->imr", J, MPhi)
+    return np.matmul(np.swapaxes(J, 1, 2), MPhi)                   # (N, dM, dQ) @ (dQ, rQ): BLAS, not a naive einsum loop
 
 
 def j_psi(J, Psi):
     """JPsi_i = J_i Psi, stacked (N, dQ, rM)  (dataGenerator.py:177,585)."""
-    return np.einsum("iqm,mr->iqr", J, Psi)
+    return np.matmul(J, Psi)
 
 
 def reduced_jacobians(J, PhiEnc, V):
     """Phi_enc^T J_i V, stacked (N, rQ, rM) (north star: 'Phi^T J V over all samples')."""
-    return np.einsum("qa,iqm,mb->iab", PhiEnc, J, V)
+    return np.matmul(PhiEnc.T, np.matmul(J, V))                    # Phi^T (J_i V) per sample
 
 
 # ----------------------------------------------------------------------------- comparison metrics

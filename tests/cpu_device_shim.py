@@ -49,37 +49,8 @@ def _scipy_csr(rowptr, colind, val, ncols=None):
     return sp.csr_matrix((v, ci, rp), shape=(n, ncols if ncols is not None else n))
 
 
-def _decode_blobs(K, plan):
-    """Rebuild the sparse matrix from the TMA kernel's per-cluster blobs (checks the packing the kernel will read)."""
-    mr, mc, me = plan["max_rows"], plan["max_cols_cap"], plan["max_entries"]
-    stride = int(K.lib().hfb_csr_cluster_blob_stride(mr, mc, me))
-    blobs = plan["blobs"].numpy().reshape(-1, stride)
-    r4 = lambda x: (x + 3) // 4 * 4
-    off_rowoff = 16
-    off_outrow = off_rowoff + 4 * r4(mr + 1)
-    off_cols = off_outrow + 4 * r4(mr)
-    off_ent = off_cols + 4 * r4(mc)
-    rows, cols, vals = [], [], []
-    nmax = 0
-    for b in blobs:
-        nrow, ncol, nent = (int(x) for x in b[:12].view(np.int32))
-        ro = b[off_rowoff:off_rowoff + 4 * (nrow + 1)].view(np.int32)
-        orow = b[off_outrow:off_outrow + 4 * nrow].view(np.int32)
-        cl = b[off_cols:off_cols + 4 * ncol].view(np.int32)
-        e = b[off_ent:off_ent + 16 * nent].reshape(-1, 16)
-        v = e[:, :8].copy().view(np.float64).ravel()
-        l = e[:, 8:12].copy().view(np.int32).ravel()
-        cnt = np.diff(ro)
-        rows.append(np.repeat(orow, cnt))
-        cols.append(cl[l])
-        vals.append(v)
-        nmax = max(nmax, int(orow.max()) + 1)
-    n = plan["order"].numel()
-    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
-
-
-def _decode_blobs_regblock(K, plan):
-    """Rebuild the matrix the way csr_spmm_regblock_kernel reads the blobs: (local column, local ROW) fields of every
+def _decode_panel_blobs(K, plan):
+    """Rebuild the matrix the way csr_spmm_dmma_kernel reads its records: (local column, local ROW) fields of every
     entry scattered into a dense per-cluster block -- the row offsets are not consulted."""
     mr, mc, me = plan["max_rows"], plan["max_cols_cap"], plan["max_entries"]
     stride = int(K.lib().hfb_csr_cluster_blob_stride(mr, mc, me))
@@ -133,24 +104,6 @@ def decode_frag_blobs(K, fblobs, max_rows, max_cols, n):
         rr, jj = np.nonzero(D)
         rows.append(orow[rr]); cols.append(cl[jj]); vals.append(D[rr, jj])
     return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
-
-
-def _decode_staged(plan):
-    order = plan["order"].numpy().astype(np.int64)
-    s_rowptr = plan["s_rowptr"].numpy().astype(np.int64)
-    ent = plan["entries"].numpy()
-    vals = ent[:, 0]
-    lcol = ent[:, 1].copy().view(np.int64)
-    cl_rowptr = plan["cl_rowptr"].numpy().astype(np.int64)
-    cl_colptr = plan["cl_colptr"].numpy().astype(np.int64)
-    cl_cols = plan["cl_cols"].numpy().astype(np.int64)
-    n = order.size
-    counts = np.diff(s_rowptr)
-    rows = np.repeat(order, counts)
-    cl_of_slot = np.repeat(np.arange(cl_rowptr.size - 1), np.diff(cl_rowptr))
-    cl_of_nnz = np.repeat(cl_of_slot, counts)
-    cols = cl_cols[cl_colptr[cl_of_nnz] + lcol]
-    return sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
 
 
 @contextlib.contextmanager
@@ -214,28 +167,13 @@ def emulated_device():
     def csr_spmm(rowptr, colind, val, B, out=None, order=None):
         return _spmm(_scipy_csr(rowptr, colind, val, B.shape[0]), B, out)
 
-    def csr_spmm_staged(plan, B, out=None):
-        key = ("staged", id(plan))
-        if key not in cache:
-            cache[key] = _decode_staged(plan)
-        return _spmm(cache[key], B, out)
-
-    def csr_spmm_tma(plan, B, out=None):
-        key = ("tma", id(plan))
-        if key not in cache:
-            cache[key] = _decode_blobs(K, plan)
-        return _spmm(cache[key], B, out)
-
-    def csr_spmm_regblock(plan, B, out=None):
-        key = ("regblock", id(plan))
-        if key not in cache:
-            cache[key] = _decode_blobs_regblock(K, plan)
-        return _spmm(cache[key], B, out)
-
     def csr_spmm_dmma(plan, B, out=None):
-        return csr_spmm_regblock(plan, B, out)     # reads the same fields of the same records
+        key = ("dmma", id(plan))
+        if key not in cache:
+            cache[key] = _decode_panel_blobs(K, plan)
+        return _spmm(cache[key], B, out)
 
-    def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0, pipelined=False):
+    def csr_spmm_dmma_frag(plan, B, out=None, chunk_cols=0):
         key = ("frag", id(plan))
         if key not in cache:
             cache[key] = decode_frag_blobs(K, plan["fblobs"].numpy(), plan["max_rows"], plan["max_cols_cap"], plan["order"].numel())
@@ -306,8 +244,7 @@ def emulated_device():
         k.pop("pin_memory", None)
         return saved_empty(*a, **k)
 
-    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_staged=csr_spmm_staged,
-                   csr_spmm_tma=csr_spmm_tma, csr_spmm_regblock=csr_spmm_regblock, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
+    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
                    colsum=colsum, subtract_row_=subtract_row_, rank1_update_=rank1_update_, axpby_=axpby_,
                    axpby_cols_=axpby_cols_, rowscale=rowscale, fill_random_=fill_random_,
                    measure_dmma_peak=lambda device: 1.0, launch_count=lambda: counter["n"],

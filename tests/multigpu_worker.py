@@ -40,7 +40,7 @@ def sharded_mean_shift_case(hf, dev, coll, rank, world):
     for entry in ("host", "resident"):
         data = shard.copy() if entry == "host" else K.to_padded(shard, dev)
         d, phi, Mphi, shift = proj.construct_subspace(data, 24, shifted=True, method="randomized", Omega=Om, collective=coll)
-        assert proj.shift_route == ("pipelined" if entry == "host" else "implicit")
+        assert proj.shift_route.startswith("pipelined" if entry == "host" else "implicit")   # "implicit (lazy mean redone)" when the mean is large
         np.testing.assert_allclose(d, d0, rtol=1e-10)
         from oracle import projectors_np as P
         assert P.principal_angle(phi[:, :k], U0[:, :k], M) < 1e-8

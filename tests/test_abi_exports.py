@@ -45,7 +45,7 @@ def test_argument_validation_without_gpu():
     assert L.hfb_dgemm(0, 4, 4, 4, 1.0, 24, 4, 32, 4, 64, 4, None, 0, 0, None) == -2   # misaligned A
     assert L.hfb_csr_spmm(0, 4, None, None, None, None, 4, None, 4, None) == -1
     # the cluster SpMM entry points: null pointers, caps beyond the kernels' budgets, misaligned / too narrow operands
-    for fn in (L.hfb_csr_spmm_dmma_frag, L.hfb_csr_spmm_dmma_pipe):
+    for fn in (L.hfb_csr_spmm_dmma_frag,):
         assert fn(10, 266, None, 16, 32, 0, 16, 272, 32, 272, None) == -1                 # no records
         assert fn(10, 266, 64, 16, 32, 0, 16, 272, 16, 272, None) == -1                   # B == C
         assert fn(10, 266, 64, 16, 32, 0, 16, 272, 32, 200, None) == -1                   # ldc < m
@@ -54,9 +54,20 @@ def test_argument_validation_without_gpu():
         assert fn(10, 266, 64, 16, 32, 0, 16, 273, 32, 272, None) == -2                   # odd ldb
         assert fn(10, 266, 64, 32, 64, 0, 16, 272, 32, 272, None) == -5                   # clusters too large for the A fragments
     assert L.hfb_csr_spmm_dmma(10, 266, 64, 32, 64, 200, 16, 272, 32, 272, None) == -5
-    assert L.hfb_csr_spmm_regblock(10, 266, 64, 64, 128, 500, 16, 272, 32, 272, None) == -5
     assert L.hfb_csr_frag_blob_stride(16, 32) == 4352 and L.hfb_csr_frag_blob_stride(8, 24) == 1792
     assert L.hfb_csr_frag_blob_stride(17, 32) < 0 and L.hfb_csr_frag_blob_stride(16, 49) < 0
+    # round-2 entry points: strided-batch GEMM, device Cholesky-QR factor, batched Jacobi SVD
+    assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 16, 32, 4, 16, 64, 4, 8, 3, 0, 0, None, 0, None) == -1      # outputs overlap
+    assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 15, 32, 4, 16, 64, 4, 16, 3, 0, 0, None, 0, None) == -2     # odd batch stride
+    assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 16, 32, 4, 16, 64, 4, 16, 3, 7, 0, None, 0, None) == -1     # unknown mode
+    assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 16, 32, 4, 16, 64, 4, 16, 3, 0, 1, None, 0, None) == -5     # symmetric flag
+    assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 0, 32, 4, 0, 64, 4, 0, 3, 1, 0, None, 0, None) == -1        # reduce over shared operands
+    assert L.hfb_chol_inverse(2000, 16, 2000, 32, 2000, 64, 1, None, 0, None) == -5                                 # m > 1024
+    assert L.hfb_chol_inverse(8, 16, 4, 32, 8, 64, 1, None, 0, None) == -1                                          # ldg < m
+    assert L.hfb_chol_inverse(8, 16, 8, 32, 8, 64, 1, None, 0, None) == -3                                          # no workspace
+    assert L.hfb_chol_inverse_workspace_bytes(266) == 2 * 266 * 266 * 8 and L.hfb_chol_inverse_workspace_bytes(5000) == 0
+    assert L.hfb_jacobi_svd_batched(400, 400, 16, 400, 160000, 2, 32, 400, 64, 30, 0, None) == -5                   # does not fit shared memory
+    assert L.hfb_jacobi_svd_batched(10, 4, 16, 2, 40, 2, 32, 4, 64, 30, 0, None) == -1                              # lda < cols
     assert L.hfb_dgemm_workspace_bytes(0, 128, 16, 4096, 4) == 4 * 128 * 16 * 8
     assert L.hfb_dgemm_auto_splits(0, 4096, 266, 263169) >= 2
 

@@ -115,10 +115,10 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag", "pipe"])
+@pytest.mark.parametrize("impl", ["dmma", "frag"])
 @pytest.mark.parametrize("m", [96, 137, 138, 266, 300, 511, 1100])
 def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
-    """The cluster-plan kernels (persistent TMA ring / cp.async panels / register-blocked) on a mesh matrix large enough to get a
+    """The cluster-plan kernels (panel records / fragment records) on a mesh matrix large enough to get a
     plan (n >= 4096), odd and even widths, widths that need 1..4 column chunks; padding columns stay untouched."""
     from hippyflow_b200 import synthetic as syn
     from hippyflow_b200.linalg import CsrMatrix
@@ -139,44 +139,16 @@ def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     assert torch.equal(again, out)                 # fixed summation order: bitwise reproducible
 
 
-@pytest.mark.parametrize("caps", [(8, 20), (12, 24), (16, 32), (24, 48), (32, 64), (5, 20)])
-@pytest.mark.parametrize("m", [10, 74, 96, 138, 266, 267, 600])
-def test_csr_spmm_regblock_cluster_caps(K, cuda_device, caps, m):
-    """Every register-block instantiation (R = 8, 12, 16, 24, 32) and both lane maps (full 64-column panels, narrow tail
-    panels that fold several row groups into one warp) against SciPy; padding columns stay untouched."""
-    from hippyflow_b200 import synthetic as syn
-    from hippyflow_b200.linalg import CsrMatrix
-    M = syn.p1_mass_matrix(41, 37).tocsr()
-    n = M.shape[0]
-    Md = CsrMatrix(M, cuda_device, cluster_rows=False)
-    plan = CsrMatrix._tma_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
-    B = np.random.default_rng(m).standard_normal((n, m))
-    out = K.padded_empty(n, m, cuda_device)
-    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
-    full.fill_(7.0)
-    K.csr_spmm_regblock(plan, K.to_padded(B, cuda_device), out)
-    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
-    if K._ld(out) > m:
-        assert bool((full[:, m:] == 7.0).all())
-    assert torch.equal(K.csr_spmm_regblock(plan, K.to_padded(B, cuda_device)), out)       # bitwise reproducible
-    del Md
-
-
-@pytest.mark.parametrize("mode", ["panel64", "panel128", "slab64", "slab144", "slabfull"])
+@pytest.mark.parametrize("mode", ["panel64", "panel128"])
 @pytest.mark.parametrize("caps", [(8, 16), (8, 20), (8, 32), (8, 40), (12, 24), (16, 24), (16, 32), (16, 48), (5, 20)])
 @pytest.mark.parametrize("m", [10, 74, 138, 266, 267, 600])
 def test_csr_spmm_dmma_cluster_caps(K, cuda_device, caps, m, mode, monkeypatch):
     """Every instantiation of the cluster-dense DMMA kernel (1 or 2 row halves, 4..12 k-steps; double-buffered 64- and
-    128-column panels, and the row-slab staging with one or several column chunks) against SciPy: narrow blocks, partial
+    128-column panels) against SciPy: narrow blocks, partial
     last panels / chunks, odd widths; padding columns stay untouched; run-to-run bitwise equal."""
     from hippyflow_b200 import synthetic as syn
     from hippyflow_b200.linalg import CsrMatrix
-    monkeypatch.delenv("HFB_SPMM_DMMA_W", raising=False)
-    monkeypatch.delenv("HFB_SPMM_DMMA_NT", raising=False)
-    if mode.startswith("panel"):
-        monkeypatch.setenv("HFB_SPMM_DMMA_NT", "2" if mode == "panel128" else "1")
-    else:
-        monkeypatch.setenv("HFB_SPMM_DMMA_W", {"slab64": "64", "slab144": "144", "slabfull": "100000"}[mode])
+    monkeypatch.setenv("HFB_SPMM_DMMA_NT", "2" if mode == "panel128" else "1")
     M = syn.p1_mass_matrix(41, 37).tocsr()
     n = M.shape[0]
     plan = CsrMatrix._tma_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
@@ -191,29 +163,26 @@ def test_csr_spmm_dmma_cluster_caps(K, cuda_device, caps, m, mode, monkeypatch):
     assert torch.equal(K.csr_spmm_dmma(plan, K.to_padded(B, cuda_device)), out)
 
 
-@pytest.mark.parametrize("pipelined", [False, True])
 @pytest.mark.parametrize("chunk", [0, 64, 144])
 @pytest.mark.parametrize("caps", [(8, 16), (8, 24), (8, 32), (8, 40), (12, 24), (16, 24), (16, 32), (16, 48), (5, 20)])
 @pytest.mark.parametrize("m", [10, 74, 138, 266, 267, 330, 600])
-def test_csr_spmm_dmma_frag_cluster_caps(K, cuda_device, caps, m, chunk, pipelined):
+def test_csr_spmm_dmma_frag_cluster_caps(K, cuda_device, caps, m, chunk):
     """Fragment-record DMMA kernel: every (row halves, k-steps) instantiation, whole-row and chunked staging, widths that
     need 1..5 column groups per warp and several chunks, odd widths; padding untouched; bitwise reproducible."""
     from hippyflow_b200 import synthetic as syn
     from hippyflow_b200.linalg import CsrMatrix
-    # the pipelined kernel launches resident CTAs only: the larger mesh gives every CTA 2-4 clusters to walk
-    M = (syn.p1_mass_matrix(90, 80) if pipelined else syn.p1_mass_matrix(41, 37)).tocsr()
+    M = syn.p1_mass_matrix(41, 37).tocsr()
     n = M.shape[0]
     plan = CsrMatrix._frag_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
     B = np.random.default_rng(m).standard_normal((n, m))
     out = K.padded_empty(n, m, cuda_device)
     full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
     full.fill_(7.0)
-    K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), out, chunk_cols=chunk, pipelined=pipelined)
+    K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), out, chunk_cols=chunk)
     np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
     if K._ld(out) > m:
         assert bool((full[:, m:] == 7.0).all())
-    # the per-cluster and the cluster-pipelined kernel add in the same order: bitwise equal, run to run and to each other
-    assert torch.equal(K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), chunk_cols=chunk, pipelined=not pipelined), out)
+    assert torch.equal(K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), chunk_cols=chunk), out)     # bitwise reproducible
 
 
 def test_csr_spmm_dmma_frag_irregular_and_unaligned_rows(K, cuda_device):
@@ -263,7 +232,7 @@ def test_csr_spmm_dmma_irregular_matrix_and_limits(K, cuda_device):
         K.csr_spmm_dmma(big, K.to_padded(B, cuda_device))
 
 
-@pytest.mark.parametrize("impl", ["tma", "staged", "regblock", "dmma", "frag", "pipe"])
+@pytest.mark.parametrize("impl", ["dmma", "frag", "auto"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
     import scipy.sparse as sp

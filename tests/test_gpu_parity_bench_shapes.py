@@ -62,7 +62,7 @@ def test_cfg2_shape_weighted_pod_vs_blocked_oracle(hf, cuda_device, cfg2_case, e
     proj = hf.PODProjectorFromData(None, M_output=c["M"], device=cuda_device)
     data = c["u"] if entry == "host_pipelined" else K.to_padded(c["u"], cuda_device)
     d, phi, Mphi, shift = proj.construct_subspace(data, c["rank"], shifted=True, method="randomized", Omega=c["Om"])
-    assert proj.shift_route == ("pipelined" if entry == "host_pipelined" else "implicit")
+    assert proj.shift_route.startswith("pipelined" if entry == "host_pipelined" else "implicit")
     assert proj.info["passes"] >= 1
     k = check_eigs(d, c["d0"])
     assert k >= 200                                                           # the comparison covers (nearly) the whole basis

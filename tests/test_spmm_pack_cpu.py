@@ -1,5 +1,5 @@
 """Host preprocessing of the cluster SpMM kernels (no GPU): hfb_csr_cluster_rows_capped + hfb_csr_pack_clusters must
-describe exactly the matrix they were given.  The packed records are decoded here the way csr_spmm_regblock_kernel
+describe exactly the matrix they were given.  The packed records are decoded here the way csr_spmm_dmma_kernel
 decodes them (dense [distinct column][cluster row] block per cluster) and the matrix is rebuilt bit-exactly."""
 import numpy as np
 import pytest
@@ -43,7 +43,7 @@ def _decode(M, max_rows, max_cols):
         v = ent.view(np.float64)[0::2]
         lr = ent.view(np.int32).reshape(-1, 4)[:, 2:]
         assert rowoff[0] == 0 and rowoff[nrow] == nent
-        # the local row field agrees with the row offsets (the TMA kernel reads the offsets, regblock the field)
+        # the local row field agrees with the row offsets
         assert np.array_equal(lr[:, 1], np.repeat(np.arange(nrow), np.diff(rowoff)))
         D = np.zeros((max_cols, mr))
         D[lr[:, 0], lr[:, 1]] = v

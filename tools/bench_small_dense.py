@@ -13,6 +13,7 @@ import hippyflow_b200 as hf
 from hippyflow_b200 import _lib as K
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+only = sys.argv[2] if len(sys.argv) > 2 else "all"          # "chol": just the Cholesky-QR factor timings
 dev = torch.device("cuda:0")
 res = {}
 
@@ -38,6 +39,10 @@ for m in (138, 210, 266, 522, 1024):
     G = K.to_padded(Y.t() @ Y, dev)
     res["chol_inverse_m%d_ms" % m] = timed(lambda: K.chol_inverse(G), n=10)
     print("chol_inverse m=%d: %.3f ms" % (m, res["chol_inverse_m%d_ms" % m]), flush=True)
+
+if only == "chol":
+    json.dump(res, open("gpurun_out/%s_small_dense_chol.json" % tag, "w"), indent=1)
+    sys.exit(0)
 
 # ---- batched Jacobi SVD
 for (batch, rows, cols) in ((592, 100, 60), (592, 100, 110), (296, 200, 138), (592, 138, 138)):
