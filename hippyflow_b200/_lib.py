@@ -78,6 +78,7 @@ def lib():
         "hfb_measure_dmma_peak": (i32, [vp, sz, ctypes.POINTER(ctypes.c_double), vp]),
         "hfb_chol_inverse_workspace_bytes": (sz, [i64]),
         "hfb_chol_inverse": (i32, [i64, vp, i64, vp, i64, vp, i32, vp, sz, vp]),
+        "hfb_chol_inverse_profile": (i32, [i64, vp, i64, vp, i64, vp, i32, vp, sz, vp, vp]),
         "hfb_jacobi_svd_max_elems": (i64, []),
         "hfb_jacobi_svd_batched": (i32, [i64, i64, vp, i64, i64, i64, vp, i64, vp, i32, i32, vp]),
         "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
@@ -100,7 +101,8 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
-            "hfb_measure_dmma_peak", "hfb_chol_inverse_workspace_bytes", "hfb_chol_inverse", "hfb_jacobi_svd_max_elems",
+            "hfb_measure_dmma_peak", "hfb_chol_inverse_workspace_bytes", "hfb_chol_inverse", "hfb_chol_inverse_profile",
+            "hfb_jacobi_svd_max_elems",
             "hfb_jacobi_svd_batched"]
 
 
@@ -171,7 +173,7 @@ def to_padded(a, device, pad=16):
     return out
 
 
-def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumulate=False):
+def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumulate=False, b_upper=False):
     """out[M,N] = alpha * op(A) op(B) on the DMMA/TMA kernel.  layout: HFB_NN (A MxK, B KxN),
     HFB_TN (A KxM), HFB_NT (B NxK).  symmetric=True: the caller asserts a symmetric result (Gram matrix); only the
     tiles on or above the diagonal are computed, the rest is mirrored."""
@@ -201,6 +203,11 @@ def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumula
         if fresh_out or flags:
             raise HfbError("dgemm: accumulate needs an existing out and is not combinable with symmetric")
         flags |= 2
+    if b_upper:                     # B is the upper-triangular factor S of Cholesky-QR: skip the zero k-blocks (TRMM)
+        if K != N or layout == HFB_NT:
+            raise HfbError("dgemm: b_upper needs a square K x N operand B (NN / TN layouts)")
+        flags |= 4
+        splits = 1
     nbytes = L.hfb_dgemm_ex_workspace_bytes(layout, M, N, K, splits, flags)
     ws = workspace(nbytes, A.device) if nbytes else None
     if TIMING is not None:
@@ -543,6 +550,21 @@ def measure_dmma_peak(device):
 
 
 CHOL_INVERSE_MAX = 1024
+
+
+def chol_inverse_profile(G, scale_columns=True):
+    """Debug aid: per-section clock cycles of one hfb_chol_inverse launch (NumPy int64[11], see include/hfb200.h)."""
+    L = lib()
+    _req(G, "G")
+    m = G.shape[0]
+    S = padded_empty(m, m, G.device)
+    stat = torch.empty(8, dtype=torch.float64, device=G.device)
+    prof = torch.zeros(16, dtype=torch.int64, device=G.device)
+    ws = torch.empty(L.hfb_chol_inverse_workspace_bytes(m), dtype=torch.uint8, device=G.device)
+    rc = L.hfb_chol_inverse_profile(m, G.data_ptr(), _ld(G), S.data_ptr(), _ld(S), stat.data_ptr(), 1 if scale_columns else 0,
+                                    ws.data_ptr(), ws.numel(), prof.data_ptr(), _stream())
+    _check(rc, "hfb_chol_inverse_profile")
+    return prof.cpu().numpy()[:11]
 
 
 def chol_inverse(G, scale_columns=True):

@@ -192,6 +192,8 @@ static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, double alpha, 
                      int mode, void* workspace, size_t workspace_bytes, int splits, int flags, cudaStream_t stream) {
     const int symmetric = ((flags & HFB_GEMM_SYMMETRIC) && M == N) ? 1 : 0;
     const int accumulate = (flags & HFB_GEMM_ACCUMULATE) ? 1 : 0;
+    const int b_upper = (flags & HFB_GEMM_B_UPPER) ? 1 : 0;
+    if (b_upper && (layout == HFB_NT || K != N || batch > 1)) return HFB_E_BADARG;
     if ((flags & HFB_GEMM_SYMMETRIC) && M != N) return HFB_E_BADARG;
     if (symmetric && accumulate) return HFB_E_UNSUPPORTED;  // the mirror pass would overwrite the accumulated half
     if (layout < 0 || layout > 2 || M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || splits < 0 || batch < 1) return HFB_E_BADARG;
@@ -254,6 +256,7 @@ static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, double alpha, 
     p.vec_store = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & 1) == 0 && (p.strideC & 1) == 0) ? 1 : 0;
     p.symmetric = symmetric;
     p.accumulate = accumulate;
+    p.b_upper = b_upper;
     if ((long long)p.m_tiles * p.n_tiles * p.splits * nbat > 0x7fffffffLL) return HFB_E_BADARG;
 
     CUtensorMap mapA, mapB;

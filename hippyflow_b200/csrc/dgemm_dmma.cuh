@@ -51,6 +51,7 @@ struct GemmParams {
     int kb_per;            // k-blocks per sample; kb_total = kb_per * kfold
     int a_batched, b_batched;  // operand has a sample axis (third coordinate = sample) or is shared (third coordinate 0)
     long long strideC;     // elements between consecutive C_b
+    int b_upper;           // 1: B (K x N, NN/TN layouts) is upper triangular: k-blocks past the tile's last column are skipped
 };
 
 template <int LAYOUT, int NT>
@@ -95,9 +96,13 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int bat = bid / p.splits;  // sample of an independent-output batch (0 for a plain GEMM)
     const int kb_base = p.kb_total / p.splits, kb_rem = p.kb_total % p.splits;
     const int kb_begin = split * kb_base + (split < kb_rem ? split : kb_rem);
-    const int kb_count = kb_base + (split < kb_rem ? 1 : 0);
+    int kb_count = kb_base + (split < kb_rem ? 1 : 0);
     const int m0 = m_tile * GEMM_BM;
     const int n0 = n_tile * Cfg::BN;
+    if (p.b_upper) {  // B[k][j] = 0 for k > j: columns n0 .. n0+BN-1 only need k <= n0+BN-1 (uniform per CTA)
+        const int kb_last = (min(n0 + Cfg::BN, p.N) + GEMM_BK - 1) / GEMM_BK;
+        kb_count = max(0, min(kb_count, kb_last - kb_begin));
+    }
     if (p.symmetric && n0 + Cfg::BN <= m0) return;  // whole tile below the diagonal: filled by the mirror kernel
 
     if (threadIdx.x == 0) {

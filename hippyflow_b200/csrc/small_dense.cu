@@ -61,8 +61,16 @@ constexpr int CI_U = 4;   // independent global read-modify-writes in flight per
 // (W0, W and S are written earlier in the same kernel: plain pointers, no __restrict__/const, so that no load is routed
 // through the non-coherent read-only path; the price -- the compiler keeps every load behind earlier stores -- is why the
 // loads of a batch are issued explicitly before its stores.)
+// section profiling (debug aid, hfb_chol_inverse_profile): thread 0 accumulates clock64() deltas per section
+#define CI_TICK(i)                                  \
+    if (prof && threadIdx.x == 0) {                 \
+        const long long now_ = clock64();           \
+        prof[i] += now_ - tlast;                    \
+        tlast = now_;                               \
+    }
+
 __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, double shift, double* P, int PW, double* rdiag,
-                                  double* Dblk, int* s_fail) {
+                                  double* Dblk, int* s_fail, long long* prof, long long& tlast) {
     const int tid = threadIdx.x, T = blockDim.x;
     for (int base = tid; base < m * m; base += T * CI_U) {
         double v[CI_U];
@@ -81,6 +89,7 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
     }
     if (tid == 0) *s_fail = 0;
     __syncthreads();
+    CI_TICK(1)
     for (int i0 = 0; i0 < m; i0 += CI_NB) {
         const int nb = min(CI_NB, m - i0), i1 = i0 + nb, w = m - i0;
         for (int idx = tid; idx < CI_NB * (w + 8); idx += T) {
@@ -88,6 +97,7 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
             P[r * PW + cc] = (r < nb && cc >= r && cc < w) ? W[(long long)(i0 + r) * ldw + i0 + cc] : 0.0;
         }
         __syncthreads();
+        CI_TICK(2)
         if (tid < 32) {  // diagonal block R11^T R11 = A11 (8 x 8) by warp 0: lane c owns column c in registers
             const int c = tid;
             double d[CI_NB];
@@ -115,6 +125,7 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
             if (bad && c == 0) *s_fail = 1;
         }
         __syncthreads();
+        CI_TICK(3)
         if (*s_fail) return 1;
         for (int cc = tid; cc < w; cc += T) {
             if (cc < nb) {
@@ -134,6 +145,7 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
             }
         }
         __syncthreads();
+        CI_TICK(4)
         for (int idx = tid; idx < nb * w; idx += T) {
             const int r = idx / w, cc = idx - r * w;
             if (cc >= r) W[(long long)(i0 + r) * ldw + i0 + cc] = P[r * PW + cc];
@@ -175,6 +187,7 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
             }
         }
         __syncthreads();
+        CI_TICK(5)
     }
     return 0;
 }
@@ -184,10 +197,11 @@ __device__ int chol_upper_blocked(int m, double* W0, double* W, long long ldw, d
 // thread back-substitutes its own columns in registers, then ALL threads add the panel's contribution to the rows above
 // (block column of R staged in shared memory, read-modify-writes issued CI_U at a time).
 __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S, long long lds, double* P, int PW,
-                                      double* Dblk, double* Rcol) {
+                                      double* Dblk, double* Rcol, long long* prof, long long& tlast) {
     const int tid = threadIdx.x, T = blockDim.x;
     for (int idx = tid; idx < m * m; idx += T) S[(long long)(idx / m) * lds + idx % m] = 0.0;
     __syncthreads();
+    CI_TICK(6)
     for (int i0 = ((m - 1) / CI_NB) * CI_NB; i0 >= 0; i0 -= CI_NB) {
         const int nb = min(CI_NB, m - i0), w = m - i0;
         for (int idx = tid; idx < CI_NB * (w + 8); idx += T) {
@@ -199,6 +213,7 @@ __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S
             Dblk[tid] = (r < nb && q < nb && q >= r) ? W[(long long)(i0 + r) * ldw + i0 + q] : (r == q ? 1.0 : 0.0);
         }
         __syncthreads();
+        CI_TICK(7)
         for (int cc = tid; cc < w; cc += T) {  // rows of the panel, bottom-up, for column cc: t_jj = (delta - sums) / r_jj
             double t[CI_NB];
 #pragma unroll
@@ -216,6 +231,7 @@ __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S
             Rcol[idx] = (i < i0 && q < nb) ? W[(long long)i * ldw + i0 + q] : 0.0;
         }
         __syncthreads();
+        CI_TICK(8)
         for (int idx = tid; idx < nb * w; idx += T) {
             const int r = idx / w, cc = idx - r * w;
             if (cc >= r) S[(long long)(i0 + r) * lds + i0 + cc] = P[r * PW + cc];
@@ -256,6 +272,7 @@ __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S
             }
         }
         __syncthreads();
+        CI_TICK(9)
     }
 }
 
@@ -263,7 +280,7 @@ __device__ void inverse_upper_blocked(int m, double* W, long long ldw, double* S
 __global__ void __launch_bounds__(CI_THREADS, 1)
 chol_inverse_kernel(int m, const double* __restrict__ G, long long ldg, double* S, long long lds,
                     double* W0, double* W, long long ldw, double* __restrict__ stat,
-                    int scale_columns, double cond_max) {
+                    int scale_columns, double cond_max, long long* prof) {
     extern __shared__ double sm[];
     const int PW = (m + 9) & ~1;          // + 8 zero columns: partial DMMA tiles read past the panel width
     double* P = sm;                       // CI_NB x PW
@@ -275,6 +292,7 @@ chol_inverse_kernel(int m, const double* __restrict__ G, long long ldg, double* 
     const int tid = threadIdx.x, T = blockDim.x;
     const double eps = DBL_EPSILON;
     __shared__ int s_fail;
+    long long tlast = prof ? clock64() : 0;
 
     // column scaling d_j = sqrt(G_jj); a zero column stays zero (dinv = 0, unit diagonal), as in hIPPYlib's MGS
     double dmaxdev = 0.0, ndead = 0.0;
@@ -316,11 +334,12 @@ chol_inverse_kernel(int m, const double* __restrict__ G, long long ldg, double* 
     ndead = red[33];
     __syncthreads();
 
+    CI_TICK(0)
     double shift = 0.0, cond = 0.0;
     int attempts = 0, ok = 0;
     for (int attempt = 0; attempt < 8; ++attempt) {
         ++attempts;
-        const int fail = chol_upper_blocked(m, W0, W, ldw, shift, P, PW, rdiag, Dblk, &s_fail);
+        const int fail = chol_upper_blocked(m, W0, W, ldw, shift, P, PW, rdiag, Dblk, &s_fail, prof, tlast);
         __syncthreads();
         if (!fail) {
             double mx = 0.0, mn = DBL_MAX;
@@ -339,7 +358,7 @@ chol_inverse_kernel(int m, const double* __restrict__ G, long long ldg, double* 
         shift = (shift == 0.0) ? 100.0 * m * eps : shift * 100.0;
     }
     if (ok) {
-        inverse_upper_blocked(m, W, ldw, S, lds, P, PW, Dblk, Rcol);
+        inverse_upper_blocked(m, W, ldw, S, lds, P, PW, Dblk, Rcol, prof, tlast);
         // undo the column scaling (S = D^-1 R^-1) and clear the strictly lower part
         for (int base = tid; base < m * m; base += T * CI_U) {
             double v[CI_U];
@@ -356,6 +375,8 @@ chol_inverse_kernel(int m, const double* __restrict__ G, long long ldg, double* 
             }
         }
     }
+    __syncthreads();
+    CI_TICK(10)
     if (tid == 0) {
         stat[0] = ok ? 0.0 : 1.0;
         stat[1] = shift;
@@ -500,8 +521,25 @@ extern "C" size_t hfb_chol_inverse_workspace_bytes(int64_t m) {
     return 2 * (size_t)m * ldw * 8;
 }
 
+static int chol_inverse_impl(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat, int scale_columns,
+                             void* workspace, size_t workspace_bytes, long long* prof, void* stream_);
+
 extern "C" int hfb_chol_inverse(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat,
                                 int scale_columns, void* workspace, size_t workspace_bytes, void* stream_) {
+    return chol_inverse_impl(m, G, ldg, S, lds, stat, scale_columns, workspace, workspace_bytes, nullptr, stream_);
+}
+
+// Debug aid: same call, thread 0 additionally accumulates clock64() cycles per kernel section into prof[0..10] (DEVICE,
+// zeroed by the caller): {scaling, copy, panel load, diagonal block, panel solve, trailing update, zero S, panel load,
+// panel solve + column stage, eager update, final scaling}.
+extern "C" int hfb_chol_inverse_profile(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat,
+                                        int scale_columns, void* workspace, size_t workspace_bytes, int64_t* prof, void* stream_) {
+    if (!prof) return HFB_E_BADARG;
+    return chol_inverse_impl(m, G, ldg, S, lds, stat, scale_columns, workspace, workspace_bytes, (long long*)prof, stream_);
+}
+
+static int chol_inverse_impl(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat, int scale_columns,
+                             void* workspace, size_t workspace_bytes, long long* prof, void* stream_) {
     if (m <= 0 || !G || !S || !stat || ldg < m || lds < m) return HFB_E_BADARG;
     if (m > 1024) return HFB_E_UNSUPPORTED;
     const size_t need = hfb_chol_inverse_workspace_bytes(m);
@@ -521,7 +559,7 @@ extern "C" int hfb_chol_inverse(int64_t m, const double* G, int64_t ldg, double*
         configured[dev] = true;
     }
     chol_inverse_kernel<<<1, CI_THREADS, smem, (cudaStream_t)stream_>>>((int)m, G, ldg, S, lds, W0, W, ldw, stat,
-                                                                        scale_columns ? 1 : 0, 1.0e13);
+                                                                        scale_columns ? 1 : 0, 1.0e13, prof);
     ++g_launch_count;
     return (int)cudaGetLastError();
 }

@@ -243,8 +243,10 @@ static bool frag_shape(int max_rows, int max_cols, int& rh, int& maxks) {
     return true;
 }
 
-template <int RH, int MAXKS>
-__global__ void __launch_bounds__(DM_WARPS * 32, 3)
+// NG = column groups per warp (W <= 64 * NG): 5 for whole rows of up to 320 columns (3 CTAs/SM), 3 and 2 for chunks of up to
+// 192 / 128 columns, whose smaller accumulator sets and row buffers let 4 / 5 CTAs share an SM.
+template <int RH, int MAXKS, int NG>
+__global__ void __launch_bounds__(DM_WARPS * 32, NG >= 5 ? 3 : NG == 3 ? 4 : 5)
     csr_spmm_dmma_frag_kernel(int m, int W, int st256, FragBlobLayout F, const unsigned char* __restrict__ blobs,
                               const double* __restrict__ B, long long ldb, double* __restrict__ C, long long ldc) {
     constexpr int COLS = 4 * MAXKS;
@@ -296,9 +298,9 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 3)
 
     constexpr int GSTRIDE = (DM_WARPS / RH) * TILEW;
     const int ngrp = (wcur > cg * TILEW) ? (wcur - cg * TILEW + GSTRIDE - 1) / GSTRIDE : 0;
-    double acc[SLAB_NG][NA];
+    double acc[NG][NA];
 #pragma unroll
-    for (int i = 0; i < SLAB_NG; ++i)
+    for (int i = 0; i < NG; ++i)
 #pragma unroll
         for (int q = 0; q < NA; ++q) acc[i][q] = 0.0;
     uint32_t bfrag;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 3)
         if (nz >> ks & 1u) {
             const uint32_t bk = bfrag + ks * kstep_bytes;
 #pragma unroll
-            for (int i = 0; i < SLAB_NG; ++i) {
+            for (int i = 0; i < NG; ++i) {
                 if (i < ngrp) {
                     if (RH == 2) {
                         const double2 b = lds128(bk + (uint32_t)(i * GSTRIDE) * 8u);
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 3)
     if (orow >= 0) {
         double* outp = C + (long long)orow * ldc + c0 + cg * TILEW + (RH == 2 ? 4 * t : 2 * t);
 #pragma unroll
-        for (int i = 0; i < SLAB_NG; ++i) {
+        for (int i = 0; i < NG; ++i) {
             if (i < ngrp) {
                 double* cp = outp + i * GSTRIDE;
                 const int cc = c0 + cg * TILEW + i * GSTRIDE + (RH == 2 ? 4 * t : 2 * t);
@@ -372,15 +374,15 @@ __global__ void __launch_bounds__(DM_WARPS * 32, 3)
     }
 }
 
-template <int RH, int MAXKS>
-static int launch_dmma_frag(int64_t nclusters, int m, int W, const FragBlobLayout& F, const void* blobs, const double* B,
-                            int64_t ldb, double* C, int64_t ldc, cudaStream_t stream) {
+template <int RH, int MAXKS, int NG>
+static int launch_dmma_frag_ng(int64_t nclusters, int m, int W, const FragBlobLayout& F, const void* blobs, const double* B,
+                               int64_t ldb, double* C, int64_t ldc, cudaStream_t stream) {
     constexpr int COLS = 4 * MAXKS;
     const size_t smem = sizeof(double) * (size_t)COLS * (W + 4);
-    if (smem > 227 * 1024 || W > 64 * SLAB_NG) return HFB_E_UNSUPPORTED;
+    if (smem > 227 * 1024 || W > 64 * NG) return HFB_E_UNSUPPORTED;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_frag_kernel<RH, MAXKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_frag_kernel<RH, MAXKS, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return (int)e;
         configured = smem;
@@ -389,10 +391,18 @@ static int launch_dmma_frag(int64_t nclusters, int m, int W, const FragBlobLayou
     if (nchunk > 65535) return HFB_E_UNSUPPORTED;
     const int st256 = ((reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc & 3) == 0) ? 1 : 0;
     dim3 grid((unsigned)nclusters, (unsigned)nchunk);
-    csr_spmm_dmma_frag_kernel<RH, MAXKS><<<grid, DM_WARPS * 32, smem, stream>>>(
+    csr_spmm_dmma_frag_kernel<RH, MAXKS, NG><<<grid, DM_WARPS * 32, smem, stream>>>(
         m, W, st256, F, static_cast<const unsigned char*>(blobs), B, ldb, C, ldc);
     ++g_launch_count;
     return (int)cudaGetLastError();
+}
+
+template <int RH, int MAXKS>
+static int launch_dmma_frag(int64_t nclusters, int m, int W, const FragBlobLayout& F, const void* blobs, const double* B,
+                            int64_t ldb, double* C, int64_t ldc, cudaStream_t stream) {
+    if (W <= 128) return launch_dmma_frag_ng<RH, MAXKS, 2>(nclusters, m, W, F, blobs, B, ldb, C, ldc, stream);
+    if (W <= 192) return launch_dmma_frag_ng<RH, MAXKS, 3>(nclusters, m, W, F, blobs, B, ldb, C, ldc, stream);
+    return launch_dmma_frag_ng<RH, MAXKS, 5>(nclusters, m, W, F, blobs, B, ldb, C, ldc, stream);
 }
 
 }  // namespace hfb

@@ -22,7 +22,8 @@ class CsrMatrix:
     """Sparse SPD weight matrix (mass matrix M, prior precision R) resident on the device as int32 CSR,
     the format the reference exports (PODProjector.py:695-697)."""
 
-    WIDE_DEFAULT = "frag"       # kernel 'auto' uses for blocks of >= 192 columns
+    WIDE_DEFAULT = "frag"       # kernel 'auto' uses over the cluster plan (r02: 5 / 3 / 2 column groups per warp by width)
+    CLUSTER_MIN_COLS = int(__import__("os").environ.get("HFB_SPMM_MIN_COLS", 96))   # narrower blocks: generic L1-panel kernel
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
@@ -41,7 +42,7 @@ class CsrMatrix:
         self.plan = None
         import os
         # SpMM kernel for blocks of >= 96 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
-        #   "auto"  (default) "frag" for m >= 192, "dmma" for narrower blocks
+        #   "auto"  (default) "frag" (measured r02: 0.164 ms vs 0.183 ms for "dmma" at m = 138, 0.271 vs 0.306 ms at m = 266)
         #   "frag"  dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
         #   "dmma"  same arithmetic, records decoded in the kernel, double-buffered 64-column panels
         # (five further variants were measured and retired: profiles/r01_spmm_variants.md, tools/experiments/spmm_variants/)
@@ -117,7 +118,7 @@ class CsrMatrix:
     def _matmat(self, B, out):
         m = B.shape[1]
         wide = K._ld(B) >= m + (m & 1)                      # the padding column of an odd width may be read
-        if self.plan is not None and m >= 96 and wide and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
+        if self.plan is not None and m >= self.CLUSTER_MIN_COLS and wide and B.data_ptr() % 16 == 0 and K._ld(B) % 2 == 0 and \
                 self.plan["max_rows"] <= 16 and self.plan["max_cols_cap"] <= 48 and \
                 (out is None or (out.data_ptr() % 16 == 0 and K._ld(out) % 2 == 0)):
             import os
@@ -125,7 +126,7 @@ class CsrMatrix:
             if impl == "auto":
                 # measured on B200 (profiles/r01_spmm_variants.md): whole-row fragment-record kernel for wide blocks,
                 # double-buffered 64-column panels for narrow ones (a CTA's share is too small to amortise its latency chain)
-                impl = os.environ.get("HFB_SPMM_WIDE", self.WIDE_DEFAULT) if m >= 192 else "dmma"
+                impl = os.environ.get("HFB_SPMM_WIDE", self.WIDE_DEFAULT)
             if impl == "frag":
                 return K.csr_spmm_dmma_frag(self._frag_blobs(self.plan, self.device), B, out,
                                             int(os.environ.get("HFB_SPMM_FRAG_W", 0))), "csr_spmm_dmma_frag_kernel"
@@ -352,7 +353,7 @@ def b_orthonormalize_device(Y, Bmat=None, return_BQ=True):
     Z = Bmat.matmat(Y) if Bmat is not None else Y
     G = sym_gram(Y, Z)
     S1, stat1 = K.chol_inverse(G, scale_columns=True)
-    Q1 = K.dgemm(K.HFB_NN, Y, S1)
+    Q1 = K.dgemm(K.HFB_NN, Y, S1, b_upper=True)                          # S1 is upper triangular: TRMM
     if Bmat is not None:
         Z1 = Bmat.matmat(Q1, out=Z)
     else:
@@ -444,7 +445,7 @@ def b_orthonormalize(Y, Bmat=None, max_passes=5, return_BQ=True, defer_last=Fals
         if fail != 0:
             raise K.HfbError("b_orthonormalize: singular triangular factor")
         S *= dinv[:, None]
-        spare = K.dgemm(K.HFB_NN, Y, K.to_padded(S, Y.device), out=spare)
+        spare = K.dgemm(K.HFB_NN, Y, K.to_padded(S, Y.device), out=spare, b_upper=True)    # S upper triangular: TRMM
         Y, spare = spare, Y                                      # ping-pong instead of copying the (n x m) block back
         info["passes"] += 1
         if defer_last and it == 0 and shift == 0.0 and cond * eps * m < 1e-4:

@@ -66,6 +66,10 @@ int hfb_dgemm(int layout, int64_t M, int64_t N, int64_t K, double alpha,
 /* HFB_GEMM_ACCUMULATE: C += alpha * op(A) op(B) (C is read; not combinable with HFB_GEMM_SYMMETRIC).  Used to sum the
  * per-chunk lifts Y += X_c^T W_c while the snapshots are still being uploaded. */
 #define HFB_GEMM_ACCUMULATE 2
+/* HFB_GEMM_B_UPPER: the caller asserts that B (K x N with K == N, layouts NN / TN) is upper triangular -- the triangular
+ * inverse S of Cholesky-QR in Q = Y S.  k-blocks below a tile's last column are skipped (a TRMM: ~25 % less work at two
+ * column tiles); entries of B below the diagonal are never read past the tile boundary, so they must be zero. */
+#define HFB_GEMM_B_UPPER 4
 size_t hfb_dgemm_ex_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int splits, int flags);
 int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double alpha,
                  const double* A, int64_t lda, const double* B, int64_t ldb,
@@ -230,6 +234,11 @@ int hfb_fill_random(int64_t nrows, int64_t ncols, double* X, int64_t ldx, uint64
 size_t hfb_chol_inverse_workspace_bytes(int64_t m);
 int hfb_chol_inverse(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat, int scale_columns,
                      void* workspace, size_t workspace_bytes, void* stream);
+/* Debug aid: the same call; thread 0 additionally accumulates clock64() cycles per kernel section into prof[0..10]
+ * (DEVICE int64, zeroed by the caller): scaling, copy, panel load, diagonal block, panel solve, trailing update, zero S,
+ * panel load, panel solve + column stage, eager update, final scaling (tools/bench_small_dense.py prints them). */
+int hfb_chol_inverse_profile(int64_t m, const double* G, int64_t ldg, double* S, int64_t lds, double* stat, int scale_columns,
+                             void* workspace, size_t workspace_bytes, int64_t* prof, void* stream);
 
 /*
  * Batched one-sided Jacobi SVD of small blocks, one CTA per sample, block resident in shared memory

@@ -126,7 +126,7 @@ def emulated_device():
     def out_or_new(out, rows, cols, dev):
         return out if out is not None else K.padded_empty(rows, cols, dev)
 
-    def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumulate=False):
+    def dgemm(layout, A, B, out=None, alpha=1.0, splits=0, symmetric=False, accumulate=False, b_upper=False):
         K._req(A, "A"), K._req(B, "B")
         opA = A.t() if layout == K.HFB_TN else A
         opB = B.t() if layout == K.HFB_NT else B

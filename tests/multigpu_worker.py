@@ -129,6 +129,30 @@ def main():
     coll.allReduce(mv, "avg")
     assert torch.allclose(mv.tensor(), torch.full_like(mv.tensor(), (world + 1) / 2.0))
     assert coll.allReduce(float(rank), "sum") == sum(range(world))
+    # strided operands under NCCL (advisor r1): a DeviceVector is an (n, 1) column view of a padded block, mv[j] a column
+    # of a multivector -- NCCL rejects non-contiguous tensors, the collective must pack / unpack them
+    dv = hf.DeviceVector(37, dev)
+    dv.set_local(np.full(37, float(rank + 1)))
+    assert not dv.storage_tensor().is_contiguous()
+    coll.allReduce(dv, "sum")
+    np.testing.assert_allclose(dv.get_local(), sum(range(1, world + 1)))
+    mv.tensor().fill_(float(rank))
+    col = mv[3]
+    coll.allReduce(col, "avg")
+    assert torch.allclose(mv.tensor()[:, 3], torch.full((50,), (world - 1) / 2.0, dtype=torch.float64, device=dev))
+    assert torch.allclose(mv.tensor()[:, 2], torch.full((50,), float(rank), dtype=torch.float64, device=dev))
+    bv = hf.DeviceVector(11, dev)
+    bv.set_local(np.full(11, float(rank + 5)))
+    coll.bcast(bv, root=world - 1)
+    np.testing.assert_allclose(bv.get_local(), float(world + 4))
+    # operator applies on device VECTORS through the collective (CollectiveOperator.mult path, collectiveOperator.py:31-38)
+    from hippyflow_b200.linalg import SampleCovariance
+    cov_op = hf.SampleCovarianceOperator(SampleCovariance(hf._lib.to_padded(shard, dev)), coll, "avg")
+    xv, yv = hf.DeviceVector(n, dev), hf.DeviceVector(n, dev)
+    xvec = np.cos(np.arange(n) * 0.1)
+    xv.set_local(xvec)
+    cov_op.mult(xv, yv)
+    np.testing.assert_allclose(yv.get_local(), u.T @ (u @ xvec) / u.shape[0], rtol=1e-11, atol=1e-13)
     dist.barrier()
     if rank == 0:
         print("MULTIGPU_OK world=%d" % world)

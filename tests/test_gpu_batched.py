@@ -97,6 +97,26 @@ def test_dgemm_batched_on_jacobian_view_and_argument_checks(env):
         K.dgemm_batched(K.HFB_TN, J3, stack(K, dev, rng.standard_normal((5, 100, 20))))   # batch sizes differ
 
 
+@pytest.mark.parametrize("shape", [(1000, 266), (300, 138), (64, 17), (5000, 522)])
+@pytest.mark.parametrize("layout", ["NN", "TN"])
+def test_dgemm_upper_triangular_B_skips_zero_blocks(env, shape, layout):
+    """HFB_GEMM_B_UPPER (the TRMM Q = Y S of Cholesky-QR): same result as the full product when B is upper triangular;
+    garbage below the diagonal past the tile boundary is never read."""
+    hf, K, dev = env
+    M, N = shape
+    rng = np.random.default_rng(M + N)
+    A = rng.standard_normal((N, M) if layout == "TN" else (M, N))
+    S = np.triu(rng.standard_normal((N, N)))
+    lay = K.HFB_TN if layout == "TN" else K.HFB_NN
+    ref = (A.T if layout == "TN" else A) @ S
+    out = K.dgemm(lay, K.to_padded(A, dev), K.to_padded(S, dev), b_upper=True)
+    assert rel(out.cpu().numpy(), ref) < 1e-13
+    full = K.dgemm(lay, K.to_padded(A, dev), K.to_padded(S, dev))
+    assert rel(out.cpu().numpy(), full.cpu().numpy()) < 1e-14
+    with pytest.raises(K.HfbError):
+        K.dgemm(lay, K.to_padded(A, dev), K.to_padded(S[:, : N - 1], dev), b_upper=True)
+
+
 # ------------------------------------------------------------------ device Cholesky-QR factor
 @pytest.mark.parametrize("m", [1, 7, 8, 9, 64, 138, 266, 513, 1024])
 def test_chol_inverse_vs_numpy(env, m):

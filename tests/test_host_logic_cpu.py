@@ -129,7 +129,7 @@ def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
         assert Dd.plan is not None and 32 < Dd.plan["max_cols_cap"] <= 48
         assert Dd.shape[0] / Dd.plan["nclusters"] > 6                      # (16, 32) would leave ~2.4 rows per cluster
         rng = np.random.default_rng(0)
-        for m, kernel in ((266, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_dmma_kernel"),
+        for m, kernel in ((266, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_dmma_frag_kernel"),
                           (40, "csr_spmm_panel_kernel")):
             B = K.to_padded(rng.standard_normal((dense.shape[0], m)), dev)
             out, used = Dd._matmat(B, None)

@@ -39,6 +39,13 @@ for m in (138, 210, 266, 522, 1024):
     G = K.to_padded(Y.t() @ Y, dev)
     res["chol_inverse_m%d_ms" % m] = timed(lambda: K.chol_inverse(G), n=10)
     print("chol_inverse m=%d: %.3f ms" % (m, res["chol_inverse_m%d_ms" % m]), flush=True)
+    if m in (138, 266):
+        K.chol_inverse_profile(G)
+        cyc = K.chol_inverse_profile(G)
+        names = ["scaling", "copy", "panel load", "diag block", "panel solve", "trailing update", "zero S", "inv panel load",
+                 "inv solve+stage", "inv eager update", "final scaling"]
+        res["chol_inverse_m%d_section_kcycles" % m] = {nm: float(c) / 1e3 for nm, c in zip(names, cyc)}
+        print("   sections (k cycles):", res["chol_inverse_m%d_section_kcycles" % m], flush=True)
 
 if only == "chol":
     json.dump(res, open("gpurun_out/%s_small_dense_chol.json" % tag, "w"), indent=1)

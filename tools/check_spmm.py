@@ -1,7 +1,7 @@
-"""SpMM micro-benchmark: the cluster-plan kernels ("staged" cp.async panels, "tma" persistent bulk-copy ring, "regblock"
-register-blocked, "dmma" DMMA panels, "frag" fragment records with whole-row staging, "pipe" cluster-pipelined frag) at the
-benchmark shapes, for a few cluster caps; every result is checked against torch's sparse product.
-Usage (GPU box): python tools/check_spmm.py [--quick] [--impls staged,frag] [--json out.json]; HFB_CHECK_CAPS=16,32 pins the caps.
+"""SpMM micro-benchmark: the cluster-plan kernels ("dmma" DMMA panels, "frag" fragment records with whole-row or chunked
+staging at 5 / 3 / 2 column groups per warp) and the generic panel kernel at the benchmark shapes, for a few cluster caps;
+every result is checked against torch's sparse product.
+Usage (GPU box): python tools/check_spmm.py [--quick] [--impls dmma,frag] [--json out.json]; HFB_CHECK_CAPS=16,32 pins the caps.
 Operands (0.56-2.1 GB) exceed L2; times are the best of 20 launches (CUDA events)."""
 import json
 import os
@@ -15,11 +15,11 @@ from hippyflow_b200.linalg import CsrMatrix
 dev = torch.device("cuda:0")
 PEAK = 6542.1   # MEASURED_PEAKS.json hbm_gbs
 quick = "--quick" in sys.argv
-shapes = ((263169, 266),) if quick else ((263169, 266), (1002001, 266), (251001, 138))
+shapes = ((263169, 266), (251001, 138), (263169, 74)) if quick else ((263169, 266), (1002001, 266), (251001, 138), (251001, 210), (263169, 74))
 caps = ((16, 32),) if quick else ((16, 32), (12, 32), (8, 24))
 if os.environ.get("HFB_CHECK_CAPS", "").replace(",", "").isdigit():
     caps = (tuple(int(v) for v in os.environ["HFB_CHECK_CAPS"].split(",")),)
-impls = ("tma", "staged", "regblock", "dmma", "frag", "pipe")
+impls = ("dmma", "frag")
 if "--impls" in sys.argv:
     impls = tuple(sys.argv[sys.argv.index("--impls") + 1].split(","))
 results = []
@@ -51,8 +51,8 @@ for n, m in shapes:
         for impl in impls:
             Md.impl = impl
             # tuning knobs swept per variant (None: leave the environment alone)
-            knob = {"regblock": "HFB_SPMM_RB_DEPTH", "dmma": "HFB_SPMM_DMMA_W", "frag": "HFB_SPMM_FRAG_W"}.get(impl)
-            depths = {"regblock": (0,), "dmma": (0,), "frag": (0,)}.get(impl, (None,)) if not quick else (None,)
+            knob = {"frag": "HFB_SPMM_FRAG_W"}.get(impl)
+            depths = {"frag": (0, 192, 128, 96)}.get(impl, (None,))
             for dep in depths:
                 if dep is not None:
                     os.environ.pop(knob, None)
@@ -66,7 +66,7 @@ for n, m in shapes:
                     continue
                 by = Md.spmm_bytes(m)
                 err = float((C - ref).abs().max())
-                tag = impl + (f"/{'depth' if impl == 'regblock' else 'w'}{dep}" if dep else "")
+                tag = impl + (f"/w{dep}" if dep else "")
                 print(f"n={n} m={m} caps=({rows},{cols}) clusters={Md.plan['nclusters']} {tag}: {t:.3f} ms "
                       f"{by / t / 1e6:.0f} GB/s ({by / t / 1e6 / PEAK * 100:.1f}% of HBM peak) err {err:.2e}", flush=True)
                 results.append({"n": n, "m": m, "caps": [rows, cols], "clusters": Md.plan["nclusters"], "impl": tag, "ms": t,
