@@ -62,6 +62,7 @@ def lib():
         "hfb_csr_frag_blob_stride": (i64, [i32, i32]),
         "hfb_csr_pack_clusters_frag": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
         "hfb_csr_spmm_dmma_frag": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_spmm_dmma_ring": (i32, [i64, i64, vp, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -97,7 +98,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", 
             "hfb_csr_cluster_rows_capped", 
             "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_dmma",
-            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", 
+            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", "hfb_csr_spmm_dmma_ring", 
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -382,6 +383,20 @@ def csr_spmm_dmma(plan, B, out=None):
     rc = L.hfb_csr_spmm_dmma(plan["nclusters"], m, plan["blobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
                              plan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
     _check(rc, "hfb_csr_spmm_dmma")
+    return out
+
+
+def csr_spmm_dmma_ring(plan, B, out=None):
+    """C = M @ B with the ring-pipelined fragment-record kernel (hfb_csr_spmm_dmma_ring); same records and results as
+    ``csr_spmm_dmma_frag``.  Needs clusters of 9..16 rows and m <= 384."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_dmma_ring(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
+                                  B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_dmma_ring")
     return out
 
 

@@ -20,6 +20,7 @@
 #include "../../include/hfb200.h"
 #include "hfb_common.cuh"
 #include "spmm_blob.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -405,6 +406,276 @@ static int launch_dmma_frag(int64_t nclusters, int m, int W, const FragBlobLayou
     return launch_dmma_frag_ng<RH, MAXKS, 5>(nclusters, m, W, F, blobs, B, ldb, C, ldc, stream);
 }
 
+
+// ---------------------------------------------------------------------------------------------------- ring-pipelined variant
+// The fragment-record kernel with the per-CTA latency chain (column list -> row copies -> DMMAs -> stores) taken apart by
+// warp specialisation.  One resident CTA per SM walks clusters blockIdx.x, blockIdx.x + gridDim.x, ... :
+//   * one producer warp keeps a ring of 2-8 cluster buffers full: for every cluster it posts the byte count on the slot's FULL
+//     mbarrier and issues one TMA linear copy (cp.async.bulk, SASS UBLKCP) for the fragment record and one per distinct B row
+//     (lane j copies row j; the column lists are fetched three clusters ahead, in three register sets used in turn by a loop
+//     unrolled by hand -- rotating them with moves would expose one DRAM latency per cluster);
+//   * RING_CONSUMERS = 16 consumer warps (2 row halves x 8 column groups) wait for a slot, take their A fragments, masks and
+//     result rows from the record in shared memory, run the k-steps, release the slot with one arrive per warp on EMPTY, and
+//     store.
+// Measured on B200 (profiles/r02_spmm_ring.md, clock64 sections): the TMA engine retires one small linear copy per ~65 cycles
+// per SM (33 requests = ~2150 cycles per cluster whatever the row length), a DMMA.8x8x4 that accumulates into the result of
+// the previous one issues ~250 cycles after it, and at m = 266 the 16 consumer warps keep the FP64 pipe ~56 % busy in the
+// multiply phase (2150 cycles per cluster for 408 DMMAs); the period of the ring is the larger of the two, ~2900 cycles.
+// Splitting the k-steps over two accumulator sets (RING_KSPLIT = 2) or the consumers over two clusters was measured slower
+// (registers / fewer warps per cluster).  With RING_KSPLIT = 1 the summation order is that of the per-cluster kernel: results
+// are bitwise equal to hfb_csr_spmm_dmma_frag.  TMA copies cannot zero-fill: the ring is zeroed once, and rows past a
+// cluster's column count keep finite earlier data that only meets zero fragment entries.
+constexpr int RING_CONSUMERS = 16;
+constexpr int RING_THREADS = (RING_CONSUMERS + 1) * 32;
+constexpr int RING_CG = RING_CONSUMERS / 2;   // column groups (two row halves)
+constexpr int RING_NG = 3;                    // 16-column tiles per consumer warp: W <= 16 * RING_CG * RING_NG = 384
+constexpr int RING_KSPLIT = 1;                // independent accumulator sets (k-step parity); 2 measured slower (spills)
+constexpr int RING_MAX_SLOTS = 8;
+
+template <int MAXKS>
+__global__ void __launch_bounds__(RING_THREADS, 1)
+    csr_spmm_ring_kernel(int m, int W, int st256, int nclusters, int nslots, int slot_bytes, FragBlobLayout F,
+                         const unsigned char* __restrict__ blobs, const double* __restrict__ B, long long ldb,
+                         double* __restrict__ C, long long ldc, unsigned long long* prof) {
+    constexpr int RH = 2;
+    constexpr int COLS = 4 * MAXKS;
+    constexpr int TILEW = 8 * RH;
+    extern __shared__ __align__(128) unsigned char smem_ring[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_ring);
+    uint64_t* empty = full + RING_MAX_SLOTS;
+    unsigned char* slots = smem_ring + 128;
+    const int pitch = W + 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < nslots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], RING_CONSUMERS);
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < nslots * slot_bytes / 8; i += blockDim.x) reinterpret_cast<double*>(slots)[i] = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int width = m + (m & 1);
+    const int npiece = (min(W, width) + 1) >> 1;                       // 16-byte pieces of a B row that exist
+
+    if (warp == RING_CONSUMERS) {
+        // ------------------------------------------------------------------ producer
+        int c = blockIdx.x;
+        auto fetch = [&](int cl, int& col, int& col2, int& nc) {
+            col = col2 = nc = 0;
+            if (cl < nclusters) {
+                const unsigned char* bl = blobs + (size_t)cl * F.stride;
+                nc = __ldg(reinterpret_cast<const int*>(bl) + 1);
+                col = __ldg(reinterpret_cast<const int*>(bl + F.off_cols) + lane);
+                if (COLS > 32 && lane + 32 < COLS) col2 = __ldg(reinterpret_cast<const int*>(bl + F.off_cols) + lane + 32);
+            }
+        };
+        int colA, colB, colC, c2A, c2B, c2C, nA, nB, nC;
+        fetch(c, colA, c2A, nA);
+        fetch(c + (int)gridDim.x, colB, c2B, nB);
+        fetch(c + 2 * (int)gridDim.x, colC, c2C, nC);
+        int it = 0;
+        const uint32_t rowbytes = (uint32_t)npiece * 16u;
+        auto one_cluster = [&](int& colX, int& col2X, int& nX) {
+            const int s = it % nslots;
+            const uint32_t ph = (uint32_t)(it / nslots) & 1u;
+            const int cur_col = colX, cur_col2 = col2X, cur_ncol = nX;
+            const unsigned char* blob = blobs + (size_t)c * F.stride;
+            fetch(c + 3 * (int)gridDim.x, colX, col2X, nX);
+            const long long tp0 = prof ? clock64() : 0;
+            mbar_wait(&empty[s], ph ^ 1u);
+            if (prof && lane == 0) atomicAdd(prof + 0, (unsigned long long)(clock64() - tp0));
+            unsigned char* st = slots + (size_t)s * slot_bytes;
+            double* sB = reinterpret_cast<double*>(st + F.stride);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], (uint32_t)F.stride + (uint32_t)cur_ncol * rowbytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(st)),
+                             "l"(reinterpret_cast<uint64_t>(blob)), "r"((uint32_t)F.stride), "r"(smem_u32(&full[s]))
+                             : "memory");
+            }
+            __syncwarp();
+            if (lane < cur_ncol)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(sB + lane * pitch)),
+                             "l"(reinterpret_cast<uint64_t>(B + (long long)cur_col * ldb)), "r"(rowbytes), "r"(smem_u32(&full[s]))
+                             : "memory");
+            if (COLS > 32 && lane + 32 < cur_ncol)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(sB + (lane + 32) * pitch)),
+                             "l"(reinterpret_cast<uint64_t>(B + (long long)cur_col2 * ldb)), "r"(rowbytes), "r"(smem_u32(&full[s]))
+                             : "memory");
+        };
+        while (true) {
+            if (c >= nclusters) break;
+            one_cluster(colA, c2A, nA);
+            c += gridDim.x;
+            ++it;
+            if (c >= nclusters) break;
+            one_cluster(colB, c2B, nB);
+            c += gridDim.x;
+            ++it;
+            if (c >= nclusters) break;
+            one_cluster(colC, c2C, nC);
+            c += gridDim.x;
+            ++it;
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int g = lane >> 2, t = lane & 3;
+    const int h = warp & 1, cg = warp >> 1;
+    const int ntiles = (min(W, m) + TILEW - 1) / TILEW;
+    const uint32_t kstep_bytes = (uint32_t)(4 * pitch) * 8u;
+    int it = 0;
+    for (int c = blockIdx.x; c < nclusters; c += gridDim.x, ++it) {
+        const int s = it % nslots;
+        const uint32_t ph = (uint32_t)(it / nslots) & 1u;
+        const long long tc0 = prof ? clock64() : 0;
+        mbar_wait(&full[s], ph);
+        const long long tc1 = prof ? clock64() : 0;
+        const unsigned char* st = slots + (size_t)s * slot_bytes;
+        const int* hdr = reinterpret_cast<const int*>(st);
+        const int nrow = hdr[0];
+        const unsigned nz = (unsigned)hdr[2 + h];
+        const double* afrag = reinterpret_cast<const double*>(st + F.off_afrag) + h * 32 + lane;
+        double a[MAXKS];
+#pragma unroll
+        for (int ks = 0; ks < MAXKS; ++ks) a[ks] = (nz >> ks & 1u) ? afrag[ks * RH * 32] : 0.0;
+        const int r = g + 8 * h;
+        const int orow = r < nrow ? reinterpret_cast<const int*>(st + F.off_outrow)[r] : -1;
+        // 16-column tiles of this warp: tile = i * RING_CG + ((cg + it) mod RING_CG); the rotation spreads the odd tile of a
+        // width like 272 = 17 tiles over the warps from cluster to cluster
+        const int rot = (cg + it) & (RING_CG - 1);
+        double acc[RING_KSPLIT][RING_NG][4];
+#pragma unroll
+        for (int q = 0; q < RING_KSPLIT; ++q)
+#pragma unroll
+            for (int i = 0; i < RING_NG; ++i) acc[q][i][0] = acc[q][i][1] = acc[q][i][2] = acc[q][i][3] = 0.0;
+        const uint32_t bbase = smem_u32(reinterpret_cast<const double*>(st + F.stride) + t * pitch + rot * TILEW + 2 * g);
+        // software pipeline: the B fragments of k-step ks + 1 are requested before the DMMAs of k-step ks are issued
+        // (lds128 / dmma884 are volatile asm and keep their program order, so the order below is the issue order)
+        bool live[RING_NG];
+#pragma unroll
+        for (int i = 0; i < RING_NG; ++i) live[i] = i * RING_CG + rot < ntiles;
+        double2 bcur[RING_NG], bnxt[RING_NG];
+#pragma unroll
+        for (int i = 0; i < RING_NG; ++i) {
+            bcur[i] = make_double2(0.0, 0.0);
+            if ((nz & 1u) && live[i]) bcur[i] = lds128(bbase + (uint32_t)(i * RING_CG * TILEW) * 8u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < MAXKS; ++ks) {
+            if (ks + 1 < MAXKS) {
+                const uint32_t bk = bbase + (ks + 1) * kstep_bytes;
+#pragma unroll
+                for (int i = 0; i < RING_NG; ++i) {
+                    bnxt[i] = make_double2(0.0, 0.0);
+                    if ((nz >> (ks + 1) & 1u) && live[i]) bnxt[i] = lds128(bk + (uint32_t)(i * RING_CG * TILEW) * 8u);
+                }
+            }
+            if (nz >> ks & 1u) {
+#pragma unroll
+                for (int i = 0; i < RING_NG; ++i) {
+                    if (live[i]) {
+                        dmma884(acc[ks % RING_KSPLIT][i][0], acc[ks % RING_KSPLIT][i][1], a[ks], bcur[i].x);
+                        dmma884(acc[ks % RING_KSPLIT][i][2], acc[ks % RING_KSPLIT][i][3], a[ks], bcur[i].y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < RING_NG; ++i) bcur[i] = bnxt[i];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);      // everything this warp needs from the slot is in registers now
+        if (orow >= 0) {
+#pragma unroll
+            for (int i = 0; i < RING_NG; ++i) {
+                if (live[i]) {
+                    double v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = acc[0][i][e];
+#pragma unroll
+                        for (int q = 1; q < RING_KSPLIT; ++q) v[e] += acc[q][i][e];
+                    }
+                    const int cc = (i * RING_CG + rot) * TILEW + 4 * t;
+                    double* cp = C + (long long)orow * ldc + cc;
+                    if (st256 && cc + 3 < m) {
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(cp)),
+                                     "d"(v[0]), "d"(v[2]), "d"(v[1]), "d"(v[3])
+                                     : "memory");
+                    } else {
+                        if (cc + 1 < m) {
+                            *reinterpret_cast<double2*>(cp) = make_double2(v[0], v[2]);
+                        } else if (cc < m) {
+                            cp[0] = v[0];
+                        }
+                        if (cc + 3 < m) {
+                            *reinterpret_cast<double2*>(cp + 2) = make_double2(v[1], v[3]);
+                        } else if (cc + 2 < m) {
+                            cp[2] = v[1];
+                        }
+                    }
+                }
+            }
+        }
+        if (prof && lane == 0 && warp == 0) {
+            atomicAdd(prof + 1, (unsigned long long)(tc1 - tc0));            // consumer: waiting for data
+            atomicAdd(prof + 2, (unsigned long long)(clock64() - tc1));      // consumer: fragments + k-steps + stores
+            atomicAdd(prof + 3, 1ull);
+        }
+    }
+}
+
+template <int MAXKS>
+static int launch_ring(int64_t nclusters, int m, const FragBlobLayout& F, const void* blobs, const double* B, int64_t ldb,
+                       double* C, int64_t ldc, cudaStream_t stream) {
+    constexpr int COLS = 4 * MAXKS;
+    const int W = (m + 15) / 16 * 16;
+    if (W > 16 * RING_CG * RING_NG) return HFB_E_UNSUPPORTED;
+    const int slot_bytes = round_up(F.stride + 8 * COLS * (W + 4), 128);
+    int nslots = (227 * 1024 - 256) / slot_bytes;
+    static const int max_slots = getenv("HFB_RING_SLOTS") ? atoi(getenv("HFB_RING_SLOTS")) : RING_MAX_SLOTS;
+    if (nslots > max_slots) nslots = max_slots;
+    if (nslots > RING_MAX_SLOTS) nslots = RING_MAX_SLOTS;
+    if (nslots < 2) return HFB_E_UNSUPPORTED;
+    const size_t smem = 128 + (size_t)nslots * slot_bytes;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && smem > configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(csr_spmm_ring_kernel<MAXKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured[dev] = smem;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long gx = sms;
+    if (gx > nclusters) gx = nclusters;
+    const int st256 = ((reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc & 3) == 0) ? 1 : 0;
+    static unsigned long long* prof_dev = nullptr;
+    unsigned long long* prof_buf = nullptr;
+    if (getenv("HFB_RING_PROF")) {   // debug aid: cycles the producer waits for a slot / a consumer warp waits for data / works
+        if (!prof_dev) cudaMalloc(&prof_dev, 4 * sizeof(unsigned long long));
+        cudaMemsetAsync(prof_dev, 0, 4 * sizeof(unsigned long long), stream);
+        prof_buf = prof_dev;
+    }
+    csr_spmm_ring_kernel<MAXKS><<<(unsigned)gx, RING_THREADS, smem, stream>>>(
+        m, W, st256, (int)nclusters, nslots, slot_bytes, F, static_cast<const unsigned char*>(blobs), B, ldb, C, ldc, prof_buf);
+    ++g_launch_count;
+    if (prof_buf) {
+        unsigned long long h[4];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ring prof] m=%d slots=%d: producer wait-empty %.0f cyc/cluster, consumer wait-full %.0f, consumer work %.0f (%llu samples)\n",
+                m, nslots, (double)h[0] / (double)nclusters, (double)h[1] / (double)(h[3] ? h[3] : 1), (double)h[2] / (double)(h[3] ? h[3] : 1), h[3]);
+    }
+    return (int)cudaGetLastError();
+}
+
 }  // namespace hfb
 
 using namespace hfb;
@@ -625,4 +896,23 @@ static int dmma_frag_dispatch(int64_t nclusters, int64_t m, const void* blobs, i
 extern "C" int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                                       int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream) {
     return dmma_frag_dispatch(nclusters, m, blobs, max_rows, max_cols, chunk_cols, B, ldb, C, ldc, stream);
+}
+
+/* Ring-pipelined form of hfb_csr_spmm_dmma_frag (same records, same results bit for bit): clusters of two row halves
+ * (8 < max_rows <= 16), blocks of up to 384 columns. */
+extern "C" int hfb_csr_spmm_dmma_ring(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                                      const double* B, int64_t ldb, double* C, int64_t ldc, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (nclusters <= 0 || m <= 0 || !blobs || !B || !C || B == C) return HFB_E_BADARG;
+    if (ldb < m + (m & 1) || ldc < m) return HFB_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15) || (reinterpret_cast<uintptr_t>(blobs) & 15) ||
+        (ldb & 1) || (ldc & 1))
+        return HFB_E_ALIGN;
+    if (nclusters > 0x7fffffffLL || m > 16 * RING_CG * RING_NG) return HFB_E_UNSUPPORTED;
+    int rh, maxks;
+    if (!frag_shape(max_rows, max_cols, rh, maxks) || rh != 2) return HFB_E_UNSUPPORTED;
+    const FragBlobLayout F = frag_layout(rh, maxks);
+    if (maxks <= 6) return launch_ring<6>(nclusters, (int)m, F, blobs, B, ldb, C, ldc, stream);
+    if (maxks == 8) return launch_ring<8>(nclusters, (int)m, F, blobs, B, ldb, C, ldc, stream);
+    return launch_ring<12>(nclusters, (int)m, F, blobs, B, ldb, C, ldc, stream);
 }

@@ -23,7 +23,8 @@ class CsrMatrix:
     the format the reference exports (PODProjector.py:695-697)."""
 
     WIDE_DEFAULT = "frag"       # kernel 'auto' uses over the cluster plan (r02: 5 / 3 / 2 column groups per warp by width)
-    CLUSTER_MIN_COLS = int(__import__("os").environ.get("HFB_SPMM_MIN_COLS", 96))   # narrower blocks: generic L1-panel kernel
+    # narrower blocks go to the generic L1-panel kernel (r02, m = 74: fragment kernel 0.129 ms = 2601 GB/s vs 0.222 ms)
+    CLUSTER_MIN_COLS = int(__import__("os").environ.get("HFB_SPMM_MIN_COLS", 32))
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
@@ -44,6 +45,7 @@ class CsrMatrix:
         # SpMM kernel for blocks of >= 96 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
         #   "auto"  (default) "frag" (measured r02: 0.164 ms vs 0.183 ms for "dmma" at m = 138, 0.271 vs 0.306 ms at m = 266)
         #   "frag"  dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
+        #   "ring"  the same records through resident CTAs with producer warps + a ring of cluster buffers (m <= 384)
         #   "dmma"  same arithmetic, records decoded in the kernel, double-buffered 64-column panels
         # (five further variants were measured and retired: profiles/r01_spmm_variants.md, tools/experiments/spmm_variants/)
         self.impl = os.environ.get("HFB_SPMM_IMPL", "auto")
@@ -126,13 +128,17 @@ class CsrMatrix:
             if impl == "auto":
                 # measured on B200 (profiles/r01_spmm_variants.md): whole-row fragment-record kernel for wide blocks,
                 # double-buffered 64-column panels for narrow ones (a CTA's share is too small to amortise its latency chain)
-                impl = os.environ.get("HFB_SPMM_WIDE", self.WIDE_DEFAULT)
-            if impl == "frag":
+                # whole-row fragment kernel; ring-pipelined form of it for 192 <= m <= 384 (r02: 0.244 ms vs 0.272 ms at m = 266;
+                # narrower blocks are bound by its per-cluster TMA request count and stay with the per-cluster kernel)
+                impl = os.environ.get("HFB_SPMM_WIDE", "ring" if 192 <= m <= 384 else self.WIDE_DEFAULT)
+            if impl == "ring" and 8 < self.plan["max_rows"] <= 16 and m <= 384:
+                return K.csr_spmm_dmma_ring(self._frag_blobs(self.plan, self.device), B, out), "csr_spmm_ring_kernel"
+            if impl in ("frag", "ring"):
                 return K.csr_spmm_dmma_frag(self._frag_blobs(self.plan, self.device), B, out,
                                             int(os.environ.get("HFB_SPMM_FRAG_W", 0))), "csr_spmm_dmma_frag_kernel"
             if impl == "dmma":
                 return K.csr_spmm_dmma(self._panel_blobs(self.plan, self.device), B, out), "csr_spmm_dmma_kernel"
-            raise K.HfbError("unknown HFB_SPMM_IMPL '%s' (auto | frag | dmma)" % impl)
+            raise K.HfbError("unknown HFB_SPMM_IMPL '%s' (auto | frag | ring | dmma)" % impl)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order), "csr_spmm_panel_kernel"
 
     def matmat_rows(self, X, out=None):

@@ -163,6 +163,13 @@ int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, const int32_t* 
                                void* blobs_out /* HOST, nclusters * stride bytes */);
 int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                            int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+/* Ring-pipelined form over the same fragment records (results bitwise equal to hfb_csr_spmm_dmma_frag): one resident CTA per
+ * SM, two producer warps keep a ring of 2-3 cluster buffers (fragment record + whole B rows, cp.async completing on mbarriers)
+ * full while 16 consumer warps run the DMMA k-steps and store -- the column-list / copy / multiply / store chain of a cluster
+ * overlaps its neighbours' inside the SM.  Clusters of two row halves (8 < max_rows <= 16), m <= 384; other shapes return
+ * HFB_E_UNSUPPORTED and the caller uses hfb_csr_spmm_dmma_frag. */
+int hfb_csr_spmm_dmma_ring(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
+                           const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.

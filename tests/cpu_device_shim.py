@@ -179,6 +179,9 @@ def emulated_device():
             cache[key] = decode_frag_blobs(K, plan["fblobs"].numpy(), plan["max_rows"], plan["max_cols_cap"], plan["order"].numel())
         return _spmm(cache[key], B, out)
 
+    def csr_spmm_dmma_ring(plan, B, out=None):
+        return csr_spmm_dmma_frag(plan, B, out)      # same records
+
     def csr_spmm_rows(rowptr, colind, val, X, out=None):
         Msp = _scipy_csr(rowptr, colind, val, X.shape[1])
         res = torch.from_numpy(np.ascontiguousarray((Msp @ X.numpy().T).T))
@@ -244,7 +247,7 @@ def emulated_device():
         k.pop("pin_memory", None)
         return saved_empty(*a, **k)
 
-    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
+    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_dmma_ring=csr_spmm_dmma_ring, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
                    colsum=colsum, subtract_row_=subtract_row_, rank1_update_=rank1_update_, axpby_=axpby_,
                    axpby_cols_=axpby_cols_, rowscale=rowscale, fill_random_=fill_random_,
                    measure_dmma_peak=lambda device: 1.0, launch_count=lambda: counter["n"],

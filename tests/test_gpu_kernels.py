@@ -115,8 +115,8 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
-@pytest.mark.parametrize("impl", ["dmma", "frag"])
-@pytest.mark.parametrize("m", [96, 137, 138, 266, 300, 511, 1100])
+@pytest.mark.parametrize("impl", ["dmma", "frag", "ring"])
+@pytest.mark.parametrize("m", [33, 96, 137, 138, 266, 300, 383, 511, 1100])
 def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     """The cluster-plan kernels (panel records / fragment records) on a mesh matrix large enough to get a
     plan (n >= 4096), odd and even widths, widths that need 1..4 column chunks; padding columns stay untouched."""
@@ -185,6 +185,35 @@ def test_csr_spmm_dmma_frag_cluster_caps(K, cuda_device, caps, m, chunk):
     assert torch.equal(K.csr_spmm_dmma_frag(plan, K.to_padded(B, cuda_device), chunk_cols=chunk), out)     # bitwise reproducible
 
 
+@pytest.mark.parametrize("caps", [(16, 24), (16, 32), (16, 48), (12, 24), (9, 20)])
+@pytest.mark.parametrize("m", [10, 74, 138, 266, 267, 330, 384])
+def test_csr_spmm_ring_vs_scipy_and_frag(K, cuda_device, caps, m):
+    """Ring-pipelined kernel: every k-step instantiation, widths with 1..3 tiles per warp and a partial last tile, a mesh
+    large enough that every resident CTA walks several clusters through its 2-8 slot ring; bitwise equal to the per-cluster
+    fragment kernel (same summation order) and to itself run to run; padding columns stay untouched."""
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    M = syn.p1_mass_matrix(120, 100).tocsr()
+    n = M.shape[0]
+    plan = CsrMatrix._frag_blobs(CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1]), cuda_device)
+    assert plan["nclusters"] > 4 * 148
+    B = np.random.default_rng(m).standard_normal((n, m))
+    Bd = K.to_padded(B, cuda_device)
+    out = K.padded_empty(n, m, cuda_device)
+    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
+    full.fill_(7.0)
+    try:
+        K.csr_spmm_dmma_ring(plan, Bd, out)
+    except K.HfbError as e:                      # two ring slots of (48 columns x 336) do not fit shared memory: refused, not wrong
+        assert "unsupported" in str(e) and caps[1] > 32 and m > 300
+        return
+    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
+    if K._ld(out) > m:
+        assert bool((full[:, m:] == 7.0).all())
+    assert torch.equal(K.csr_spmm_dmma_frag(plan, Bd), out)
+    assert torch.equal(K.csr_spmm_dmma_ring(plan, Bd), out)
+
+
 def test_csr_spmm_dmma_frag_irregular_and_unaligned_rows(K, cuda_device):
     """Ragged pattern with empty rows; result block whose rows are only 16-byte aligned (128-bit store path)."""
     import scipy.sparse as sp
@@ -232,7 +261,7 @@ def test_csr_spmm_dmma_irregular_matrix_and_limits(K, cuda_device):
         K.csr_spmm_dmma(big, K.to_padded(B, cuda_device))
 
 
-@pytest.mark.parametrize("impl", ["dmma", "frag", "auto"])
+@pytest.mark.parametrize("impl", ["dmma", "frag", "ring", "auto"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
     import scipy.sparse as sp

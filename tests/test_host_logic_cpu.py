@@ -105,8 +105,8 @@ def test_shim_decodes_the_cluster_plans():
 
 def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
     """Host side of the SpMM dispatch: a 7-point mesh matrix gets (16, 32) clusters, a 21-point one the (16, 48) budget
-    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the fragment kernel for wide blocks, the panel kernel for
-    narrow ones, the generic CSR kernel below 96 columns, and duplicates in the input matrix are summed first."""
+    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the fragment kernel for blocks of >= 32 columns, the generic
+    CSR kernel below, and duplicates in the input matrix are summed first."""
     import numpy as np
     import scipy.sparse as sp
     from hippyflow_b200 import _lib as K, synthetic as syn
@@ -129,8 +129,8 @@ def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
         assert Dd.plan is not None and 32 < Dd.plan["max_cols_cap"] <= 48
         assert Dd.shape[0] / Dd.plan["nclusters"] > 6                      # (16, 32) would leave ~2.4 rows per cluster
         rng = np.random.default_rng(0)
-        for m, kernel in ((266, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_dmma_frag_kernel"),
-                          (40, "csr_spmm_panel_kernel")):
+        for m, kernel in ((266, "csr_spmm_ring_kernel"), (500, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_dmma_frag_kernel"),
+                          (40, "csr_spmm_dmma_frag_kernel"), (20, "csr_spmm_panel_kernel")):
             B = K.to_padded(rng.standard_normal((dense.shape[0], m)), dev)
             out, used = Dd._matmat(B, None)
             assert used == kernel
