@@ -77,6 +77,17 @@ def _copy_stream(dev):
 _staging = {}
 
 
+def _host_copy_threads():
+    """Threads for the pageable -> pinned staging copies: the cores this process may run on, shared between the ranks of
+    the node (LOCAL_WORLD_SIZE), at most 16."""
+    import os
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return int(max(1, min(16, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))))
+
+
 def _staging_ring(dev, n, nbuf=3, target_bytes=96 << 20):
     """Ring of pinned staging buffers (rows x n) for uploads from pageable host memory, cached per device and row length."""
     key = (dev.index, n)
@@ -327,6 +338,9 @@ class PODProjectorFromData:
             # previous chunk.
             ring = _staging_ring(dev, n)
             rows_per = ring[0][0].shape[0]
+            # torchrun exports OMP_NUM_THREADS=1; the staging copies are worth this rank's share of the host cores
+            saved_threads = torch.get_num_threads()
+            torch.set_num_threads(_host_copy_threads())
             j = 0
             for i, (lo, hi) in enumerate(bounds):
                 for s0 in range(lo, hi, rows_per):
@@ -341,6 +355,7 @@ class PODProjectorFromData:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 consume(i, lo, hi, ev)
+            torch.set_num_threads(saved_threads)
         Xt.record_stream(copy_stream)
         if not shifted:
             return Xt, torch.zeros(n, dtype=torch.float64, device=dev), None, (W, Y)

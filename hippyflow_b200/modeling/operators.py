@@ -44,12 +44,15 @@ class SampleCovarianceOperator:
 
     matMvTranspmult = matMvMult
 
-    def lift_reduced(self, GW, Y, nchunk=4):
+    LIFT_CHUNKS = int(__import__("os").environ.get("HFB_LIFT_CHUNKS", 4))
+
+    def lift_reduced(self, GW, Y, nchunk=None):
         """Y = allReduce_op( (1/N_loc) Xt^T GW ).  With more than one rank the lift GEMM is cut into row blocks of Y and
         the NCCL allreduce of each block is issued asynchronously as soon as its GEMM is queued, so the exchange of
         block i overlaps the GEMM of block i+1 (the 'avg' factor 1/size is folded into the GEMM's alpha)."""
         Yt = Y.tensor()
         n = Yt.shape[0]
+        nchunk = self.LIFT_CHUNKS if nchunk is None else nchunk
         scale = 1.0 / self.cov.nsamples
         size = self.collective.size()
         lazy = self.cov.lazy_pending()
