@@ -83,6 +83,15 @@ def lib():
         "hfb_jacobi_svd_max_elems": (i64, []),
         "hfb_jacobi_svd_batched": (i32, [i64, i64, vp, i64, i64, i64, vp, i64, vp, i32, i32, vp]),
         "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
+        "hfb_peer_alloc": (i32, [sz, ctypes.POINTER(vp)]),
+        "hfb_peer_free": (i32, [vp]),
+        "hfb_peer_get_handle": (i32, [vp, ctypes.c_char_p]),
+        "hfb_peer_open": (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
+        "hfb_peer_close": (i32, [vp]),
+        "hfb_dgemm_peer": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, ctypes.POINTER(vp), i32, i64, i64, vp]),
+        "hfb_peer_barrier": (i32, [ctypes.POINTER(vp), i32, i32, u64, dbl, vp]),
+        "hfb_peer_reduce": (i32, [vp, i64, i32, i64, i64, i64, vp, vp, i64, i32, vp]),
+        "hfb_peer_gather": (i32, [ctypes.POINTER(vp), i32, i32, i64, i64, i64, i64, vp, i64, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -104,7 +113,9 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
             "hfb_measure_dmma_peak", "hfb_chol_inverse_workspace_bytes", "hfb_chol_inverse", "hfb_chol_inverse_profile",
             "hfb_jacobi_svd_max_elems",
-            "hfb_jacobi_svd_batched"]
+            "hfb_jacobi_svd_batched",
+            "hfb_peer_alloc", "hfb_peer_free", "hfb_peer_get_handle", "hfb_peer_open", "hfb_peer_close", "hfb_dgemm_peer",
+            "hfb_peer_barrier", "hfb_peer_reduce", "hfb_peer_gather"]
 
 
 def _check(rc, what):
@@ -645,3 +656,79 @@ def stop_timing():
 
 def launch_count():
     return int(lib().hfb_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------- peer exchange (NVLink)
+PEER_HANDLE_BYTES = 64
+PEER_MAX_RANKS = 16
+
+
+def peer_alloc(nbytes):
+    """Zeroed device buffer that can be shared with the other ranks of the node through CUDA IPC (address as int)."""
+    p = ctypes.c_void_p()
+    _check(lib().hfb_peer_alloc(int(nbytes), ctypes.byref(p)), "hfb_peer_alloc")
+    return int(p.value)
+
+
+def peer_free(ptr):
+    _check(lib().hfb_peer_free(ctypes.c_void_p(ptr)), "hfb_peer_free")
+
+
+def peer_get_handle(ptr):
+    buf = ctypes.create_string_buffer(PEER_HANDLE_BYTES)
+    _check(lib().hfb_peer_get_handle(ctypes.c_void_p(ptr), buf), "hfb_peer_get_handle")
+    return bytes(buf.raw)
+
+
+def peer_open(handle):
+    if len(handle) != PEER_HANDLE_BYTES:
+        raise HfbError("peer_open: a CUDA IPC handle has %d bytes" % PEER_HANDLE_BYTES)
+    p = ctypes.c_void_p()
+    _check(lib().hfb_peer_open(ctypes.c_char_p(handle), ctypes.byref(p)), "hfb_peer_open")
+    return int(p.value)
+
+
+def peer_close(ptr):
+    _check(lib().hfb_peer_close(ctypes.c_void_p(ptr)), "hfb_peer_close")
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs])
+
+
+def dgemm_peer(A, B, slot_ptrs, block_rows, ld_slot, alpha=1.0):
+    """Fused lift + reduce-scatter: rows [o * block_rows, (o+1) * block_rows) of alpha * A^T B (TN layout, A: K x M) are
+    stored by the GEMM epilogue into ``slot_ptrs[o]`` (this rank's slot in rank o's exchange buffer, leading dimension
+    ``ld_slot``), over NVLink for o != this rank."""
+    _req(A, "A"), _req(B, "B")
+    Kd, M = A.shape
+    K2, N = B.shape
+    if Kd != K2:
+        raise HfbError("dgemm_peer: inner dimensions differ (%d vs %d)" % (Kd, K2))
+    if TIMING is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = lib().hfb_dgemm_peer(HFB_TN, M, N, Kd, float(alpha), A.data_ptr(), _ld(A), B.data_ptr(), _ld(B),
+                              _ptr_array(slot_ptrs), len(slot_ptrs), int(block_rows), int(ld_slot), _stream())
+    if TIMING is not None:
+        e1.record()
+        TIMING.append(((HFB_TN, M, N, Kd), e0, e1))
+    _check(rc, "hfb_dgemm_peer")
+
+
+def peer_barrier(flag_ptrs, me, epoch, timeout_s=600.0):
+    _check(lib().hfb_peer_barrier(_ptr_array(flag_ptrs), int(me), len(flag_ptrs), int(epoch), float(timeout_s), _stream()),
+           "hfb_peer_barrier")
+
+
+def peer_reduce(slots_ptr, slot_stride, nranks, rows, cols, ld, reduced_ptr, y_ptr, ldy, max_ctas=0):
+    _check(lib().hfb_peer_reduce(ctypes.c_void_p(slots_ptr), int(slot_stride), int(nranks), int(rows), int(cols), int(ld),
+                                 ctypes.c_void_p(reduced_ptr), ctypes.c_void_p(y_ptr), int(ldy), int(max_ctas), _stream()),
+           "hfb_peer_reduce")
+
+
+def peer_gather(reduced_ptrs, me, block_rows, n, cols, ld, y_ptr, ldy, ctas_per_peer=0):
+    _check(lib().hfb_peer_gather(_ptr_array(reduced_ptrs), int(me), len(reduced_ptrs), int(block_rows), int(n), int(cols),
+                                 int(ld), ctypes.c_void_p(y_ptr), int(ldy), int(ctas_per_peer), _stream()),
+           "hfb_peer_gather")

@@ -189,7 +189,8 @@ extern "C" size_t hfb_dgemm_ex_workspace_bytes(int layout, int64_t M, int64_t N,
 //           range, summed in fixed order).
 static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda, int64_t strideA,
                      const double* B, int64_t ldb, int64_t strideB, double* C, int64_t ldc, int64_t strideC, int64_t batch,
-                     int mode, void* workspace, size_t workspace_bytes, int splits, int flags, cudaStream_t stream) {
+                     int mode, void* workspace, size_t workspace_bytes, int splits, int flags, cudaStream_t stream,
+                     double* const* peer_dst = nullptr, int npeers = 0, int64_t peer_rows = 0) {
     const int symmetric = ((flags & HFB_GEMM_SYMMETRIC) && M == N) ? 1 : 0;
     const int accumulate = (flags & HFB_GEMM_ACCUMULATE) ? 1 : 0;
     const int b_upper = (flags & HFB_GEMM_B_UPPER) ? 1 : 0;
@@ -257,6 +258,23 @@ static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, double alpha, 
     p.symmetric = symmetric;
     p.accumulate = accumulate;
     p.b_upper = b_upper;
+    p.peer_rows = 0;
+    memset(p.peer_dst, 0, sizeof(p.peer_dst));
+    if (peer_dst) {
+        // fused reduce-scatter epilogue: one destination per 128-row tile, direct stores only
+        if (npeers < 1 || npeers > GEMM_MAX_PEERS || peer_rows <= 0 || (peer_rows % GEMM_BM) || peer_rows > 0x7fffffffLL ||
+            (long long)npeers * peer_rows < M)
+            return HFB_E_BADARG;
+        if (splits != 1 || batched || symmetric || accumulate) return HFB_E_UNSUPPORTED;
+        if (ldc & 1) return HFB_E_ALIGN;
+        for (int o = 0; o < npeers; ++o) {
+            if (!peer_dst[o]) return HFB_E_BADARG;
+            if (reinterpret_cast<uintptr_t>(peer_dst[o]) & 15) return HFB_E_ALIGN;
+            p.peer_dst[o] = peer_dst[o];
+        }
+        p.peer_rows = (int)peer_rows;
+        p.vec_store = 1;
+    }
     if ((long long)p.m_tiles * p.n_tiles * p.splits * nbat > 0x7fffffffLL) return HFB_E_BADARG;
 
     CUtensorMap mapA, mapB;
@@ -297,6 +315,15 @@ extern "C" int hfb_dgemm_ex(int layout, int64_t M, int64_t N, int64_t K, double 
                             size_t workspace_bytes, int splits, int flags, void* stream_) {
     return gemm_impl(layout, M, N, K, alpha, A, lda, 0, B, ldb, 0, C, ldc, 0, 1, 0, workspace, workspace_bytes, splits, flags,
                      (cudaStream_t)stream_);
+}
+
+extern "C" int hfb_dgemm_peer(int layout, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                              const double* B, int64_t ldb, double* const* slot_ptrs, int nranks, int64_t block_rows,
+                              int64_t ld_slot, void* stream_) {
+    if (!slot_ptrs || nranks < 1) return HFB_E_BADARG;
+    // C is only a placeholder for the argument checks: every tile is redirected to slot_ptrs[row / block_rows]
+    return gemm_impl(layout, M, N, K, alpha, A, lda, 0, B, ldb, 0, slot_ptrs[0], ld_slot, 0, 1, 0, nullptr, 0, 1, 0,
+                     (cudaStream_t)stream_, slot_ptrs, nranks, block_rows);
 }
 
 extern "C" size_t hfb_dgemm_batched_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K, int64_t batch, int mode) {

@@ -32,6 +32,7 @@ constexpr int GEMM_CONSUMER_WARPS = 8;
 constexpr int GEMM_PRODUCER_WARPS = 4;  // a full warpgroup so setmaxnreg can hand its registers to the consumers
 constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + GEMM_PRODUCER_WARPS) * 32;
 constexpr int GEMM_REGS_PRODUCER = 40;
+constexpr int GEMM_MAX_PEERS = 16;       // ranks of one NVLink domain addressed by the fused reduce-scatter epilogue
 constexpr int GEMM_REGS_CONSUMER = 232;  // per SMSP: 2 consumer warps x 232 + 1 producer warp x 40 = 504 <= 512
 
 struct GemmParams {
@@ -52,6 +53,12 @@ struct GemmParams {
     int a_batched, b_batched;  // operand has a sample axis (third coordinate = sample) or is shared (third coordinate 0)
     long long strideC;     // elements between consecutive C_b
     int b_upper;           // 1: B (K x N, NN/TN layouts) is upper triangular: k-blocks past the tile's last column are skipped
+    // fused reduce-scatter over peer memory (hfb_dgemm_peer): rows [o*peer_rows, (o+1)*peer_rows) of the result are stored
+    // into peer_dst[o] -- this rank's slot inside rank o's exchange buffer, a peer-mapped (NVLink) or local address -- with
+    // leading dimension ldc and rows counted from the start of the block.  peer_rows is a multiple of GEMM_BM, so a CTA's
+    // tile has ONE destination.  0 = off (plain store into C).
+    int peer_rows;
+    double* peer_dst[GEMM_MAX_PEERS];
 };
 
 template <int LAYOUT, int NT>
@@ -70,7 +77,7 @@ struct GemmCfg {
 
 __device__ __forceinline__ int rho(int g) { return ((g & 1) << 2) | (g >> 1); }
 
-template <int LAYOUT, int NT>
+template <int LAYOUT, int NT, bool PEER = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const GemmParams p) {
@@ -265,6 +272,11 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
     // ---------------------------------------------------------------------- epilogue
     double* Cout = p.C + (long long)split * p.split_stride + (long long)bat * p.strideC;
+    if (PEER) {
+        // reduce-scatter by push: the tile goes straight from the accumulators into the owner's exchange buffer over NVLink
+        const int owner = m0 / p.peer_rows;
+        Cout = p.peer_dst[owner] - (long long)owner * p.peer_rows * p.ldc;
+    }
     const double alpha = (p.splits == 1) ? p.alpha : 1.0;
     const bool accum = (p.splits == 1) && p.accumulate;
     auto put1 = [&](double* dst, double v) { *dst = accum ? (*dst + v) : v; };

@@ -9,20 +9,30 @@
 
 namespace hfb {
 
-template <int LAYOUT, int NT>
-static int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, cudaStream_t stream) {
+template <int LAYOUT, int NT, bool PEER>
+static int launch_k(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<LAYOUT, NT>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<LAYOUT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<LAYOUT, NT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const long long grid = (long long)p.m_tiles * p.n_tiles * p.splits * p.batch;
-    dgemm_dmma_kernel<LAYOUT, NT><<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
+    dgemm_dmma_kernel<LAYOUT, NT, PEER><<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);
     ++g_launch_count;
     return (int)cudaGetLastError();
+}
+
+// The peer-store epilogue (fused reduce-scatter of the lift Y = Xt^T W) exists for the TN layout only.
+template <int LAYOUT, int NT>
+static int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, cudaStream_t stream) {
+    if (p.peer_rows > 0) {
+        if constexpr (LAYOUT == 1) return launch_k<LAYOUT, NT, true>(mapA, mapB, p, stream);
+        else return HFB_E_UNSUPPORTED;
+    }
+    return launch_k<LAYOUT, NT, false>(mapA, mapB, p, stream);
 }
 
 template <int LAYOUT>

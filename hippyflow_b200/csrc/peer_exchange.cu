@@ -1,0 +1,264 @@
+// Sketch exchange over NVLink peer memory (see include/hfb200.h, "peer exchange"): the allreduce of the (n x m) lift
+//   Y = sum_g X_g^T W_g                (collectiveOperator.py:73-80 -> collective.py:108-111, one MPI message per column)
+// as  reduce-scatter by PUSH from the lift GEMM's epilogue (hfb_dgemm_peer, dgemm_dmma.cuh)  ->  fixed-order sum of the
+// P slots by the owner of each row block  ->  all-gather by PULL of the reduced blocks.  Everything here is plain
+// ld/st on peer-mapped addresses (cudaIpc*), ordered by system-scope release/acquire flags; no NCCL on the data path.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/hfb200.h"
+#include "hfb_common.cuh"
+
+namespace hfb {
+
+constexpr int PEER_MAX = 16;
+
+struct PeerPtrs {
+    void* p[PEER_MAX];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* addr, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* addr) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Barrier over the ranks of one NVLink domain.  flags.p[r] is rank r's flag array (PEER_MAX counters, peer-mapped for
+// r != me).  Thread t publishes flags[t][me] = epoch (release, system scope: every store this stream issued before --
+// the GEMM's peer stores included -- is visible to whoever acquires the flag) and then waits for flags[me][t] >= epoch.
+// Epochs only grow, so no flag is ever reset.  A wait longer than timeout_ns traps (a dead peer must not hang the GPU).
+__global__ void peer_barrier_kernel(PeerPtrs flags, int me, int nranks, unsigned long long epoch,
+                                    unsigned long long timeout_ns) {
+    const int t = threadIdx.x;
+    if (t >= nranks) return;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long*>(flags.p[t]) + me, epoch);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flags.p[me]) + t;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    while (ld_acquire_sys(mine) < epoch) {
+        if ((++spins & 1023u) == 0 && timeout_ns && global_timer_ns() - t0 > timeout_ns) {
+            printf("hfb peer barrier: rank %d timed out waiting for rank %d (epoch %llu)\n", me, t, epoch);
+            __trap();
+        }
+    }
+    __threadfence_system();
+}
+
+// Owner side of the reduce-scatter: red[r][c] = sum_{s < nranks} slots[s][r][c] in FIXED order (bitwise reproducible and
+// identical on every rank, because only the owner computes it), written to the peer-visible `red` block and to the owner's
+// own rows of Y.
+__global__ void peer_reduce_kernel(const double* __restrict__ slots, long long slot_stride, int nranks, long long rows,
+                                   int cols, long long ld, double* __restrict__ red, double* __restrict__ Y,
+                                   long long ldy, int y_vec) {
+    const int pairs = (cols + 1) >> 1;
+    const long long total = rows * pairs;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / pairs;
+        const int c = 2 * (int)(idx - r * pairs);
+        const long long off = r * ld + c;
+        if (c + 1 < cols) {
+            // loads of four slots are issued together (the adds stay in rank order)
+            double2 s = make_double2(0.0, 0.0);
+            for (int k = 0; k < nranks; k += 4) {
+                double2 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = (k + j < nranks) ? *reinterpret_cast<const double2*>(slots + (long long)(k + j) * slot_stride + off)
+                                            : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (k + j < nranks) {
+                        s.x = (k + j == 0) ? v[j].x : s.x + v[j].x;
+                        s.y = (k + j == 0) ? v[j].y : s.y + v[j].y;
+                    }
+                }
+            }
+            *reinterpret_cast<double2*>(red + off) = s;
+            if (y_vec) {
+                *reinterpret_cast<double2*>(Y + r * ldy + c) = s;
+            } else {
+                Y[r * ldy + c] = s.x;
+                Y[r * ldy + c + 1] = s.y;
+            }
+        } else {
+            double s = slots[off];
+            for (int k = 1; k < nranks; ++k) s += slots[(long long)k * slot_stride + off];
+            red[off] = s;
+            Y[r * ldy + c] = s;
+        }
+    }
+}
+
+// All-gather by pull: rows of block o come from rank o's reduced block over NVLink (peer loads bypass the local L2 and
+// are read with ld.global.cv so that no stale L1 line of an earlier exchange is used).  blockIdx.y selects the peer,
+// starting with me + 1 so that the ranks do not all read from the same GPU at the same time.
+__global__ void peer_gather_kernel(PeerPtrs red, int me, int nranks, long long block_rows, long long n, int cols,
+                                   long long ld, double* __restrict__ Y, long long ldy, int y_vec) {
+    const int o = (me + 1 + (int)blockIdx.y) % nranks;
+    const long long row0 = (long long)o * block_rows;
+    long long rows = n - row0;
+    if (rows > block_rows) rows = block_rows;
+    if (rows <= 0) return;
+    const double* src = reinterpret_cast<const double*>(red.p[o]);
+    double* dst = Y + row0 * ldy;
+    const int pairs = (cols + 1) >> 1;
+    const long long total = rows * pairs;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread (NVLink latency ~2 us)
+    for (; idx + (U - 1) * stride < total; idx += U * stride) {
+        double2 v[U];
+        long long rr[U];
+        int cc[U];
+        bool full[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = idx + u * stride;
+            rr[u] = i / pairs;
+            cc[u] = 2 * (int)(i - rr[u] * pairs);
+            full[u] = cc[u] + 1 < cols;
+            const double* a = src + rr[u] * ld + cc[u];
+            if (full[u]) {
+                v[u] = __ldcv(reinterpret_cast<const double2*>(a));
+            } else {
+                v[u].x = __ldcv(a);
+                v[u].y = 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double* d = dst + rr[u] * ldy + cc[u];
+            if (full[u] && y_vec) {
+                *reinterpret_cast<double2*>(d) = v[u];
+            } else {
+                d[0] = v[u].x;
+                if (full[u]) d[1] = v[u].y;
+            }
+        }
+    }
+    for (; idx < total; idx += stride) {
+        const long long r = idx / pairs;
+        const int c = 2 * (int)(idx - r * pairs);
+        const double* a = src + r * ld + c;
+        double* d = dst + r * ldy + c;
+        d[0] = __ldcv(a);
+        if (c + 1 < cols) d[1] = __ldcv(a + 1);
+    }
+}
+
+}  // namespace hfb
+
+using namespace hfb;
+
+// ---------------------------------------------------------------------------------------------------------- memory
+extern "C" int hfb_peer_alloc(size_t bytes, void** ptr) {
+    if (!ptr || bytes == 0) return HFB_E_BADARG;
+    *ptr = nullptr;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(*ptr, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return (int)e;
+}
+
+extern "C" int hfb_peer_free(void* ptr) {
+    if (!ptr) return HFB_E_BADARG;
+    return (int)cudaFree(ptr);
+}
+
+extern "C" int hfb_peer_get_handle(void* ptr, unsigned char* handle64) {
+    if (!ptr || !handle64) return HFB_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == HFB_PEER_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) return (int)e;
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int hfb_peer_open(const unsigned char* handle64, void** ptr) {
+    if (!handle64 || !ptr) return HFB_E_BADARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *ptr = nullptr;
+    return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+extern "C" int hfb_peer_close(void* ptr) {
+    if (!ptr) return HFB_E_BADARG;
+    return (int)cudaIpcCloseMemHandle(ptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------- kernels
+extern "C" int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch, double timeout_s, void* stream_) {
+    if (!flag_ptrs || nranks < 1 || nranks > PEER_MAX || me < 0 || me >= nranks || epoch == 0) return HFB_E_BADARG;
+    PeerPtrs f;
+    memset(&f, 0, sizeof(f));
+    for (int r = 0; r < nranks; ++r) {
+        if (!flag_ptrs[r] || (reinterpret_cast<uintptr_t>(flag_ptrs[r]) & 7)) return HFB_E_BADARG;
+        f.p[r] = flag_ptrs[r];
+    }
+    const unsigned long long tns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ULL;
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(f, me, nranks, (unsigned long long)epoch, tns);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_peer_reduce(const double* slots, int64_t slot_stride, int nranks, int64_t rows, int64_t cols, int64_t ld,
+                               double* reduced, double* Y, int64_t ldy, int max_ctas, void* stream_) {
+    if (!slots || !reduced || !Y || nranks < 1 || nranks > PEER_MAX || rows < 0 || cols <= 0 || ld < cols || ldy < cols ||
+        slot_stride < rows * ld || cols > 0x7ffffffeLL)
+        return HFB_E_BADARG;
+    if ((ld & 1) || (slot_stride & 1) || (reinterpret_cast<uintptr_t>(slots) & 15) || (reinterpret_cast<uintptr_t>(reduced) & 15))
+        return HFB_E_ALIGN;
+    if (reinterpret_cast<uintptr_t>(Y) & 7) return HFB_E_ALIGN;
+    if (rows == 0) return 0;
+    const int y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
+    // max_ctas > 0: narrow launch beside a running GEMM -- few SMs, 1024 threads each (the exchange is latency/NVLink-bound)
+    const int threads = max_ctas > 0 ? 1024 : 256;
+    const long long total = rows * ((cols + 1) / 2);
+    long long blocks = (total + threads - 1) / threads;
+    const long long cap = max_ctas > 0 ? max_ctas : 148 * 8;
+    if (blocks > cap) blocks = cap;
+    peer_reduce_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream_>>>(slots, slot_stride, nranks, rows, (int)cols, ld,
+                                                                            reduced, Y, ldy, y_vec);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hfb_peer_gather(const double* const* reduced_ptrs, int me, int nranks, int64_t block_rows, int64_t n,
+                               int64_t cols, int64_t ld, double* Y, int64_t ldy, int ctas_per_peer, void* stream_) {
+    if (!reduced_ptrs || !Y || nranks < 1 || nranks > PEER_MAX || me < 0 || me >= nranks || block_rows <= 0 || n <= 0 ||
+        cols <= 0 || ld < cols || ldy < cols || cols > 0x7ffffffeLL || (long long)nranks * block_rows < n)
+        return HFB_E_BADARG;
+    if (ld & 1) return HFB_E_ALIGN;
+    if (reinterpret_cast<uintptr_t>(Y) & 7) return HFB_E_ALIGN;
+    if (nranks == 1) return 0;
+    PeerPtrs f;
+    memset(&f, 0, sizeof(f));
+    for (int r = 0; r < nranks; ++r) {
+        if (!reduced_ptrs[r]) return HFB_E_BADARG;
+        if (reinterpret_cast<uintptr_t>(reduced_ptrs[r]) & 15) return HFB_E_ALIGN;
+        f.p[r] = const_cast<double*>(reduced_ptrs[r]);
+    }
+    const int y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
+    const int threads = ctas_per_peer > 0 ? 1024 : 256;
+    if (ctas_per_peer <= 0) {
+        ctas_per_peer = (148 * 4) / (nranks - 1);
+        if (ctas_per_peer < 1) ctas_per_peer = 1;
+    }
+    peer_gather_kernel<<<dim3((unsigned)ctas_per_peer, (unsigned)(nranks - 1)), threads, 0, (cudaStream_t)stream_>>>(
+        f, me, nranks, block_rows, n, (int)cols, ld, Y, ldy, y_vec);
+    ++g_launch_count;
+    return (int)cudaGetLastError();
+}

@@ -74,6 +74,13 @@ class SampleCovarianceOperator:
             scale /= float(size)
         elif self.mpi_op.lower() != "sum":
             raise NotImplementedError("Unknown operation *{0}*".format(self.mpi_op))
+        if self._lift_peer(GW, Y, Yt, scale, lazy):
+            return
+        self._lift_nccl(GW, Y, Yt, scale, lazy, nchunk)
+
+    def _lift_nccl(self, GW, Y, Yt, scale, lazy, nchunk):
+        """Row blocks of the lift, each followed by an asynchronous NCCL allreduce (``scale`` carries the 1/size of 'avg')."""
+        n = Yt.shape[0]
         step = max(128, ((n + nchunk - 1) // nchunk + 127) // 128 * 128)     # 128-row multiples keep TMA alignment
         full = Y.storage_tensor()
         works = []
@@ -87,6 +94,72 @@ class SampleCovarianceOperator:
             # the chunks carried scale / size and were summed: the extra column is the global mean already; 1^T W / N is
             # averaged inside finish_lazy
             self.cov.finish_lazy(Yt, self.collective, "avg")
+
+    PEER_LIFT = __import__("os").environ.get("HFB_PEER_LIFT", "1") != "0"
+    PEER_CHUNKS = int(__import__("os").environ.get("HFB_PEER_CHUNKS", 4))
+    PEER_VERIFY_TOL = 1e-11
+
+    def _peer_exchange(self, n, ld, ncols):
+        """The collective's NVLink exchange buffers for this block shape (created collectively on first use; None when the
+        ranks cannot map each other's memory -- then every rank takes the NCCL route)."""
+        if not self.PEER_LIFT or getattr(self.collective, "_backend", None) != "nccl":
+            return None
+        cache = self.collective.__dict__.setdefault("_peer_exchanges", {})
+        key = (n, ld, ncols, self.PEER_CHUNKS)
+        if key not in cache:
+            from ..peer import PeerExchange
+            if len(cache) >= 4:                                   # bound the device memory held by stale shapes
+                for ex in cache.values():
+                    if ex is not None:
+                        ex.close()
+                cache.clear()
+            cache[key] = PeerExchange.create(self.collective.group, self.device, n, ld, ncols, self.PEER_CHUNKS)
+        return cache[key]
+
+    def _lift_peer(self, GW, Y, Yt, scale, lazy):
+        """The lift with its allreduce fused into the GEMM epilogue over NVLink peer memory (hippyflow_b200/peer.py).
+        Returns False when the route is unavailable.  The first exchange of every buffer set is checked against the NCCL
+        route on the same operands; a mismatch disables the peer route on all ranks (with a warning)."""
+        cov = self.cov
+        m = GW.shape[1]
+        ld = K._ld(Yt)
+        if Yt.data_ptr() % 16 or ld % 2:
+            return False
+        if lazy:
+            Wop, ncols = cov._Wext, m + 1
+            if GW.data_ptr() != cov._Wext.data_ptr() or ld < m + 1:
+                return False
+        else:
+            Wop, ncols = GW, m
+        ex = self._peer_exchange(Yt.shape[0], ld, ncols)
+        if ex is None:
+            return False
+        Yv = Yt.as_strided((Yt.shape[0], ncols), (ld, 1))
+        ex.lift_allreduce(cov.Xt, Wop, Yv, scale)
+        if not getattr(ex, "verified", False):
+            ref = torch.empty_like(Y.storage_tensor())
+            rv = ref.as_strided((Yt.shape[0], ncols), (ld, 1))
+            K.dgemm(K.HFB_TN, cov.Xt, Wop, out=rv, alpha=scale)
+            self.collective.allReduce(ref, "sum")
+            err = (rv - Yv).abs().max() / rv.abs().max().clamp_min(1e-300)
+            bad = torch.tensor([1 if not (float(err) < self.PEER_VERIFY_TOL) else 0], dtype=torch.int32, device=self.device)
+            self.collective.allReduce(bad, "sum")
+            ex.verified = True
+            ex.verify_err = float(err)
+            if int(bad.item()):
+                import warnings
+                warnings.warn("hippyflow_b200: NVLink peer exchange disagrees with the NCCL allreduce (rel. error %.2e); "
+                              "peer route disabled" % float(err))
+                self.collective._peer_exchanges[(Yt.shape[0], ld, ncols, self.PEER_CHUNKS)] = None
+                ex.close()
+                Yv.copy_(rv)
+        if lazy:
+            cov.finish_lazy(Yt, self.collective, "avg")
+        elif cov.center is not None:
+            cw = K.colsum(GW, 1.0)                                 # - c (1^T W) with the GLOBAL sum of the projections
+            self.collective.allReduce(cw, "sum")
+            K.rank1_update_(Yt, -scale, cov.center, cw)
+        return True
 
     def mult(self, x, y):
         self.cov.apply(x.storage_tensor(), out=y.storage_tensor())

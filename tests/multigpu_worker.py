@@ -47,6 +47,43 @@ def sharded_mean_shift_case(hf, dev, coll, rank, world):
         np.testing.assert_allclose(shift, u.mean(0), rtol=1e-13)
 
 
+def peer_exchange_case(hf, dev, coll, rank, world):
+    """The fused lift + NVLink exchange (hippyflow_b200/peer.py) against the lift GEMM followed by an NCCL allreduce:
+    equal to round-off of the summation order, bitwise identical on all ranks and from call to call, with one chunk and
+    with pipeline chunks on the side stream; then the operator route (first use verifies itself against NCCL)."""
+    from hippyflow_b200 import _lib as K
+    from hippyflow_b200.peer import PeerExchange
+    n, R, ncols = 66049, 192, 67
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    X = K.to_padded(torch.randn((R, n), generator=g, dtype=torch.float64), dev)
+    W = K.to_padded(torch.randn((R, ncols), generator=g, dtype=torch.float64), dev)
+    ref = K.dgemm(K.HFB_TN, X, W, alpha=0.5)
+    refc = ref.contiguous()
+    dist.all_reduce(refc)
+    for nchunk in (1, 3):
+        ex = PeerExchange.create(None, dev, n, K._ld(ref), ncols, nchunk)
+        assert ex is not None, "peer exchange unavailable on an NVLink box"
+        assert len(ex.chunks) == nchunk
+        Y = K.padded_zeros(n, ncols, dev)
+        first = None
+        for rep in range(3):
+            Y.zero_()
+            ex.lift_allreduce(X, W, Y, 0.5)
+            torch.cuda.synchronize()
+            err = float((Y - refc).abs().max() / refc.abs().max())
+            assert err < 1e-13, (nchunk, rep, err)
+            first = Y.clone() if first is None else first
+            assert torch.equal(Y, first), "exchange not reproducible from call to call"
+        gathered = [torch.empty_like(first.contiguous()) for _ in range(world)]
+        dist.all_gather(gathered, first.contiguous())
+        for t in gathered:
+            assert torch.equal(t, gathered[0]), "ranks hold different bits"
+        ex.close()
+    # operator route: SampleCovarianceOperator.lift_reduced takes the peer route and verified it against NCCL on first use
+    exs = [e for e in getattr(coll, "_peer_exchanges", {}).values() if e is not None]
+    assert exs and all(e.verified and e.verify_err < 1e-12 for e in exs), "operator lifts did not take the peer route"
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -122,6 +159,7 @@ def main():
     np.testing.assert_allclose(db2, db0, rtol=1e-10)
 
     sharded_mean_shift_case(hf, dev, coll, rank, world)
+    peer_exchange_case(hf, dev, coll, rank, world)
 
     # collective on device blocks: one NCCL call for the whole padded block, 'avg' = sum / size
     mv = hf.DeviceMultiVector(50, 7, device=dev)

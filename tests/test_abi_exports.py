@@ -68,6 +68,25 @@ def test_argument_validation_without_gpu():
     assert L.hfb_chol_inverse_workspace_bytes(266) == 2 * 266 * 266 * 8 and L.hfb_chol_inverse_workspace_bytes(5000) == 0
     assert L.hfb_jacobi_svd_batched(400, 400, 16, 400, 160000, 2, 32, 400, 64, 30, 0, None) == -5                   # does not fit shared memory
     assert L.hfb_jacobi_svd_batched(10, 4, 16, 2, 40, 2, 32, 4, 64, 30, 0, None) == -1                              # lda < cols
+    # peer exchange (fused lift + reduce-scatter over NVLink): rank tables, block alignment, epochs
+    import ctypes as C
+    two = (C.c_void_p * 2)(C.c_void_p(4096), C.c_void_p(8192))
+    bad = (C.c_void_p * 2)(C.c_void_p(4096), C.c_void_p(8200))
+    assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, None, 2, 512, 32, None) == -1               # no slot table
+    assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, two, 2, 500, 32, None) == -1                # block not a multiple of 128
+    assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, two, 2, 384, 32, None) == -1                # blocks do not cover M
+    assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, two, 17, 512, 32, None) == -1               # more ranks than the table holds
+    assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, bad, 2, 512, 32, None) == -2                # slot not 16-byte aligned
+    assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, two, 2, 512, 33, None) == -2                # odd slot ld
+    assert L.hfb_dgemm_peer(0, 1000, 32, 64, 1.0, 16, 64, 32, 32, two, 2, 512, 32, None) in (-5, -4)            # TN only (or no driver here)
+    assert L.hfb_peer_barrier(None, 0, 2, 1, 1.0, None) == -1
+    assert L.hfb_peer_barrier(two, 2, 2, 1, 1.0, None) == -1                                                    # rank out of range
+    assert L.hfb_peer_barrier(two, 0, 2, 0, 1.0, None) == -1                                                    # epoch 0 is the initial flag value
+    assert L.hfb_peer_reduce(16, 100, 2, 10, 20, 20, 32, 64, 20, 0, None) == -1                                 # slots overlap
+    assert L.hfb_peer_reduce(16, 210, 2, 10, 20, 21, 32, 64, 20, 0, None) == -2                                 # odd ld
+    assert L.hfb_peer_gather(two, 0, 2, 128, 300, 20, 20, 64, 20, 0, None) == -1                                # blocks do not cover n
+    assert L.hfb_peer_gather(two, 0, 2, 256, 300, 20, 10, 64, 20, 0, None) == -1                                # ld < cols
+    assert L.hfb_peer_alloc(0, None) == -1 and L.hfb_peer_free(None) == -1 and L.hfb_peer_open(None, None) == -1
     assert L.hfb_dgemm_workspace_bytes(0, 128, 16, 4096, 4) == 4 * 128 * 16 * 8
     assert L.hfb_dgemm_auto_splits(0, 4096, 266, 263169) >= 2
 

@@ -390,3 +390,17 @@ def test_dgemm_random_shape_fuzz(K, cuda_device):
         K.dgemm(layout, Ad, Bd, out=out, splits=splits)
         err = float((out - ref).norm() / ref.norm())
         assert err < 1e-13, (trial, layout, M, N, Kd, splits, err)
+
+
+def test_peer_exchange_emulated_ranks_on_one_gpu():
+    """The fused lift + reduce-scatter epilogue (hfb_dgemm_peer), the flag barrier, the fixed-order slot reduction and the
+    gather of hippyflow_b200/peer.py with 2-4 emulated ranks on ONE device (every 'peer' pointer local): bitwise equal to the
+    rank-ordered sum of plain lifts, with and without pipeline chunks.  Runs in a subprocess because a barrier time-out
+    traps the kernel (and the context with it)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "peer_selftest.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "PEER_SELFTEST_OK" in r.stdout, r.stdout[-3000:]
