@@ -632,6 +632,22 @@ def run_ours(args):
         targets = {"cfg5_shard": target_cfg5_shard(hf, K, syn, coll, dev, rank, world, torch, dist, peak),
                    "cfg3_shard": target_cfg3_shard(hf, K, syn, coll, dev, rank, world, torch, dist, peak)}
 
+    # ---- how the (n x m) sketch travelled between the GPUs
+    exchange = None
+    if world > 1:
+        exs = {key: e for key, e in getattr(coll, "_peer_exchanges", {}).items()}
+        mine = [e for key, e in exs.items() if key[0] == n]
+        if mine and mine[0] is not None:
+            e = mine[0]
+            exchange = {"route": "peer", "kernel": "dgemm_dmma_kernel<TN,*,PEER> epilogue st.global on CUDA-IPC peer addresses -> "
+                                 "peer_barrier -> peer_reduce (fixed rank order) -> peer_barrier -> peer_gather (ld.global peer)",
+                        "rows_per_owner": e.block, "verified_against_nccl_rel_err": getattr(e, "verify_err", None),
+                        "nvlink_bytes_pushed_per_rank_per_step": e.n * e.ld * 8.0 * (world - 1) / world,
+                        "nvlink_bytes_pulled_per_rank_per_step": e.n * e.ld * 8.0 * (world - 1) / world,
+                        "nccl_on_data_path": "no (m x m Rayleigh matrix and two m-vectors only)"}
+        else:
+            exchange = {"route": "nccl", "note": "row blocks of the lift, asynchronous allreduce per block (peer route "
+                                 "unavailable or disabled: HFB_PEER_LIFT=%s)" % os.environ.get("HFB_PEER_LIFT", "1")}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -639,7 +655,7 @@ def run_ours(args):
                 "config": config_dict(args.workload, world),
                 "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "cuda_mallocs_in_timed_region": int(new_segments), "clocks": clocks,
-                "parity_full_size": parity_full, "sharded_parity": sharded, "targets": targets,
+                "parity_full_size": parity_full, "sharded_parity": sharded, "exchange": exchange, "targets": targets,
                 "eigenvalues_head": [float(x) for x in d_last[:3]]}
         print(json.dumps(line))
     if world > 1:

@@ -89,9 +89,9 @@ def lib():
         "hfb_peer_open": (i32, [ctypes.c_char_p, ctypes.POINTER(vp)]),
         "hfb_peer_close": (i32, [vp]),
         "hfb_dgemm_peer": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, ctypes.POINTER(vp), i32, i64, i64, vp]),
-        "hfb_peer_barrier": (i32, [ctypes.POINTER(vp), i32, i32, u64, dbl, vp]),
-        "hfb_peer_reduce": (i32, [vp, i64, i32, i64, i64, i64, vp, vp, i64, i32, vp]),
-        "hfb_peer_gather": (i32, [ctypes.POINTER(vp), i32, i32, i64, i64, i64, i64, vp, i64, i32, vp]),
+        "hfb_peer_barrier": (i32, [ctypes.POINTER(vp), i32, i32, u64, dbl, i32, vp]),
+        "hfb_peer_reduce": (i32, [vp, i64, i32, i64, i64, i64, vp, vp, i64, vp]),
+        "hfb_peer_gather": (i32, [ctypes.POINTER(vp), i32, i32, i64, i64, i64, i64, vp, i64, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -717,18 +717,21 @@ def dgemm_peer(A, B, slot_ptrs, block_rows, ld_slot, alpha=1.0):
     _check(rc, "hfb_dgemm_peer")
 
 
-def peer_barrier(flag_ptrs, me, epoch, timeout_s=600.0):
-    _check(lib().hfb_peer_barrier(_ptr_array(flag_ptrs), int(me), len(flag_ptrs), int(epoch), float(timeout_s), _stream()),
-           "hfb_peer_barrier")
+PEER_SIGNAL, PEER_WAIT = 1, 2
 
 
-def peer_reduce(slots_ptr, slot_stride, nranks, rows, cols, ld, reduced_ptr, y_ptr, ldy, max_ctas=0):
+def peer_barrier(flag_ptrs, me, epoch, timeout_s=600.0, mode=PEER_SIGNAL | PEER_WAIT):
+    _check(lib().hfb_peer_barrier(_ptr_array(flag_ptrs), int(me), len(flag_ptrs), int(epoch), float(timeout_s), int(mode),
+                                  _stream()), "hfb_peer_barrier")
+
+
+def peer_reduce(slots_ptr, slot_stride, nranks, rows, cols, ld, reduced_ptr, y_ptr, ldy):
     _check(lib().hfb_peer_reduce(ctypes.c_void_p(slots_ptr), int(slot_stride), int(nranks), int(rows), int(cols), int(ld),
-                                 ctypes.c_void_p(reduced_ptr), ctypes.c_void_p(y_ptr), int(ldy), int(max_ctas), _stream()),
+                                 ctypes.c_void_p(reduced_ptr), ctypes.c_void_p(y_ptr), int(ldy), _stream()),
            "hfb_peer_reduce")
 
 
-def peer_gather(reduced_ptrs, me, block_rows, n, cols, ld, y_ptr, ldy, ctas_per_peer=0):
+def peer_gather(reduced_ptrs, me, block_rows, n, cols, ld, y_ptr, ldy):
     _check(lib().hfb_peer_gather(_ptr_array(reduced_ptrs), int(me), len(reduced_ptrs), int(block_rows), int(n), int(cols),
-                                 int(ld), ctypes.c_void_p(y_ptr), int(ldy), int(ctas_per_peer), _stream()),
+                                 int(ld), ctypes.c_void_p(y_ptr), int(ldy), _stream()),
            "hfb_peer_gather")

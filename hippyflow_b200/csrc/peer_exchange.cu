@@ -35,12 +35,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // r != me).  Thread t publishes flags[t][me] = epoch (release, system scope: every store this stream issued before --
 // the GEMM's peer stores included -- is visible to whoever acquires the flag) and then waits for flags[me][t] >= epoch.
 // Epochs only grow, so no flag is ever reset.  A wait longer than timeout_ns traps (a dead peer must not hang the GPU).
+// mode: HFB_PEER_SIGNAL | HFB_PEER_WAIT (both = a barrier).
 __global__ void peer_barrier_kernel(PeerPtrs flags, int me, int nranks, unsigned long long epoch,
-                                    unsigned long long timeout_ns) {
+                                    unsigned long long timeout_ns, int mode) {
     const int t = threadIdx.x;
     if (t >= nranks) return;
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long*>(flags.p[t]) + me, epoch);
+    if (mode & HFB_PEER_SIGNAL) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(flags.p[t]) + me, epoch);
+    }
+    if (!(mode & HFB_PEER_WAIT)) return;
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(flags.p[me]) + t;
     const unsigned long long t0 = global_timer_ns();
     unsigned int spins = 0;
@@ -200,8 +204,10 @@ extern "C" int hfb_peer_close(void* ptr) {
 }
 
 // ---------------------------------------------------------------------------------------------------------- kernels
-extern "C" int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch, double timeout_s, void* stream_) {
+extern "C" int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch, double timeout_s, int mode,
+                                void* stream_) {
     if (!flag_ptrs || nranks < 1 || nranks > PEER_MAX || me < 0 || me >= nranks || epoch == 0) return HFB_E_BADARG;
+    if (mode < 1 || mode > (HFB_PEER_SIGNAL | HFB_PEER_WAIT)) return HFB_E_BADARG;
     PeerPtrs f;
     memset(&f, 0, sizeof(f));
     for (int r = 0; r < nranks; ++r) {
@@ -209,13 +215,13 @@ extern "C" int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint
         f.p[r] = flag_ptrs[r];
     }
     const unsigned long long tns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ULL;
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(f, me, nranks, (unsigned long long)epoch, tns);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(f, me, nranks, (unsigned long long)epoch, tns, mode);
     ++g_launch_count;
     return (int)cudaGetLastError();
 }
 
 extern "C" int hfb_peer_reduce(const double* slots, int64_t slot_stride, int nranks, int64_t rows, int64_t cols, int64_t ld,
-                               double* reduced, double* Y, int64_t ldy, int max_ctas, void* stream_) {
+                               double* reduced, double* Y, int64_t ldy, void* stream_) {
     if (!slots || !reduced || !Y || nranks < 1 || nranks > PEER_MAX || rows < 0 || cols <= 0 || ld < cols || ldy < cols ||
         slot_stride < rows * ld || cols > 0x7ffffffeLL)
         return HFB_E_BADARG;
@@ -224,20 +230,17 @@ extern "C" int hfb_peer_reduce(const double* slots, int64_t slot_stride, int nra
     if (reinterpret_cast<uintptr_t>(Y) & 7) return HFB_E_ALIGN;
     if (rows == 0) return 0;
     const int y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
-    // max_ctas > 0: narrow launch beside a running GEMM -- few SMs, 1024 threads each (the exchange is latency/NVLink-bound)
-    const int threads = max_ctas > 0 ? 1024 : 256;
     const long long total = rows * ((cols + 1) / 2);
-    long long blocks = (total + threads - 1) / threads;
-    const long long cap = max_ctas > 0 ? max_ctas : 148 * 8;
-    if (blocks > cap) blocks = cap;
-    peer_reduce_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream_>>>(slots, slot_stride, nranks, rows, (int)cols, ld,
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    peer_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(slots, slot_stride, nranks, rows, (int)cols, ld,
                                                                             reduced, Y, ldy, y_vec);
     ++g_launch_count;
     return (int)cudaGetLastError();
 }
 
 extern "C" int hfb_peer_gather(const double* const* reduced_ptrs, int me, int nranks, int64_t block_rows, int64_t n,
-                               int64_t cols, int64_t ld, double* Y, int64_t ldy, int ctas_per_peer, void* stream_) {
+                               int64_t cols, int64_t ld, double* Y, int64_t ldy, void* stream_) {
     if (!reduced_ptrs || !Y || nranks < 1 || nranks > PEER_MAX || me < 0 || me >= nranks || block_rows <= 0 || n <= 0 ||
         cols <= 0 || ld < cols || ldy < cols || cols > 0x7ffffffeLL || (long long)nranks * block_rows < n)
         return HFB_E_BADARG;
@@ -252,12 +255,9 @@ extern "C" int hfb_peer_gather(const double* const* reduced_ptrs, int me, int nr
         f.p[r] = const_cast<double*>(reduced_ptrs[r]);
     }
     const int y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
-    const int threads = ctas_per_peer > 0 ? 1024 : 256;
-    if (ctas_per_peer <= 0) {
-        ctas_per_peer = (148 * 4) / (nranks - 1);
-        if (ctas_per_peer < 1) ctas_per_peer = 1;
-    }
-    peer_gather_kernel<<<dim3((unsigned)ctas_per_peer, (unsigned)(nranks - 1)), threads, 0, (cudaStream_t)stream_>>>(
+    int ctas_per_peer = (148 * 4) / (nranks - 1);   // ~4 CTAs per SM in total: ~10 MB of loads in flight against ~2 us of NVLink latency
+    if (ctas_per_peer < 1) ctas_per_peer = 1;
+    peer_gather_kernel<<<dim3((unsigned)ctas_per_peer, (unsigned)(nranks - 1)), 256, 0, (cudaStream_t)stream_>>>(
         f, me, nranks, block_rows, n, (int)cols, ld, Y, ldy, y_vec);
     ++g_launch_count;
     return (int)cudaGetLastError();

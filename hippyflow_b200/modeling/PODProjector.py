@@ -200,19 +200,20 @@ class PODProjectorFromData:
         t1 = time.time()
         if method == 'randomized':
             d, phi_d, Mphi_d, ratio = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, center, pre)
+            worst = None        # (|mean| / rms fluctuation)^2 summed over the ranks: ONE scalar exchange serves both checks
             if isinstance(center, str):
                 # lazily centred solve: the mean is known now; its first apply lost ~eps * ratio digits, so redo the solve
                 # with the known center when the mean is not small against the fluctuations
                 center = u_shift_d = self._last_cov.center
-                worst = ratio.reshape(1).clone()
-                collective.allReduce(worst, 'sum')
-                if float(worst) > SampleCovariance.LAZY_MAX_RATIO * collective.size():
+                worst = float(collective.allReduce(ratio.reshape(1).clone(), 'sum'))
+                if worst > SampleCovariance.LAZY_MAX_RATIO * collective.size():
                     self.shift_route = 'implicit (lazy mean redone)'
                     d, phi_d, Mphi_d, ratio = self._randomized(Xt, Md, u_rank, oversampling, Omega, collective, faithful, center, None)
+                    worst = None
             if ratio is not None:
-                worst = ratio.reshape(1).clone()
-                collective.allReduce(worst, 'sum')
-                if float(worst) > self.IMPLICIT_SHIFT_MAX_RATIO * collective.size():
+                if worst is None:
+                    worst = float(collective.allReduce(ratio.reshape(1).clone(), 'sum'))
+                if worst > self.IMPLICIT_SHIFT_MAX_RATIO * collective.size():
                     # the mean dominates the fluctuations: redo with the data shifted explicitly, as the reference does
                     Xt = self._shift_explicit(Xt, center, owns or overwrite_data)
                     center = None

@@ -96,7 +96,6 @@ class SampleCovarianceOperator:
             self.cov.finish_lazy(Yt, self.collective, "avg")
 
     PEER_LIFT = __import__("os").environ.get("HFB_PEER_LIFT", "1") != "0"
-    PEER_CHUNKS = int(__import__("os").environ.get("HFB_PEER_CHUNKS", 4))
     PEER_VERIFY_TOL = 1e-11
 
     def _peer_exchange(self, n, ld, ncols):
@@ -105,7 +104,7 @@ class SampleCovarianceOperator:
         if not self.PEER_LIFT or getattr(self.collective, "_backend", None) != "nccl":
             return None
         cache = self.collective.__dict__.setdefault("_peer_exchanges", {})
-        key = (n, ld, ncols, self.PEER_CHUNKS)
+        key = (n, ld, ncols)
         if key not in cache:
             from ..peer import PeerExchange
             if len(cache) >= 4:                                   # bound the device memory held by stale shapes
@@ -113,7 +112,7 @@ class SampleCovarianceOperator:
                     if ex is not None:
                         ex.close()
                 cache.clear()
-            cache[key] = PeerExchange.create(self.collective.group, self.device, n, ld, ncols, self.PEER_CHUNKS)
+            cache[key] = PeerExchange.create(self.collective.group, self.device, n, ld, ncols)
         return cache[key]
 
     def _lift_peer(self, GW, Y, Yt, scale, lazy):
@@ -150,7 +149,7 @@ class SampleCovarianceOperator:
                 import warnings
                 warnings.warn("hippyflow_b200: NVLink peer exchange disagrees with the NCCL allreduce (rel. error %.2e); "
                               "peer route disabled" % float(err))
-                self.collective._peer_exchanges[(Yt.shape[0], ld, ncols, self.PEER_CHUNKS)] = None
+                self.collective._peer_exchanges[(Yt.shape[0], ld, ncols)] = None
                 ex.close()
                 Yv.copy_(rv)
         if lazy:

@@ -8,8 +8,10 @@ owns those rows (reduce-scatter by push over NVLink, ``hfb_dgemm_peer``), the ow
 order, and every rank pulls the reduced blocks of the others (all-gather).  No NCCL call touches the (n x m) block; the
 process group is used once, to swap the CUDA IPC handles of the buffers.
 
-The rows are cut into pipeline chunks of whole GEMM waves: while the GEMM of chunk c+1 runs on the main stream, a narrow
-reduce + gather of chunk c runs beside it on a side stream (the exchange is NVLink-bound, a few SMs saturate it)."""
+Measured on 2 x B200 at the cfg2 shard (profiles/r02_peer_lift_2gpu.json): GEMM alone 16.36 ms, fused lift + exchange
+17.23 ms, lift in four row blocks with NCCL allreduces 17.28 ms.  Cutting the lift into pipeline chunks whose reduce + gather
+run on a side stream beside the next chunk's GEMM was measured SLOWER (18.1 ms at four chunks: a GEMM chunk sized to whole
+waves of 148 SMs needs one more wave once the side kernels hold a few SMs), so the exchange is one launch sequence."""
 import os
 import socket
 import warnings
@@ -23,73 +25,45 @@ try:
 except Exception:  # pragma: no cover
     dist = None
 
-_NT = (4, 9, 10, 14, 16, 17, 18)        # column-tile widths of the DMMA GEMM in 8-column units (csrc/dgemm_api.cu:choose_nt)
 _FLAG_BYTES = 256
 
 
-def _n_tiles(ncols):
-    best = None
-    for nt in _NT:
-        bn = 8 * nt
-        tiles = -(-ncols // bn)
-        key = (tiles * bn, tiles)
-        if best is None or key < best[0]:
-            best = (key, tiles)
-    return best[1]
-
-
-def plan_chunks(n, ncols, nchunk, nranks, sms=148):
-    """Row chunks [(lo, hi, block_rows)] of an (n x ncols) lift: whole waves of 128-row GEMM tiles per chunk (a chunk that
-    ends inside a wave leaves SMs idle at the launch boundary) and, inside a chunk, one block of ``block_rows`` rows
-    (a multiple of 128) per owning rank."""
-    m_tiles = -(-n // 128)
-    nt = _n_tiles(ncols)
-    waves = -(-(m_tiles * nt) // sms)
-    nchunk = max(1, min(int(nchunk), waves))
-    chunks, lo_tile = [], 0
-    for c in range(nchunk):
-        w = waves // nchunk + (1 if c < waves % nchunk else 0)
-        t = (w * sms) // nt
-        hi_tile = m_tiles if c == nchunk - 1 else min(m_tiles, lo_tile + t)
-        if hi_tile > lo_tile:
-            lo, hi = lo_tile * 128, min(n, hi_tile * 128)
-            block = -(-(-(-(hi - lo) // nranks)) // 128) * 128
-            chunks.append((lo, hi, block))
-        lo_tile = hi_tile
-    return chunks
+def block_rows_for(n, nranks):
+    """Rows per owning rank: ceil(n / nranks) rounded up to the 128-row GEMM tile, so a CTA's tile has ONE destination."""
+    return -(-(-(-int(n) // int(nranks))) // 128) * 128
 
 
 class PeerExchange:
-    """Exchange buffers of one process group for lifts of up to ``n`` rows with leading dimension ``ld``.
+    """Exchange buffer of one rank (flags | P slots | reduced block) plus the peer-mapped addresses of the other ranks'
+    buffers, for lifts with ``n`` rows, ``ncols`` columns and leading dimension ``ld``.
 
     Construction is COLLECTIVE over the group (IPC handles are all-gathered); ``PeerExchange.create`` returns None on every
     rank when any rank cannot take part (different hosts, no peer access, allocation failure), so the caller falls back to
     the NCCL route on all ranks together."""
 
-    def __init__(self):
-        self.base = None
-        self.own = None
+    def __init__(self, size, me, device, n, ld, ncols, timeout_s):
+        self.size, self.me, self.device = int(size), int(me), device
+        self.n, self.ld, self.ncols = int(n), int(ld), int(ncols)
+        self.block = block_rows_for(n, size)
+        self.nbytes = _FLAG_BYTES + (self.size + 1) * self.block * self.ld * 8
+        self.epoch = 0
+        self.timeout_s = float(timeout_s)
+        self.base = None          # base address of every rank's buffer as seen from this process
+        self.own = None           # this rank's allocation (freed by close())
+        self.local = False        # True: all buffers live in this process (single-GPU emulation), nothing to unmap
 
     # ------------------------------------------------------------------------------------------------ construction
     @classmethod
-    def create(cls, group, device, n, ld, ncols, nchunk):
+    def create(cls, group, device, n, ld, ncols):
         if dist is None or not dist.is_initialized() or dist.get_backend(group) != "nccl":
             return None
         size, me = dist.get_world_size(group), dist.get_rank(group)
         if size < 2 or size > K.PEER_MAX_RANKS:
             return None
-        self = cls()
-        self.group, self.size, self.me, self.device = group, size, me, device
-        self.n, self.ld, self.ncols = int(n), int(ld), int(ncols)
-        self.chunks = plan_chunks(n, ncols, nchunk, size)
-        self.block_max = max(b for _, _, b in self.chunks)
-        self.region = (size + 1) * self.block_max * ld           # doubles per chunk: P slots + the reduced block
-        nbytes = _FLAG_BYTES + len(self.chunks) * self.region * 8
-        self.epoch = 0
-        self.timeout_s = float(os.environ.get("HFB_PEER_TIMEOUT_S", 600.0))
+        self = cls(size, me, device, n, ld, ncols, os.environ.get("HFB_PEER_TIMEOUT_S", 600.0))
         ok, handle, err = 1, b"", ""
         try:
-            self.own = K.peer_alloc(nbytes)
+            self.own = K.peer_alloc(self.nbytes)
             handle = K.peer_get_handle(self.own)
         except Exception as e:                                   # noqa: BLE001 -- any failure means "no peer route"
             ok, err = 0, repr(e)
@@ -117,44 +91,28 @@ class PeerExchange:
             if err:
                 warnings.warn("hippyflow_b200: NVLink peer exchange unavailable (%s); using the NCCL route" % err)
             return None
-        self.side = torch.cuda.Stream(device=device, priority=-1)
         return self
 
     @classmethod
-    def local_group(cls, nranks, device, n, ld, ncols, nchunk, timeout_s=30.0):
-        """``nranks`` exchange objects inside ONE process whose buffers all live on ``device`` -- the same kernels and
-        addresses as the multi-process case with every 'peer' pointer local.  Test aid for single-GPU boxes: each emulated
-        rank must run its ``lift_allreduce`` on a stream of its own (the barrier kernels of the ranks wait for each other)."""
-        chunks = plan_chunks(n, ncols, nchunk, nranks)
-        block_max = max(b for _, _, b in chunks)
-        region = (nranks + 1) * block_max * ld
-        owns = [K.peer_alloc(_FLAG_BYTES + len(chunks) * region * 8) for _ in range(nranks)]
-        group = []
-        for g in range(nranks):
-            self = cls()
-            self.group, self.size, self.me, self.device = None, nranks, g, device
-            self.n, self.ld, self.ncols = int(n), int(ld), int(ncols)
-            self.chunks, self.block_max, self.region = chunks, block_max, region
-            self.epoch, self.timeout_s = 0, float(timeout_s)
-            self.base, self.own = list(owns), owns[g]
-            self.side = torch.cuda.Stream(device=device, priority=-1)
-            self._local = True
-            group.append(self)
+    def local_group(cls, nranks, device, n, ld, ncols, timeout_s=20.0):
+        """``nranks`` exchange objects inside ONE process whose buffers all live on ``device``: the same kernels and address
+        arithmetic as the multi-process case with every 'peer' pointer local.  Test aid for single-GPU boxes; drive the
+        phases (``push`` / ``signal`` / ``wait`` / ``reduce`` / ``gather``) rank by rank on one stream."""
+        group = [cls(nranks, g, device, n, ld, ncols, timeout_s) for g in range(nranks)]
+        owns = [K.peer_alloc(group[0].nbytes) for _ in range(nranks)]
+        for g, ex in enumerate(group):
+            ex.base, ex.own, ex.local = list(owns), owns[g], True
         return group
 
-    def fits(self, n, ld, ncols, nchunk):
-        return (self.n, self.ld, self.ncols) == (int(n), int(ld), int(ncols)) and \
-            self.chunks == plan_chunks(n, ncols, nchunk, self.size)
-
     def close(self):
-        if self.base is not None:
+        if self.base is not None and not self.local:
             for r, p in enumerate(self.base):
-                if p is not None and r != self.me and not getattr(self, "_local", False):
+                if p is not None and r != self.me:
                     try:
                         K.peer_close(p)
                     except Exception:                            # noqa: BLE001
                         pass
-            self.base = None
+        self.base = None
         if self.own is not None:
             try:
                 K.peer_free(self.own)
@@ -163,43 +121,49 @@ class PeerExchange:
             self.own = None
 
     # ------------------------------------------------------------------------------------------------ addresses
-    def _slot(self, rank, chunk, slot):
-        """Address of slot ``slot`` of chunk ``chunk`` inside rank ``rank``'s buffer (slot == size: the reduced block)."""
-        return self.base[rank] + _FLAG_BYTES + 8 * (chunk * self.region + slot * self.block_max * self.ld)
+    def _slot(self, rank, slot):
+        """Address of slot ``slot`` inside rank ``rank``'s buffer (slot == size: the reduced block)."""
+        return self.base[rank] + _FLAG_BYTES + 8 * slot * self.block * self.ld
 
-    def _barrier(self):
+    # ------------------------------------------------------------------------------------------------ phases
+    def push(self, Xt, W, alpha):
+        """Lift GEMM alpha * Xt^T W whose epilogue stores the rows of block o into slot ``me`` of rank o's buffer."""
+        assert Xt.shape[1] == self.n and W.shape[1] == self.ncols
+        K.dgemm_peer(Xt, W, [self._slot(o, self.me) for o in range(self.size)], self.block, self.ld, alpha)
+
+    def signal(self):
+        self.epoch += 1
+        K.peer_barrier(self.base, self.me, self.epoch, self.timeout_s, K.PEER_SIGNAL)
+
+    def wait(self):
+        K.peer_barrier(self.base, self.me, self.epoch, self.timeout_s, K.PEER_WAIT)
+
+    def barrier(self):
         self.epoch += 1
         K.peer_barrier(self.base, self.me, self.epoch, self.timeout_s)
 
+    def reduce(self, Y):
+        """Owner's fixed-order sum of its P slots -> its reduced block and its own rows of Y."""
+        lo = self.me * self.block
+        rows = max(0, min(self.block, self.n - lo))
+        if rows > 0:
+            ldy = K._ld(Y)
+            K.peer_reduce(self._slot(self.me, 0), self.block * self.ld, self.size, rows, self.ncols, self.ld,
+                          self._slot(self.me, self.size), Y.data_ptr() + 8 * lo * ldy, ldy)
+
+    def gather(self, Y):
+        """Pull the reduced blocks of the other ranks into Y."""
+        K.peer_gather([self._slot(o, self.size) for o in range(self.size)], self.me, self.block, self.n, self.ncols, self.ld,
+                      Y.data_ptr(), K._ld(Y))
+
     # ------------------------------------------------------------------------------------------------ the exchange
     def lift_allreduce(self, Xt, W, Y, alpha):
-        """Y[:, :ncols] = sum over ranks of alpha * Xt^T W  (Xt: (R, n) local rows, W: (R, ncols), Y: (n, >= ncols) view
-        with leading dimension self.ld).  COLLECTIVE: every rank of the group calls it with the same shapes."""
-        P, me, ld, ncols = self.size, self.me, self.ld, self.ncols
-        assert Xt.shape[1] == self.n and W.shape[1] == ncols and Y.shape[0] == self.n and K._ld(Y) >= ncols
-        ldy = K._ld(Y)
-        main = torch.cuda.current_stream()
-        pipelined = len(self.chunks) > 1
-        if pipelined:
-            self.side.wait_stream(main)                           # Y and the buffers of the previous exchange are free
-        for c, (lo, hi, block) in enumerate(self.chunks):
-            last = c == len(self.chunks) - 1
-            K.dgemm_peer(Xt[:, lo:hi], W, [self._slot(o, c, me) for o in range(P)], block, ld, alpha)
-            if pipelined:
-                ev = torch.cuda.Event()
-                ev.record(main)
-                self.side.wait_event(ev)
-            with torch.cuda.stream(self.side if pipelined else main):
-                self._barrier()                                   # every rank's tiles of this chunk have landed
-                own_lo = lo + me * block
-                rows = max(0, min(block, hi - own_lo))
-                narrow = pipelined and not last
-                if rows > 0:
-                    K.peer_reduce(self._slot(me, c, 0), self.block_max * ld, P, rows, ncols, ld, self._slot(me, c, P),
-                                  Y.data_ptr() + 8 * own_lo * ldy, ldy, max_ctas=8 if narrow else 0)
-                self._barrier()                                   # every owner's block is reduced
-                K.peer_gather([self._slot(o, c, P) for o in range(P)], me, block, hi - lo, ncols, ld,
-                              Y.data_ptr() + 8 * lo * ldy, ldy, ctas_per_peer=max(1, 8 // (P - 1)) if narrow else 0)
-        if pipelined:
-            main.wait_stream(self.side)
+        """Y[:, :ncols] = sum over ranks of alpha * Xt^T W  (Xt: (R, n) local rows, W: (R, ncols), Y: (n, ncols) view).
+        COLLECTIVE: every rank of the group calls it with the same shapes; asynchronous on the current stream."""
+        assert Y.shape[0] == self.n and K._ld(Y) >= self.ncols
+        self.push(Xt, W, alpha)
+        self.barrier()            # every rank's tiles have landed in the owners' slots
+        self.reduce(Y)
+        self.barrier()            # every owner's block is reduced
+        self.gather(Y)
         return Y

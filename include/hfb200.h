@@ -274,7 +274,7 @@ int hfb_measure_dmma_peak(double* scratch, size_t scratch_bytes, double* tflops_
  * stored-data operators of PODProjector.py:360-363 / activeSubspaceProjector.py:427-431.
  *
  * Each rank owns one exchange buffer (hfb_peer_alloc: cudaMalloc'd, zeroed, shareable through CUDA IPC) laid out by the
- * caller as  [flags: 16 x uint64 | slots: nranks x (block_rows x ld) | reduced: block_rows x ld]  per pipeline chunk;
+ * caller as  [flags: 16 x uint64 | slots: nranks x (block_rows x ld) | reduced: block_rows x ld];
  * the handles (hfb_peer_get_handle, 64 bytes) are exchanged out of band (torch.distributed all_gather_object) and mapped
  * with hfb_peer_open.  One exchange of rows [0, n) split into nranks blocks of block_rows (a multiple of 128) is
  *   1. hfb_dgemm_peer      rank g's partial tile of block o is stored from the accumulators straight into slot g of rank
@@ -288,13 +288,16 @@ int hfb_measure_dmma_peak(double* scratch, size_t scratch_bytes, double* tflops_
  * NVLink bytes per rank and exchange: (nranks-1)/nranks * n * ld * 8 pushed + the same pulled (the two halves of a
  * bandwidth-optimal allreduce); the push overlaps the GEMM tile by tile.
  * hfb_peer_barrier: flag_ptrs[r] = address of rank r's 16 flag words (peer-mapped for r != me); epoch must grow with every
- * call and be the same on all ranks; a wait longer than timeout_s (0 = no limit) traps the kernel.
+ * call and be the same on all ranks; a wait longer than timeout_s (0 = no limit) traps the kernel.  mode = HFB_PEER_SIGNAL
+ * (publish only), HFB_PEER_WAIT (wait only) or both (a barrier).
  * slot_ptrs[o] (hfb_dgemm_peer) = address of THIS rank's slot inside rank o's buffer; ld_slot = ld of slots and `reduced`.
- * hfb_peer_reduce: Y points at the owner's first row.  max_ctas / ctas_per_peer <= 0: full-grid defaults; small values
- * keep the kernel narrow when it runs beside the next chunk's GEMM.
+ * hfb_peer_reduce: Y points at the owner's first row.
+ * Measured (2 x B200, cfg2 shard, profiles/r02_peer_lift_2gpu.json): lift GEMM alone 16.36 ms, fused lift + exchange 17.23 ms.
  */
 #define HFB_PEER_HANDLE_BYTES 64
 #define HFB_PEER_MAX_RANKS 16
+#define HFB_PEER_SIGNAL 1
+#define HFB_PEER_WAIT 2
 int hfb_peer_alloc(size_t bytes, void** ptr);
 int hfb_peer_free(void* ptr);
 int hfb_peer_get_handle(void* ptr, unsigned char* handle64);
@@ -303,11 +306,11 @@ int hfb_peer_close(void* ptr);
 int hfb_dgemm_peer(int layout, int64_t M, int64_t N, int64_t K, double alpha,
                    const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* const* slot_ptrs, int nranks, int64_t block_rows, int64_t ld_slot, void* stream);
-int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch, double timeout_s, void* stream);
+int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch, double timeout_s, int mode, void* stream);
 int hfb_peer_reduce(const double* slots, int64_t slot_stride, int nranks, int64_t rows, int64_t cols, int64_t ld,
-                    double* reduced, double* Y, int64_t ldy, int max_ctas, void* stream);
+                    double* reduced, double* Y, int64_t ldy, void* stream);
 int hfb_peer_gather(const double* const* reduced_ptrs, int me, int nranks, int64_t block_rows, int64_t n, int64_t cols,
-                    int64_t ld, double* Y, int64_t ldy, int ctas_per_peer, void* stream);
+                    int64_t ld, double* Y, int64_t ldy, void* stream);
 
 #ifdef __cplusplus
 }

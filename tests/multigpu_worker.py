@@ -49,8 +49,7 @@ def sharded_mean_shift_case(hf, dev, coll, rank, world):
 
 def peer_exchange_case(hf, dev, coll, rank, world):
     """The fused lift + NVLink exchange (hippyflow_b200/peer.py) against the lift GEMM followed by an NCCL allreduce:
-    equal to round-off of the summation order, bitwise identical on all ranks and from call to call, with one chunk and
-    with pipeline chunks on the side stream; then the operator route (first use verifies itself against NCCL)."""
+    equal to round-off of the summation order, bitwise identical on all ranks and from call to call; then the operator route (first use verifies itself against NCCL)."""
     from hippyflow_b200 import _lib as K
     from hippyflow_b200.peer import PeerExchange
     n, R, ncols = 66049, 192, 67
@@ -60,25 +59,23 @@ def peer_exchange_case(hf, dev, coll, rank, world):
     ref = K.dgemm(K.HFB_TN, X, W, alpha=0.5)
     refc = ref.contiguous()
     dist.all_reduce(refc)
-    for nchunk in (1, 3):
-        ex = PeerExchange.create(None, dev, n, K._ld(ref), ncols, nchunk)
-        assert ex is not None, "peer exchange unavailable on an NVLink box"
-        assert len(ex.chunks) == nchunk
-        Y = K.padded_zeros(n, ncols, dev)
-        first = None
-        for rep in range(3):
-            Y.zero_()
-            ex.lift_allreduce(X, W, Y, 0.5)
-            torch.cuda.synchronize()
-            err = float((Y - refc).abs().max() / refc.abs().max())
-            assert err < 1e-13, (nchunk, rep, err)
-            first = Y.clone() if first is None else first
-            assert torch.equal(Y, first), "exchange not reproducible from call to call"
-        gathered = [torch.empty_like(first.contiguous()) for _ in range(world)]
-        dist.all_gather(gathered, first.contiguous())
-        for t in gathered:
-            assert torch.equal(t, gathered[0]), "ranks hold different bits"
-        ex.close()
+    ex = PeerExchange.create(None, dev, n, K._ld(ref), ncols)
+    assert ex is not None, "peer exchange unavailable on an NVLink box"
+    Y = K.padded_zeros(n, ncols, dev)
+    first = None
+    for rep in range(3):
+        Y.zero_()
+        ex.lift_allreduce(X, W, Y, 0.5)
+        torch.cuda.synchronize()
+        err = float((Y - refc).abs().max() / refc.abs().max())
+        assert err < 1e-13, (rep, err)
+        first = Y.clone() if first is None else first
+        assert torch.equal(Y, first), "exchange not reproducible from call to call"
+    gathered = [torch.empty_like(first.contiguous()) for _ in range(world)]
+    dist.all_gather(gathered, first.contiguous())
+    for t in gathered:
+        assert torch.equal(t, gathered[0]), "ranks hold different bits"
+    ex.close()
     # operator route: SampleCovarianceOperator.lift_reduced takes the peer route and verified it against NCCL on first use
     exs = [e for e in getattr(coll, "_peer_exchanges", {}).values() if e is not None]
     assert exs and all(e.verified and e.verify_err < 1e-12 for e in exs), "operator lifts did not take the peer route"

@@ -79,13 +79,14 @@ def test_argument_validation_without_gpu():
     assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, bad, 2, 512, 32, None) == -2                # slot not 16-byte aligned
     assert L.hfb_dgemm_peer(1, 1000, 32, 64, 1.0, 16, 1000, 32, 32, two, 2, 512, 33, None) == -2                # odd slot ld
     assert L.hfb_dgemm_peer(0, 1000, 32, 64, 1.0, 16, 64, 32, 32, two, 2, 512, 32, None) in (-5, -4)            # TN only (or no driver here)
-    assert L.hfb_peer_barrier(None, 0, 2, 1, 1.0, None) == -1
-    assert L.hfb_peer_barrier(two, 2, 2, 1, 1.0, None) == -1                                                    # rank out of range
-    assert L.hfb_peer_barrier(two, 0, 2, 0, 1.0, None) == -1                                                    # epoch 0 is the initial flag value
-    assert L.hfb_peer_reduce(16, 100, 2, 10, 20, 20, 32, 64, 20, 0, None) == -1                                 # slots overlap
-    assert L.hfb_peer_reduce(16, 210, 2, 10, 20, 21, 32, 64, 20, 0, None) == -2                                 # odd ld
-    assert L.hfb_peer_gather(two, 0, 2, 128, 300, 20, 20, 64, 20, 0, None) == -1                                # blocks do not cover n
-    assert L.hfb_peer_gather(two, 0, 2, 256, 300, 20, 10, 64, 20, 0, None) == -1                                # ld < cols
+    assert L.hfb_peer_barrier(None, 0, 2, 1, 1.0, 3, None) == -1
+    assert L.hfb_peer_barrier(two, 2, 2, 1, 1.0, 3, None) == -1                                                 # rank out of range
+    assert L.hfb_peer_barrier(two, 0, 2, 0, 1.0, 3, None) == -1                                                 # epoch 0 is the initial flag value
+    assert L.hfb_peer_barrier(two, 0, 2, 1, 1.0, 0, None) == -1                                                 # neither signal nor wait
+    assert L.hfb_peer_reduce(16, 100, 2, 10, 20, 20, 32, 64, 20, None) == -1                                    # slots overlap
+    assert L.hfb_peer_reduce(16, 210, 2, 10, 20, 21, 32, 64, 20, None) == -2                                    # odd ld
+    assert L.hfb_peer_gather(two, 0, 2, 128, 300, 20, 20, 64, 20, None) == -1                                   # blocks do not cover n
+    assert L.hfb_peer_gather(two, 0, 2, 256, 300, 20, 10, 64, 20, None) == -1                                   # ld < cols
     assert L.hfb_peer_alloc(0, None) == -1 and L.hfb_peer_free(None) == -1 and L.hfb_peer_open(None, None) == -1
     assert L.hfb_dgemm_workspace_bytes(0, 128, 16, 4096, 4) == 4 * 128 * 16 * 8
     assert L.hfb_dgemm_auto_splits(0, 4096, 266, 263169) >= 2

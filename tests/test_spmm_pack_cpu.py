@@ -115,17 +115,10 @@ def test_fragment_records_limits():
         K.csr_pack_clusters_frag(M.indptr, M.indices, M.data, order, cptr, 16, 8)
 
 
-def test_peer_exchange_chunk_plan():
-    """Row chunks of the fused lift + exchange (hippyflow_b200/peer.py): contiguous cover of the rows, chunk boundaries on
-    128-row GEMM tiles, whole waves per chunk, owner blocks that are multiples of 128 and cover each chunk."""
-    from hippyflow_b200.peer import plan_chunks, _n_tiles
-    for n, ncols, nchunk, P in [(263169, 267, 4, 8), (263169, 267, 1, 8), (1002001, 267, 4, 8), (65536, 211, 4, 8),
-                                (5041, 19, 4, 2), (66049, 66, 3, 2), (40000, 138, 2, 4), (130, 8, 4, 16)]:
-        ch = plan_chunks(n, ncols, nchunk, P)
-        assert ch[0][0] == 0 and ch[-1][1] == n and len(ch) <= nchunk
-        for (lo, hi, b), nxt in zip(ch, ch[1:] + [None]):
-            assert lo % 128 == 0 and hi > lo and b % 128 == 0 and b * P >= hi - lo
-            if nxt is not None:
-                assert nxt[0] == hi and hi % 128 == 0
-                assert ((hi - lo) // 128 * _n_tiles(ncols)) % 148 < _n_tiles(ncols)      # ends on a wave boundary
-    assert _n_tiles(266) == 2 and _n_tiles(267) == 2 and _n_tiles(138) == 1 and _n_tiles(32) == 1
+def test_peer_exchange_block_rows():
+    """Owner blocks of the fused lift + exchange (hippyflow_b200/peer.py): multiples of the 128-row GEMM tile that cover the rows."""
+    from hippyflow_b200.peer import block_rows_for
+    for n, P in [(263169, 8), (263169, 2), (1002001, 8), (65536, 8), (5041, 2), (130, 16), (128, 1)]:
+        b = block_rows_for(n, P)
+        assert b % 128 == 0 and b * P >= n and (b - 128) * P < n
+    assert block_rows_for(263169, 8) == 33024

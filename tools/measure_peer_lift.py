@@ -1,6 +1,5 @@
 """Times the sketch lift + exchange at a benchmark shape under torchrun (one rank per GPU):
-plain lift GEMM (no exchange) | lift in row blocks + NCCL allreduce (r1/r2 route) | fused lift + NVLink peer exchange with
-1..8 pipeline chunks.  Prints one JSON line on rank 0 (times = max over ranks of the CUDA-event mean per call)."""
+plain lift GEMM (no exchange) | lift in row blocks + NCCL allreduce (r1/r2 route) | fused lift + NVLink peer exchange (and its phases alone).  Prints one JSON line on rank 0 (times = max over ranks of the CUDA-event mean per call)."""
 import json
 import os
 import sys
@@ -55,15 +54,17 @@ def main():
     for nchunk in (1, 4):
         out["nccl_chunks%d_ms" % nchunk] = timed(lambda: op._lift_nccl(W, Y, Yt, scale, False, nchunk), reps, dev)
     ref = Yt.clone()
-    for nchunk in [int(c) for c in os.environ.get("PL_CHUNKS", "1,2,4,7").split(",")]:
-        ex = PeerExchange.create(None, dev, n, K._ld(Yt), ncols, nchunk)
-        if ex is None:
-            out["peer_chunks%d_ms" % nchunk] = None
-            continue
-        out["peer_chunks%d_ms" % nchunk] = timed(lambda: ex.lift_allreduce(X, W, Yt, scale), reps, dev)
-        err = float((Yt - ref).abs().max() / ref.abs().max())
-        out["peer_chunks%d_err" % nchunk] = err
-        out["peer_chunks%d_plan" % nchunk] = len(ex.chunks)
+    ex = PeerExchange.create(None, dev, n, K._ld(Yt), ncols)
+    if ex is None:
+        out["peer_ms"] = None
+    else:
+        out["peer_ms"] = timed(lambda: ex.lift_allreduce(X, W, Yt, scale), reps, dev)
+        out["peer_err_vs_nccl"] = float((Yt - ref).abs().max() / ref.abs().max())
+        # phases alone (each rank times its own kernels; the barriers absorb the skew)
+        out["peer_push_gemm_ms"] = timed(lambda: ex.push(X, W, scale), reps, dev)
+        out["peer_reduce_ms"] = timed(lambda: ex.reduce(Yt), reps, dev)
+        out["peer_gather_ms"] = timed(lambda: ex.gather(Yt), reps, dev)
+        out["peer_barrier_ms"] = timed(lambda: ex.barrier(), reps, dev)
         ex.close()
     nbytes = n * K._ld(Yt) * 8
     out["exchange_bytes_per_rank_each_way"] = nbytes * (world - 1) / world

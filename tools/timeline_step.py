@@ -4,8 +4,10 @@ Writes gpurun_out/<tag>_timeline.json and prints a summary.  Development aid: nu
 not bench values; the SHARES and the gap list are what matters.
 
     python tools/timeline_step.py [workload] [tag]
+    python -m torch.distributed.run --nproc-per-node N ... tools/timeline_step.py [workload] [tag]   (rank 0 profiles)
 """
 import json
+import os
 import sys
 import time
 
@@ -19,16 +21,23 @@ from hippyflow_b200 import synthetic as syn
 
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
 tag = sys.argv[2] if len(sys.argv) > 2 else "r02"
-dev = torch.device("cuda:0")
+world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+coll = hf.NullCollective()
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    coll = hf.TorchCollective()
 n, n_loc, k, p = wl["n"], wl["n_loc"], wl["rank"], wl["oversampling"]
 M = syn.p1_mass_matrix_for(n)
 proj = hf.PODProjectorFromData(None, M_output=M, device=dev)
-Xt = syn.snapshots_device(n, n_loc, dev, r0=wl["r0"], seed=7)
+Xt = syn.snapshots_device(n, n_loc, dev, r0=wl["r0"], seed=7, row_offset=rank * n_loc)
 
 
 def step():
     return proj.construct_subspace(Xt, k, shifted=True, method="randomized", oversampling=p, return_device=True,
-                                   overwrite_data=True)
+                                   overwrite_data=True, collective=coll)
 
 
 for _ in range(4):
@@ -44,6 +53,11 @@ print("step wall (no profiler): %.2f ms" % wall)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+    if rank != 0:
+        dist.destroy_process_group()
+        sys.exit(0)
 ev = prof.events()
 gpu = sorted([(e.time_range.start, e.time_range.end, e.name) for e in ev if e.device_type == torch.autograd.DeviceType.CUDA],
              key=lambda x: x[0])
@@ -78,3 +92,5 @@ for name, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:25]:
 json.dump({"wall_ms_no_profiler": wall, "gpu_span_ms": span, "gpu_busy_ms": busy / 1e3, "gaps": gaps[:60],
            "kernels": [{"start_ms": (s - T0) / 1e3, "dur_us": e - s, "name": nm[:90]} for s, e, nm in gpu]},
           open("gpurun_out/%s_timeline.json" % tag, "w"), indent=0)
+if world > 1:
+    dist.destroy_process_group()
