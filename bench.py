@@ -639,12 +639,13 @@ def run_ours(args):
         mine = [e for key, e in exs.items() if key[0] == n]
         if mine and mine[0] is not None:
             e = mine[0]
-            exchange = {"route": "peer", "kernel": "dgemm_dmma_kernel<TN,*,PEER> epilogue st.global on CUDA-IPC peer addresses -> "
-                                 "peer_barrier -> peer_reduce (fixed rank order) -> peer_barrier -> peer_gather (ld.global peer)",
+            exchange = {"route": "peer",
+                        "kernels": "dgemm_dmma_kernel<TN,*,PEER>: 256-bit st.global of every tile into the owner's slot (CUDA-IPC peer "
+                                   "address) -> peer_barrier -> peer_reduce_bcast: fixed-rank-order sum, stored into every rank's "
+                                   "result block over NVLink -> peer_barrier; the solver adopts the result block as its sketch",
                         "rows_per_owner": e.block, "verified_against_nccl_rel_err": getattr(e, "verify_err", None),
-                        "nvlink_bytes_pushed_per_rank_per_step": e.n * e.ld * 8.0 * (world - 1) / world,
-                        "nvlink_bytes_pulled_per_rank_per_step": e.n * e.ld * 8.0 * (world - 1) / world,
-                        "nccl_on_data_path": "no (m x m Rayleigh matrix and two m-vectors only)"}
+                        "nvlink_bytes_pushed_per_rank_per_step": 2 * e.n * e.ld * 8.0 * (world - 1) / world,
+                        "nccl_on_data_path": "no (m x m Rayleigh matrix, one m-vector and one scalar only)"}
         else:
             exchange = {"route": "nccl", "note": "row blocks of the lift, asynchronous allreduce per block (peer route "
                                  "unavailable or disabled: HFB_PEER_LIFT=%s)" % os.environ.get("HFB_PEER_LIFT", "1")}

@@ -90,8 +90,7 @@ def lib():
         "hfb_peer_close": (i32, [vp]),
         "hfb_dgemm_peer": (i32, [i32, i64, i64, i64, dbl, vp, i64, vp, i64, ctypes.POINTER(vp), i32, i64, i64, vp]),
         "hfb_peer_barrier": (i32, [ctypes.POINTER(vp), i32, i32, u64, dbl, i32, vp]),
-        "hfb_peer_reduce": (i32, [vp, i64, i32, i64, i64, i64, vp, vp, i64, vp]),
-        "hfb_peer_gather": (i32, [ctypes.POINTER(vp), i32, i32, i64, i64, i64, i64, vp, i64, vp]),
+        "hfb_peer_reduce_bcast": (i32, [vp, i64, i32, i32, i64, i64, i64, ctypes.POINTER(vp), i64, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -115,7 +114,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_jacobi_svd_max_elems",
             "hfb_jacobi_svd_batched",
             "hfb_peer_alloc", "hfb_peer_free", "hfb_peer_get_handle", "hfb_peer_open", "hfb_peer_close", "hfb_dgemm_peer",
-            "hfb_peer_barrier", "hfb_peer_reduce", "hfb_peer_gather"]
+            "hfb_peer_barrier", "hfb_peer_reduce_bcast"]
 
 
 def _check(rc, what):
@@ -725,13 +724,23 @@ def peer_barrier(flag_ptrs, me, epoch, timeout_s=600.0, mode=PEER_SIGNAL | PEER_
                                   _stream()), "hfb_peer_barrier")
 
 
-def peer_reduce(slots_ptr, slot_stride, nranks, rows, cols, ld, reduced_ptr, y_ptr, ldy):
-    _check(lib().hfb_peer_reduce(ctypes.c_void_p(slots_ptr), int(slot_stride), int(nranks), int(rows), int(cols), int(ld),
-                                 ctypes.c_void_p(reduced_ptr), ctypes.c_void_p(y_ptr), int(ldy), _stream()),
-           "hfb_peer_reduce")
+def peer_reduce_bcast(slots_ptr, slot_stride, me, rows, cols, ld, y_ptrs, ldy):
+    _check(lib().hfb_peer_reduce_bcast(ctypes.c_void_p(slots_ptr), int(slot_stride), len(y_ptrs), int(me), int(rows), int(cols),
+                                       int(ld), _ptr_array(y_ptrs), int(ldy), _stream()), "hfb_peer_reduce_bcast")
 
 
-def peer_gather(reduced_ptrs, me, block_rows, n, cols, ld, y_ptr, ldy):
-    _check(lib().hfb_peer_gather(_ptr_array(reduced_ptrs), int(me), len(reduced_ptrs), int(block_rows), int(n), int(cols),
-                                 int(ld), ctypes.c_void_p(y_ptr), int(ldy), _stream()),
-           "hfb_peer_gather")
+class _DeviceBlock:
+    """Raw device memory described through ``__cuda_array_interface__`` so that torch can view it without a copy."""
+
+    def __init__(self, ptr, rows, cols, ld, owner):
+        self.owner = owner                  # keeps the allocation alive as long as a tensor views it
+        self.__cuda_array_interface__ = {"shape": (int(rows), int(cols)), "typestr": "<f8", "data": (int(ptr), False),
+                                         "strides": (int(ld) * 8, 8), "version": 2}
+
+
+def tensor_from_ptr(ptr, rows, cols, ld, device, owner=None):
+    """(rows, cols) float64 view with leading dimension ``ld`` of device memory at ``ptr`` (not owned by torch)."""
+    t = torch.as_tensor(_DeviceBlock(ptr, rows, cols, ld, owner), device=device)
+    if t.data_ptr() != int(ptr) or t.stride(0) != int(ld):
+        raise HfbError("tensor_from_ptr: torch copied the block instead of viewing it")
+    return t

@@ -273,7 +273,9 @@ static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, double alpha, 
             p.peer_dst[o] = peer_dst[o];
         }
         p.peer_rows = (int)peer_rows;
-        p.vec_store = 1;
+        bool wide = (ldc & 3) == 0;
+        for (int o = 0; o < npeers; ++o) wide = wide && (reinterpret_cast<uintptr_t>(peer_dst[o]) & 31) == 0;
+        p.vec_store = wide ? 2 : 1;
     }
     if ((long long)p.m_tiles * p.n_tiles * p.splits * nbat > 0x7fffffffLL) return HFB_E_BADARG;
 

@@ -43,7 +43,7 @@ struct GemmParams {
     double* C;             // output (splits == 1) or split workspace (splits > 1)
     long long ldc;         // leading dimension of C / workspace
     long long split_stride;  // elements between consecutive split slabs in the workspace
-    int vec_store;         // 1 if C base is 16-byte aligned and ldc even (16-byte stores allowed)
+    int vec_store;         // 1 if C base is 16-byte aligned and ldc even (16-byte stores allowed); 2 (peer epilogue): 32-byte aligned, ldc % 4 == 0
     int symmetric;         // 1: the result is symmetric (M == N); tiles strictly below the diagonal are skipped
     int accumulate;        // 1: C += alpha * op(A) op(B)  (applied here when splits == 1, else by the split-K reduce)
     // strided-batch extension (hfb_dgemm_batched); the operands are 3-D tensor maps whose third coordinate is the sample
@@ -308,7 +308,13 @@ dgemm_dmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const int c = n0 + 16 * pp + 4 * t;
                 const double v0 = alpha * acc[j][2 * pp][0], v1 = alpha * acc[j][2 * pp + 1][0];
                 const double v2 = alpha * acc[j][2 * pp][1], v3 = alpha * acc[j][2 * pp + 1][1];
-                if (p.vec_store && c + 3 < p.N) {
+                if (PEER && p.vec_store == 2 && c + 3 < p.N) {
+                    // one 256-bit store per lane: the four lanes of a quad write a full 128-byte line of the row, so a tile row
+                    // crosses NVLink as whole lines instead of interleaved 16-byte pieces
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(crow + c)), "d"(v0),
+                                 "d"(v1), "d"(v2), "d"(v3)
+                                 : "memory");
+                } else if (p.vec_store && c + 3 < p.N) {
                     put2(crow + c, v0, v1);
                     put2(crow + c + 2, v2, v3);
                 } else {

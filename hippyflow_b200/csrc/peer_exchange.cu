@@ -1,8 +1,8 @@
 // Sketch exchange over NVLink peer memory (see include/hfb200.h, "peer exchange"): the allreduce of the (n x m) lift
 //   Y = sum_g X_g^T W_g                (collectiveOperator.py:73-80 -> collective.py:108-111, one MPI message per column)
 // as  reduce-scatter by PUSH from the lift GEMM's epilogue (hfb_dgemm_peer, dgemm_dmma.cuh)  ->  fixed-order sum of the
-// P slots by the owner of each row block  ->  all-gather by PULL of the reduced blocks.  Everything here is plain
-// ld/st on peer-mapped addresses (cudaIpc*), ordered by system-scope release/acquire flags; no NCCL on the data path.
+// P slots by the owner of each row block, stored into every rank's result block (all-gather by PUSH).  Everything here is
+// plain st.global on peer-mapped addresses (cudaIpc*), ordered by system-scope release/acquire flags; no NCCL on the data path.
 #include <cstdio>
 #include <cstring>
 
@@ -57,12 +57,12 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int me, int nranks, unsigned
     __threadfence_system();
 }
 
-// Owner side of the reduce-scatter: red[r][c] = sum_{s < nranks} slots[s][r][c] in FIXED order (bitwise reproducible and
-// identical on every rank, because only the owner computes it), written to the peer-visible `red` block and to the owner's
-// own rows of Y.
-__global__ void peer_reduce_kernel(const double* __restrict__ slots, long long slot_stride, int nranks, long long rows,
-                                   int cols, long long ld, double* __restrict__ red, double* __restrict__ Y,
-                                   long long ldy, int y_vec) {
+// Owner side of the reduce-scatter fused with the all-gather: s[r][c] = sum_{k < nranks} slots[k][r][c] in FIXED order (bitwise
+// reproducible and identical on every rank, because only the owner computes it), stored into the owner's rows of the result
+// block of EVERY rank -- local first, then the peers over NVLink, starting with me + 1 so that the ranks do not all write to
+// the same GPU at the same time.  A warp writes 512 contiguous bytes per destination.
+__global__ void peer_reduce_bcast_kernel(const double* __restrict__ slots, long long slot_stride, int nranks, int me,
+                                         long long rows, int cols, long long ld, PeerPtrs ydst, long long ldy) {
     const int pairs = (cols + 1) >> 1;
     const long long total = rows * pairs;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -70,6 +70,7 @@ __global__ void peer_reduce_kernel(const double* __restrict__ slots, long long s
         const long long r = idx / pairs;
         const int c = 2 * (int)(idx - r * pairs);
         const long long off = r * ld + c;
+        const long long yoff = r * ldy + c;
         if (c + 1 < cols) {
             // loads of four slots are issued together (the adds stay in rank order)
             double2 s = make_double2(0.0, 0.0);
@@ -87,76 +88,20 @@ __global__ void peer_reduce_kernel(const double* __restrict__ slots, long long s
                     }
                 }
             }
-            *reinterpret_cast<double2*>(red + off) = s;
-            if (y_vec) {
-                *reinterpret_cast<double2*>(Y + r * ldy + c) = s;
-            } else {
-                Y[r * ldy + c] = s.x;
-                Y[r * ldy + c + 1] = s.y;
+            for (int i = 0; i < nranks; ++i) {
+                int d = me + i;
+                if (d >= nranks) d -= nranks;
+                *reinterpret_cast<double2*>(reinterpret_cast<double*>(ydst.p[d]) + yoff) = s;
             }
         } else {
             double s = slots[off];
             for (int k = 1; k < nranks; ++k) s += slots[(long long)k * slot_stride + off];
-            red[off] = s;
-            Y[r * ldy + c] = s;
-        }
-    }
-}
-
-// All-gather by pull: rows of block o come from rank o's reduced block over NVLink (peer loads bypass the local L2 and
-// are read with ld.global.cv so that no stale L1 line of an earlier exchange is used).  blockIdx.y selects the peer,
-// starting with me + 1 so that the ranks do not all read from the same GPU at the same time.
-__global__ void peer_gather_kernel(PeerPtrs red, int me, int nranks, long long block_rows, long long n, int cols,
-                                   long long ld, double* __restrict__ Y, long long ldy, int y_vec) {
-    const int o = (me + 1 + (int)blockIdx.y) % nranks;
-    const long long row0 = (long long)o * block_rows;
-    long long rows = n - row0;
-    if (rows > block_rows) rows = block_rows;
-    if (rows <= 0) return;
-    const double* src = reinterpret_cast<const double*>(red.p[o]);
-    double* dst = Y + row0 * ldy;
-    const int pairs = (cols + 1) >> 1;
-    const long long total = rows * pairs;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    constexpr int U = 4;  // independent 16-byte loads in flight per thread (NVLink latency ~2 us)
-    for (; idx + (U - 1) * stride < total; idx += U * stride) {
-        double2 v[U];
-        long long rr[U];
-        int cc[U];
-        bool full[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = idx + u * stride;
-            rr[u] = i / pairs;
-            cc[u] = 2 * (int)(i - rr[u] * pairs);
-            full[u] = cc[u] + 1 < cols;
-            const double* a = src + rr[u] * ld + cc[u];
-            if (full[u]) {
-                v[u] = __ldcv(reinterpret_cast<const double2*>(a));
-            } else {
-                v[u].x = __ldcv(a);
-                v[u].y = 0.0;
+            for (int i = 0; i < nranks; ++i) {
+                int d = me + i;
+                if (d >= nranks) d -= nranks;
+                reinterpret_cast<double*>(ydst.p[d])[yoff] = s;
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            double* d = dst + rr[u] * ldy + cc[u];
-            if (full[u] && y_vec) {
-                *reinterpret_cast<double2*>(d) = v[u];
-            } else {
-                d[0] = v[u].x;
-                if (full[u]) d[1] = v[u].y;
-            }
-        }
-    }
-    for (; idx < total; idx += stride) {
-        const long long r = idx / pairs;
-        const int c = 2 * (int)(idx - r * pairs);
-        const double* a = src + r * ld + c;
-        double* d = dst + r * ldy + c;
-        d[0] = __ldcv(a);
-        if (c + 1 < cols) d[1] = __ldcv(a + 1);
     }
 }
 
@@ -220,45 +165,25 @@ extern "C" int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint
     return (int)cudaGetLastError();
 }
 
-extern "C" int hfb_peer_reduce(const double* slots, int64_t slot_stride, int nranks, int64_t rows, int64_t cols, int64_t ld,
-                               double* reduced, double* Y, int64_t ldy, void* stream_) {
-    if (!slots || !reduced || !Y || nranks < 1 || nranks > PEER_MAX || rows < 0 || cols <= 0 || ld < cols || ldy < cols ||
-        slot_stride < rows * ld || cols > 0x7ffffffeLL)
+extern "C" int hfb_peer_reduce_bcast(const double* slots, int64_t slot_stride, int nranks, int me, int64_t rows, int64_t cols,
+                                     int64_t ld, double* const* y_ptrs, int64_t ldy, void* stream_) {
+    if (!slots || !y_ptrs || nranks < 1 || nranks > PEER_MAX || me < 0 || me >= nranks || rows < 0 || cols <= 0 || ld < cols ||
+        ldy < cols || slot_stride < rows * ld || cols > 0x7ffffffeLL)
         return HFB_E_BADARG;
-    if ((ld & 1) || (slot_stride & 1) || (reinterpret_cast<uintptr_t>(slots) & 15) || (reinterpret_cast<uintptr_t>(reduced) & 15))
-        return HFB_E_ALIGN;
-    if (reinterpret_cast<uintptr_t>(Y) & 7) return HFB_E_ALIGN;
+    if ((ld & 1) || (ldy & 1) || (slot_stride & 1) || (reinterpret_cast<uintptr_t>(slots) & 15)) return HFB_E_ALIGN;
+    PeerPtrs y;
+    memset(&y, 0, sizeof(y));
+    for (int r = 0; r < nranks; ++r) {
+        if (!y_ptrs[r]) return HFB_E_BADARG;
+        if (reinterpret_cast<uintptr_t>(y_ptrs[r]) & 15) return HFB_E_ALIGN;
+        y.p[r] = y_ptrs[r];
+    }
     if (rows == 0) return 0;
-    const int y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
     const long long total = rows * ((cols + 1) / 2);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    peer_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(slots, slot_stride, nranks, rows, (int)cols, ld,
-                                                                            reduced, Y, ldy, y_vec);
-    ++g_launch_count;
-    return (int)cudaGetLastError();
-}
-
-extern "C" int hfb_peer_gather(const double* const* reduced_ptrs, int me, int nranks, int64_t block_rows, int64_t n,
-                               int64_t cols, int64_t ld, double* Y, int64_t ldy, void* stream_) {
-    if (!reduced_ptrs || !Y || nranks < 1 || nranks > PEER_MAX || me < 0 || me >= nranks || block_rows <= 0 || n <= 0 ||
-        cols <= 0 || ld < cols || ldy < cols || cols > 0x7ffffffeLL || (long long)nranks * block_rows < n)
-        return HFB_E_BADARG;
-    if (ld & 1) return HFB_E_ALIGN;
-    if (reinterpret_cast<uintptr_t>(Y) & 7) return HFB_E_ALIGN;
-    if (nranks == 1) return 0;
-    PeerPtrs f;
-    memset(&f, 0, sizeof(f));
-    for (int r = 0; r < nranks; ++r) {
-        if (!reduced_ptrs[r]) return HFB_E_BADARG;
-        if (reinterpret_cast<uintptr_t>(reduced_ptrs[r]) & 15) return HFB_E_ALIGN;
-        f.p[r] = const_cast<double*>(reduced_ptrs[r]);
-    }
-    const int y_vec = ((reinterpret_cast<uintptr_t>(Y) & 15) == 0 && (ldy & 1) == 0) ? 1 : 0;
-    int ctas_per_peer = (148 * 4) / (nranks - 1);   // ~4 CTAs per SM in total: ~10 MB of loads in flight against ~2 us of NVLink latency
-    if (ctas_per_peer < 1) ctas_per_peer = 1;
-    peer_gather_kernel<<<dim3((unsigned)ctas_per_peer, (unsigned)(nranks - 1)), 256, 0, (cudaStream_t)stream_>>>(
-        f, me, nranks, block_rows, n, (int)cols, ld, Y, ldy, y_vec);
+    peer_reduce_bcast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(slots, slot_stride, nranks, me, rows, (int)cols,
+                                                                                  ld, y, ldy);
     ++g_launch_count;
     return (int)cudaGetLastError();
 }

@@ -74,7 +74,7 @@ class SampleCovarianceOperator:
             scale /= float(size)
         elif self.mpi_op.lower() != "sum":
             raise NotImplementedError("Unknown operation *{0}*".format(self.mpi_op))
-        if self._lift_peer(GW, Y, Yt, scale, lazy):
+        if Yt.data_ptr() % 16 == 0 and K._ld(Yt) % 2 == 0 and self._lift_peer(GW, Y, scale, lazy):
             return
         self._lift_nccl(GW, Y, Yt, scale, lazy, nchunk)
 
@@ -106,52 +106,55 @@ class SampleCovarianceOperator:
         cache = self.collective.__dict__.setdefault("_peer_exchanges", {})
         key = (n, ld, ncols)
         if key not in cache:
-            from ..peer import PeerExchange
+            from ..peer import PeerExchange, release_all
             if len(cache) >= 4:                                   # bound the device memory held by stale shapes
-                for ex in cache.values():
-                    if ex is not None:
-                        ex.close()
+                release_all([e for e in cache.values() if e is not None], self.collective.group)
                 cache.clear()
             cache[key] = PeerExchange.create(self.collective.group, self.device, n, ld, ncols)
         return cache[key]
 
-    def _lift_peer(self, GW, Y, Yt, scale, lazy):
+    def _lift_peer(self, GW, Y, scale, lazy):
         """The lift with its allreduce fused into the GEMM epilogue over NVLink peer memory (hippyflow_b200/peer.py).
-        Returns False when the route is unavailable.  The first exchange of every buffer set is checked against the NCCL
-        route on the same operands; a mismatch disables the peer route on all ranks (with a warning)."""
+        Returns False when the route is unavailable.  The reduced sketch arrives in the exchange buffer itself: a block that
+        the solver allocated as scratch (``Y.adoptable``) is re-pointed at it, any other block receives a copy.  The first
+        exchange of every buffer set is checked against the NCCL route on the same operands; a mismatch disables the peer
+        route on all ranks (with a warning)."""
         cov = self.cov
-        m = GW.shape[1]
+        Yt = Y.tensor()
+        n, m = Yt.shape[0], GW.shape[1]
         ld = K._ld(Yt)
-        if Yt.data_ptr() % 16 or ld % 2:
-            return False
         if lazy:
             Wop, ncols = cov._Wext, m + 1
             if GW.data_ptr() != cov._Wext.data_ptr() or ld < m + 1:
                 return False
         else:
             Wop, ncols = GW, m
-        ex = self._peer_exchange(Yt.shape[0], ld, ncols)
+        ex = self._peer_exchange(n, ld, ncols)
         if ex is None:
             return False
-        Yv = Yt.as_strided((Yt.shape[0], ncols), (ld, 1))
-        ex.lift_allreduce(cov.Xt, Wop, Yv, scale)
+        R = ex.lift_allreduce(cov.Xt, Wop, scale)                  # (n, ncols) view of the exchange buffer, leading dimension ld
         if not getattr(ex, "verified", False):
-            ref = torch.empty_like(Y.storage_tensor())
-            rv = ref.as_strided((Yt.shape[0], ncols), (ld, 1))
-            K.dgemm(K.HFB_TN, cov.Xt, Wop, out=rv, alpha=scale)
+            ref = K.dgemm(K.HFB_TN, cov.Xt, Wop, alpha=scale).contiguous()
             self.collective.allReduce(ref, "sum")
-            err = (rv - Yv).abs().max() / rv.abs().max().clamp_min(1e-300)
-            bad = torch.tensor([1 if not (float(err) < self.PEER_VERIFY_TOL) else 0], dtype=torch.int32, device=self.device)
+            err = float((ref - R).abs().max() / ref.abs().max().clamp_min(1e-300))
+            bad = torch.tensor([0 if err < self.PEER_VERIFY_TOL else 1], dtype=torch.int32, device=self.device)
             self.collective.allReduce(bad, "sum")
-            ex.verified = True
-            ex.verify_err = float(err)
+            ex.verified, ex.verify_err = True, err
             if int(bad.item()):
                 import warnings
+                from ..peer import release_all
                 warnings.warn("hippyflow_b200: NVLink peer exchange disagrees with the NCCL allreduce (rel. error %.2e); "
-                              "peer route disabled" % float(err))
-                self.collective._peer_exchanges[(Yt.shape[0], ld, ncols)] = None
-                ex.close()
-                Yv.copy_(rv)
+                              "peer route disabled" % err)
+                self.collective._peer_exchanges[(n, ld, ncols)] = None
+                Yt.as_strided((n, ncols), (ld, 1)).copy_(ref)
+                release_all([ex], self.collective.group)
+                R = None
+        if R is not None:
+            if getattr(Y, "adoptable", False) and Y.tensor().shape[1] == m:
+                Y.adopt(R[:, :m])
+            else:
+                Yt.as_strided((n, ncols), (ld, 1)).copy_(R)
+        Yt = Y.tensor()
         if lazy:
             cov.finish_lazy(Yt, self.collective, "avg")
         elif cov.center is not None:
@@ -196,6 +199,7 @@ class SandwichedCovarianceOperator:
     def matMvMult(self, X, Y):
         BX = DeviceMultiVector(self.B.matmat(X.tensor()))
         CBX = DeviceMultiVector(self.n, X.nvec(), device=X.tensor().device)
+        CBX.adoptable = True                    # scratch: the sample operator may hand back its exchange block instead
         self.C.matMvMult(BX, CBX)
         self.B.matmat(CBX.tensor(), out=Y.tensor())
 

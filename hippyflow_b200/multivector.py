@@ -80,6 +80,12 @@ class DeviceMultiVector:
     def tensor(self):
         return self._t
 
+    def adopt(self, block):
+        """Re-point this multivector at another (n, k) device block of the same shape (no copy): how an operator hands back a
+        result that was produced in memory of its own (the NVLink exchange buffer of the sketch allreduce)."""
+        assert tuple(block.shape) == tuple(self._t.shape)
+        self._t = K._req(block, "block")
+
     def storage_tensor(self):
         """The full padded block (one contiguous NCCL message)."""
         t = self._t

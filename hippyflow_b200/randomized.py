@@ -25,6 +25,7 @@ from .multivector import DeviceMultiVector
 def _block_apply(A, X):
     if hasattr(A, "matMvMult") and getattr(A, "overwrites", False):
         Y = DeviceMultiVector(K.padded_empty(X.tensor().shape[0], X.nvec(), X.tensor().device))   # fully overwritten
+        Y.adoptable = True                      # scratch of this solver: the operator may hand back a block of its own
         A.matMvMult(X, Y)
         return Y
     Y = DeviceMultiVector(X.tensor().shape[0], X.nvec(), device=X.tensor().device)   # zeroed: operators may accumulate into Y (activeSubspaceProjector.py:214-221)
@@ -159,6 +160,7 @@ def doublePassG(A, B, Binv, Omega, k, s=1, faithful=False, info=None, Q0=None):
     for _ in range(s if Q0 is None else 0):
         if hasattr(A, "solveB_matMvMult") and getattr(A, "B", None) is B and (Binv is None or not faithful):
             Y = DeviceMultiVector(K.padded_empty(Q.tensor().shape[0], nvec, Q.tensor().device))   # fully overwritten
+            Y.adoptable = True                  # scratch of this solver: the operator may hand back a block of its own
             A.solveB_matMvMult(Q, Y)
             Q = Y
         else:

@@ -274,25 +274,23 @@ int hfb_measure_dmma_peak(double* scratch, size_t scratch_bytes, double* tflops_
  * stored-data operators of PODProjector.py:360-363 / activeSubspaceProjector.py:427-431.
  *
  * Each rank owns one exchange buffer (hfb_peer_alloc: cudaMalloc'd, zeroed, shareable through CUDA IPC) laid out by the
- * caller as  [flags: 16 x uint64 | slots: nranks x (block_rows x ld) | reduced: block_rows x ld];
+ * caller as  [flags: 16 x uint64 | slots: nranks x (block_rows x ld) | result blocks: (nranks*block_rows) x ld each];
  * the handles (hfb_peer_get_handle, 64 bytes) are exchanged out of band (torch.distributed all_gather_object) and mapped
  * with hfb_peer_open.  One exchange of rows [0, n) split into nranks blocks of block_rows (a multiple of 128) is
- *   1. hfb_dgemm_peer      rank g's partial tile of block o is stored from the accumulators straight into slot g of rank
- *                          o's buffer (st.global on peer-mapped addresses inside the DMMA kernel; no local copy of Y_g);
- *   2. hfb_peer_barrier    system-scope release/acquire flags: every rank's pushes have landed;
- *   3. hfb_peer_reduce     the owner sums its nranks slots in FIXED order (bitwise reproducible, identical on all ranks)
- *                          into `reduced` and into its own rows of Y;
- *   4. hfb_peer_barrier    every owner's block is reduced;
- *   5. hfb_peer_gather     every rank pulls the other blocks from the owners' `reduced` areas into Y (ld.global on peer
- *                          addresses).
- * NVLink bytes per rank and exchange: (nranks-1)/nranks * n * ld * 8 pushed + the same pulled (the two halves of a
- * bandwidth-optimal allreduce); the push overlaps the GEMM tile by tile.
+ *   1. hfb_dgemm_peer         rank g's partial tile of block o is stored from the accumulators straight into slot g of
+ *                             rank o's buffer (256-bit st.global on peer-mapped addresses inside the DMMA kernel; no local
+ *                             copy of the partial sketch Y_g);
+ *   2. hfb_peer_barrier       system-scope release/acquire flags: every rank's pushes have landed;
+ *   3. hfb_peer_reduce_bcast  the owner sums its nranks slots in FIXED order (bitwise reproducible, identical on all ranks)
+ *                             and stores the result into its rows of EVERY rank's result block (all-gather by push);
+ *   4. hfb_peer_barrier       every owner's rows have landed: the result block is complete on every rank.
+ * NVLink bytes per rank and exchange: (nranks-1)/nranks * n * ld * 8 pushed by the GEMM + the same pushed by the reduction
+ * (the two halves of a bandwidth-optimal allreduce); the first half overlaps the GEMM tile by tile.
  * hfb_peer_barrier: flag_ptrs[r] = address of rank r's 16 flag words (peer-mapped for r != me); epoch must grow with every
  * call and be the same on all ranks; a wait longer than timeout_s (0 = no limit) traps the kernel.  mode = HFB_PEER_SIGNAL
  * (publish only), HFB_PEER_WAIT (wait only) or both (a barrier).
- * slot_ptrs[o] (hfb_dgemm_peer) = address of THIS rank's slot inside rank o's buffer; ld_slot = ld of slots and `reduced`.
- * hfb_peer_reduce: Y points at the owner's first row.
- * Measured (2 x B200, cfg2 shard, profiles/r02_peer_lift_2gpu.json): lift GEMM alone 16.36 ms, fused lift + exchange 17.23 ms.
+ * slot_ptrs[o] (hfb_dgemm_peer) = address of THIS rank's slot inside rank o's buffer; ld_slot = ld of the slots.
+ * y_ptrs[r] (hfb_peer_reduce_bcast) = address of the owner's FIRST row inside rank r's result block (leading dimension ldy).
  */
 #define HFB_PEER_HANDLE_BYTES 64
 #define HFB_PEER_MAX_RANKS 16
@@ -307,10 +305,8 @@ int hfb_dgemm_peer(int layout, int64_t M, int64_t N, int64_t K, double alpha,
                    const double* A, int64_t lda, const double* B, int64_t ldb,
                    double* const* slot_ptrs, int nranks, int64_t block_rows, int64_t ld_slot, void* stream);
 int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch, double timeout_s, int mode, void* stream);
-int hfb_peer_reduce(const double* slots, int64_t slot_stride, int nranks, int64_t rows, int64_t cols, int64_t ld,
-                    double* reduced, double* Y, int64_t ldy, void* stream);
-int hfb_peer_gather(const double* const* reduced_ptrs, int me, int nranks, int64_t block_rows, int64_t n, int64_t cols,
-                    int64_t ld, double* Y, int64_t ldy, void* stream);
+int hfb_peer_reduce_bcast(const double* slots, int64_t slot_stride, int nranks, int me, int64_t rows, int64_t cols, int64_t ld,
+                          double* const* y_ptrs, int64_t ldy, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,11 +61,9 @@ def peer_exchange_case(hf, dev, coll, rank, world):
     dist.all_reduce(refc)
     ex = PeerExchange.create(None, dev, n, K._ld(ref), ncols)
     assert ex is not None, "peer exchange unavailable on an NVLink box"
-    Y = K.padded_zeros(n, ncols, dev)
     first = None
     for rep in range(3):
-        Y.zero_()
-        ex.lift_allreduce(X, W, Y, 0.5)
+        Y = ex.lift_allreduce(X, W, 0.5)
         torch.cuda.synchronize()
         err = float((Y - refc).abs().max() / refc.abs().max())
         assert err < 1e-13, (rep, err)
@@ -75,7 +73,9 @@ def peer_exchange_case(hf, dev, coll, rank, world):
     dist.all_gather(gathered, first.contiguous())
     for t in gathered:
         assert torch.equal(t, gathered[0]), "ranks hold different bits"
-    ex.close()
+    del Y
+    from hippyflow_b200.peer import release_all
+    release_all([ex], None)
     # operator route: SampleCovarianceOperator.lift_reduced takes the peer route and verified it against NCCL on first use
     exs = [e for e in getattr(coll, "_peer_exchanges", {}).values() if e is not None]
     assert exs and all(e.verified and e.verify_err < 1e-12 for e in exs), "operator lifts did not take the peer route"

@@ -83,10 +83,11 @@ def test_argument_validation_without_gpu():
     assert L.hfb_peer_barrier(two, 2, 2, 1, 1.0, 3, None) == -1                                                 # rank out of range
     assert L.hfb_peer_barrier(two, 0, 2, 0, 1.0, 3, None) == -1                                                 # epoch 0 is the initial flag value
     assert L.hfb_peer_barrier(two, 0, 2, 1, 1.0, 0, None) == -1                                                 # neither signal nor wait
-    assert L.hfb_peer_reduce(16, 100, 2, 10, 20, 20, 32, 64, 20, None) == -1                                    # slots overlap
-    assert L.hfb_peer_reduce(16, 210, 2, 10, 20, 21, 32, 64, 20, None) == -2                                    # odd ld
-    assert L.hfb_peer_gather(two, 0, 2, 128, 300, 20, 20, 64, 20, None) == -1                                   # blocks do not cover n
-    assert L.hfb_peer_gather(two, 0, 2, 256, 300, 20, 10, 64, 20, None) == -1                                   # ld < cols
+    assert L.hfb_peer_reduce_bcast(16, 100, 2, 0, 10, 20, 20, two, 20, None) == -1                              # slots overlap
+    assert L.hfb_peer_reduce_bcast(16, 210, 2, 0, 10, 20, 21, two, 21, None) == -2                              # odd ld
+    assert L.hfb_peer_reduce_bcast(16, 200, 2, 2, 10, 20, 20, two, 20, None) == -1                              # rank out of range
+    assert L.hfb_peer_reduce_bcast(16, 200, 2, 0, 10, 20, 20, bad, 20, None) == -2                              # result block not 16-byte aligned
+    assert L.hfb_peer_reduce_bcast(16, 200, 2, 0, 10, 20, 20, two, 10, None) == -1                              # ldy < cols
     assert L.hfb_peer_alloc(0, None) == -1 and L.hfb_peer_free(None) == -1 and L.hfb_peer_open(None, None) == -1
     assert L.hfb_dgemm_workspace_bytes(0, 128, 16, 4096, 4) == 4 * 128 * 16 * 8
     assert L.hfb_dgemm_auto_splits(0, 4096, 266, 263169) >= 2

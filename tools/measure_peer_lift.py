@@ -58,14 +58,18 @@ def main():
     if ex is None:
         out["peer_ms"] = None
     else:
-        out["peer_ms"] = timed(lambda: ex.lift_allreduce(X, W, Yt, scale), reps, dev)
-        out["peer_err_vs_nccl"] = float((Yt - ref).abs().max() / ref.abs().max())
+        out["peer_ms"] = timed(lambda: ex.lift_allreduce(X, W, scale), reps, dev)
+        out["peer_err_vs_nccl"] = float((ex.result_view() - ref).abs().max() / ref.abs().max())
         # phases alone (each rank times its own kernels; the barriers absorb the skew)
         out["peer_push_gemm_ms"] = timed(lambda: ex.push(X, W, scale), reps, dev)
-        out["peer_reduce_ms"] = timed(lambda: ex.reduce(Yt), reps, dev)
-        out["peer_gather_ms"] = timed(lambda: ex.gather(Yt), reps, dev)
+
+        def red():
+            ex.reduce_bcast()
+            ex.barrier()
+        out["peer_reduce_bcast_ms"] = timed(red, reps, dev)
         out["peer_barrier_ms"] = timed(lambda: ex.barrier(), reps, dev)
-        ex.close()
+        from hippyflow_b200.peer import release_all
+        release_all([ex], None)
     nbytes = n * K._ld(Yt) * 8
     out["exchange_bytes_per_rank_each_way"] = nbytes * (world - 1) / world
     if rank == 0:

@@ -1,8 +1,8 @@
 """Single-GPU self-test of the NVLink sketch exchange (hippyflow_b200/peer.py): P emulated ranks inside one process, every
 'peer' buffer local.  The phases run rank by rank on ONE stream (push of all ranks, signal of all ranks, wait of all ranks,
 reduce, ...), so no kernel ever waits for work that is queued behind it.  Exercises the peer-store epilogue of the lift GEMM
-(hfb_dgemm_peer), the flag words and epochs, the fixed-order slot reduction and the gather kernel against the rank-ordered
-sum of P plain lifts.  The concurrent barrier between real ranks is covered by tests/multigpu_worker.py.  Run in a
+(hfb_dgemm_peer), the flag words and epochs and the fixed-order slot reduction with its stores into every rank's result
+block against the rank-ordered sum of P plain lifts.  The concurrent barrier between real ranks is covered by tests/multigpu_worker.py.  Run in a
 subprocess by tests/test_gpu_kernels.py (a wait that times out traps the kernel and would poison the caller's context)."""
 import os
 import sys
@@ -27,21 +27,30 @@ def run_case(P, n, R, ncols, dev):
         ref = part.clone() if ref is None else ref + part
     ld = ((ncols + 15) // 16) * 16
     group = PeerExchange.local_group(P, dev, n, ld, ncols)
-    Ys = [K.padded_zeros(n, ncols, dev) for _ in range(P)]
-    for rep in range(2):                           # the second exchange reuses the slots and flags (growing epochs)
-        for r in range(P):
-            Ys[r].zero_()
-            group[r].push(Xs[r], Ws[r], alpha)
-        for phase in (PeerExchange.reduce, PeerExchange.gather):
+    views = {}
+    for rep in range(3):                           # later exchanges reuse the slots and flags (growing epochs), alternate blocks
+        for r, ex in enumerate(group):
+            ex.parity ^= 1
+            ex.result_view().fill_(float("nan"))
+            ex.push(Xs[r], Ws[r], alpha)
+        for phase in (PeerExchange.reduce_bcast, None):
             for ex in group:
                 ex.signal()
             for ex in group:
                 ex.wait()
-            for r, ex in enumerate(group):
-                phase(ex, Ys[r])
+            if phase is not None:
+                for ex in group:
+                    phase(ex)
         torch.cuda.synchronize()
-        for r in range(P):
-            assert torch.equal(Ys[r], ref), (P, n, ncols, rep, r, float((Ys[r] - ref).abs().max()))
+        for r, ex in enumerate(group):
+            Y = ex.result_view()
+            assert Y.shape == (n, ncols) and Y.stride(0) == ld
+            assert torch.equal(Y, ref), (P, n, ncols, rep, r, float((Y - ref).abs().max()))
+            views[(rep, r)] = Y
+        if rep:                                    # the previous exchange's block is still intact
+            for r in range(P):
+                assert torch.equal(views[(rep - 1, r)], ref)
+    del views, Y
     for ex in group:
         ex.close()
 
