@@ -12,12 +12,14 @@ namespace hfb {
 template <int LAYOUT, int NT, bool PEER>
 static int launch_k(const CUtensorMap& mapA, const CUtensorMap& mapB, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<LAYOUT, NT>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};  // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_kernel<LAYOUT, NT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[dev] = true;
     }
     const long long grid = (long long)p.m_tiles * p.n_tiles * p.splits * p.batch;
     dgemm_dmma_kernel<LAYOUT, NT, PEER><<<(unsigned)grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(mapA, mapB, p);

@@ -206,12 +206,14 @@ static int launch_dmma(int64_t nclusters, int m, const SpmmBlobLayout& L, const 
                        double* C, int64_t ldc, cudaStream_t stream) {
     constexpr int ROWS = 8 * RH, COLS = 4 * MAXKS, CP = (COLS + 11) / 16 * 16 + 4, PITCH = 64 * NT + 4;
     const size_t smem = (size_t)L.stride + sizeof(double) * ((size_t)ROWS * CP + 2 * (size_t)COLS * PITCH);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[64] = {0};  // per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_kernel<RH, MAXKS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = smem;
+        configured[dev] = smem;
     }
     csr_spmm_dmma_kernel<RH, MAXKS, NT><<<(unsigned)nclusters, DM_WARPS * 32, smem, stream>>>(
         m, L, static_cast<const unsigned char*>(blobs), B, ldb, C, ldc);
@@ -381,12 +383,14 @@ static int launch_dmma_frag_ng(int64_t nclusters, int m, int W, const FragBlobLa
     constexpr int COLS = 4 * MAXKS;
     const size_t smem = sizeof(double) * (size_t)COLS * (W + 4);
     if (smem > 227 * 1024 || W > 64 * NG) return HFB_E_UNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[64] = {0};  // per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(csr_spmm_dmma_frag_kernel<RH, MAXKS, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = smem;
+        configured[dev] = smem;
     }
     const int nchunk = (m + W - 1) / W;
     if (nchunk > 65535) return HFB_E_UNSUPPORTED;

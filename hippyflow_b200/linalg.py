@@ -10,6 +10,8 @@ Layouts ("operand layouts are fixed by the reference"):
     (operatorWrappers.py:62-64);
   * sketches / bases: (n, m) row-major, column j = vector j (mv_utilities.py:31-49).
 """
+import os
+
 import numpy as np
 import scipy.linalg as sla
 from scipy.linalg import lapack as _lapack
@@ -481,11 +483,40 @@ def cleanup_factor(G1):
     return S
 
 
+_blas_ctl = None
+
+
+def _eigh_threads():
+    """(controller, threads) for the host eigensolve, or (None, 0) when the BLAS pool is already wide enough.  torchrun
+    exports OMP_NUM_THREADS=1, which leaves LAPACK dsyevd single-threaded on the critical path of every rank (measured on the
+    B200 host, m = 266: 4.25 ms with 1 thread, 3.84 ms with 4, 3.7 ms with 6-12; tools/lapack_threads_probe.py); the solve is
+    worth this rank's share of the host cores for its few milliseconds.  Never more threads than cores: oversubscribed
+    OpenBLAS spins for ~1 s per call."""
+    global _blas_ctl
+    if _blas_ctl is None:
+        try:
+            from threadpoolctl import ThreadpoolController
+            ctl = ThreadpoolController()
+            cur = max([i.get("num_threads", 1) for i in ctl.info() if i.get("user_api") == "blas"] or [0])
+            cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            share = cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            want = int(os.environ.get("HFB_EIGH_THREADS", min(6, share)))
+            _blas_ctl = (ctl, want) if (cur and want > cur) else (None, 0)
+        except Exception:                                   # noqa: BLE001 -- threadpoolctl missing: keep the pool as it is
+            _blas_ctl = (None, 0)
+    return _blas_ctl
+
+
 def top_k_eig(T, k):
     """eigh of the small symmetric matrix T on the host, top-k descending
     (hIPPYlib doublePass: np.linalg.eigh(T), sort descending, keep k)."""
     T = _sym(np.asarray(T))
-    d, V, fail = _lapack.dsyevd(T, compute_v=1, lower=1)
+    ctl, threads = _eigh_threads()
+    if ctl is not None:
+        with ctl.limit(limits=threads, user_api="blas"):
+            d, V, fail = _lapack.dsyevd(T, compute_v=1, lower=1)
+    else:
+        d, V, fail = _lapack.dsyevd(T, compute_v=1, lower=1)
     if fail != 0:
         d, V = np.linalg.eigh(T)
     perm = np.argsort(d)[::-1][:k]

@@ -64,6 +64,22 @@ def gaussian_omega(n, m, seed, device):
     return Om
 
 
+def _upload_chunks(N, max_chunks=8):
+    """Row chunks [(lo, hi)] of a pipelined upload.  The GPU works on chunk i while chunk i+1 crosses PCIe, so what remains
+    after the LAST byte has landed is the work on the last chunk: the chunks taper (weights 8 ... 8, 4, 2, 1) to make that
+    tail small while the early chunks stay large enough for efficient GEMMs."""
+    nchunk = int(max(1, min(max_chunks, N // 256)))
+    if nchunk < 4:
+        return [(i * N // nchunk, (i + 1) * N // nchunk) for i in range(nchunk)]
+    w = [8] * (nchunk - 2) + [4, 2, 1]
+    tot, acc, cuts = float(sum(w)), 0.0, [0]
+    for x in w[:-1]:
+        acc += x
+        cuts.append(min(N, max(cuts[-1] + 8, int(round(N * acc / tot / 8.0)) * 8)))
+    cuts.append(N)
+    return [(lo, hi) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
 _copy_streams = {}
 
 
@@ -300,8 +316,7 @@ class PODProjectorFromData:
         B = Md.matmat(Omega.tensor())                                        # M Omega, ready before the data arrives
         W = K.padded_empty(N, m, dev)
         Y = K.padded_empty(n, m, dev)
-        nchunk = int(max(1, min(max_chunks, N // 256)))
-        bounds = [(i * N // nchunk, (i + 1) * N // nchunk) for i in range(nchunk)]
+        bounds = _upload_chunks(N, max_chunks)
         main = torch.cuda.current_stream(dev)
         copy_stream = _copy_stream(dev)
         copy_stream.wait_stream(main)
