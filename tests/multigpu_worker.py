@@ -81,6 +81,32 @@ def peer_exchange_case(hf, dev, coll, rank, world):
     assert exs and all(e.verified and e.verify_err < 1e-12 for e in exs), "operator lifts did not take the peer route"
 
 
+def kle_over_peer_exchange_case(hf, dev, coll, rank, world):
+    """KLE from sharded parameter draws at n >= 4096 (the lifts take the fused NVLink exchange): 'mass' (doublePassG on M C M,
+    un-centred operator: the non-lazy branch of the peer route) and 'identity' with faithful=True (T = (A Q)^T Q: two
+    exchanges per solve, so the sketch of the first must survive the second -- the alternating result blocks)."""
+    from hippyflow_b200 import synthetic as syn
+    from oracle import projectors_np as P
+    M = syn.p1_mass_matrix(66)                                     # 4489 dofs
+    n = M.shape[0]
+    per = 48
+    m_data = syn.snapshots(n, per * world, r0=40, seed=41)
+    Om = syn.gaussian_omega(n, 30, seed=42)
+    pk = hf.KLEParameterList()
+    pk["rank"], pk["oversampling"], pk["verbose"], pk["save_and_plot"] = 20, 10, False, False
+    proj = hf.KLEProjector(hf.SampleCovariancePrior(m_data[rank * per:(rank + 1) * per].copy(), M, device=dev), collective=coll,
+                           parameters=pk)
+    for orth, faithful in (("mass", False), ("identity", True), ("mass", True)):
+        d, dec, enc = proj.construct_input_subspace(orth, Omega=Om, faithful=faithful)
+        d0, V0, E0 = P.kle_from_samples(m_data, M, 20, Om, orth, ranks=world)
+        k = int(np.sum(d0 / d0[0] > 1e-5))
+        np.testing.assert_allclose(d[:k], d0[:k], rtol=1e-10)
+        assert P.principal_angle(hf.mv_to_dense(dec)[:, :k], V0[:, :k], M if orth == "mass" else None) < 1e-8, (orth, faithful)
+        if orth == "mass":
+            V, E = hf.mv_to_dense(dec), hf.mv_to_dense(enc)
+            assert np.linalg.norm(M @ V - E) / np.linalg.norm(E) < 1e-10          # test_KLEProjector.py:102-108
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -156,6 +182,7 @@ def main():
     np.testing.assert_allclose(db2, db0, rtol=1e-10)
 
     sharded_mean_shift_case(hf, dev, coll, rank, world)
+    kle_over_peer_exchange_case(hf, dev, coll, rank, world)
     peer_exchange_case(hf, dev, coll, rank, world)
 
     # collective on device blocks: one NCCL call for the whole padded block, 'avg' = sum / size
