@@ -83,6 +83,7 @@ def lib():
         "hfb_jacobi_svd_max_elems": (i64, []),
         "hfb_jacobi_svd_batched": (i32, [i64, i64, vp, i64, i64, i64, vp, i64, vp, i32, i32, vp]),
         "hfb_fill_random": (i32, [i64, i64, vp, i64, u64, i64, i32, vp]),
+        "hfb_host_copy": (i32, [vp, vp, sz, i32]),
         "hfb_peer_alloc": (i32, [sz, ctypes.POINTER(vp)]),
         "hfb_peer_free": (i32, [vp]),
         "hfb_peer_get_handle": (i32, [vp, ctypes.c_char_p]),
@@ -113,7 +114,7 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_measure_dmma_peak", "hfb_chol_inverse_workspace_bytes", "hfb_chol_inverse", "hfb_chol_inverse_profile",
             "hfb_jacobi_svd_max_elems",
             "hfb_jacobi_svd_batched",
-            "hfb_peer_alloc", "hfb_peer_free", "hfb_peer_get_handle", "hfb_peer_open", "hfb_peer_close", "hfb_dgemm_peer",
+            "hfb_host_copy", "hfb_peer_alloc", "hfb_peer_free", "hfb_peer_get_handle", "hfb_peer_open", "hfb_peer_close", "hfb_dgemm_peer",
             "hfb_peer_barrier", "hfb_peer_reduce_bcast"]
 
 
@@ -655,6 +656,17 @@ def stop_timing():
 
 def launch_count():
     return int(lib().hfb_launch_count())
+
+
+def host_copy_(dst, src, nthreads):
+    """dst[...] = src for two contiguous HOST tensors of equal size and dtype, on ``nthreads`` threads with non-temporal
+    stores (hfb_host_copy): the pageable -> pinned leg of the staged upload."""
+    if dst.is_cuda or src.is_cuda or dst.dtype != src.dtype or dst.numel() != src.numel() or \
+            not dst.is_contiguous() or not src.is_contiguous():
+        raise HfbError("host_copy_: two contiguous host tensors of equal size and dtype expected")
+    _check(lib().hfb_host_copy(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()),
+                               dst.numel() * dst.element_size(), int(nthreads)), "hfb_host_copy")
+    return dst
 
 
 # ---------------------------------------------------------------------------------------------- peer exchange (NVLink)

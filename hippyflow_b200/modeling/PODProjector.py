@@ -354,16 +354,16 @@ class PODProjectorFromData:
             # previous chunk.
             ring = _staging_ring(dev, n)
             rows_per = ring[0][0].shape[0]
-            # torchrun exports OMP_NUM_THREADS=1; the staging copies are worth this rank's share of the host cores
-            saved_threads = torch.get_num_threads()
-            torch.set_num_threads(_host_copy_threads())
+            # the staging copies are worth this rank's share of the host cores (torchrun exports OMP_NUM_THREADS=1, which
+            # would leave torch's copy_ single-threaded; hfb_host_copy runs its own threads and streams around the cache)
+            threads = _host_copy_threads()
             j = 0
             for i, (lo, hi) in enumerate(bounds):
                 for s0 in range(lo, hi, rows_per):
                     s1 = min(hi, s0 + rows_per)
                     buf, free = ring[j % len(ring)]
                     free.synchronize()                                       # its previous DMA has finished
-                    buf[:s1 - s0].copy_(src[s0:s1])
+                    K.host_copy_(buf[:s1 - s0], src[s0:s1], threads)
                     with torch.cuda.stream(copy_stream):
                         Xt[s0:s1].copy_(buf[:s1 - s0], non_blocking=True)
                         free.record(copy_stream)
@@ -371,7 +371,6 @@ class PODProjectorFromData:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 consume(i, lo, hi, ev)
-            torch.set_num_threads(saved_threads)
         Xt.record_stream(copy_stream)
         if not shifted:
             return Xt, torch.zeros(n, dtype=torch.float64, device=dev), None, (W, Y)

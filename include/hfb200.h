@@ -308,6 +308,14 @@ int hfb_peer_barrier(void* const* flag_ptrs, int me, int nranks, uint64_t epoch,
 int hfb_peer_reduce_bcast(const double* slots, int64_t slot_stride, int nranks, int me, int64_t rows, int64_t cols, int64_t ld,
                           double* const* y_ptrs, int64_t ldy, void* stream);
 
+/*
+ * HOST helper of the upload path: copy `bytes` from pageable host memory into a pinned staging buffer with `nthreads`
+ * threads and non-temporal stores (the staging buffers are only read by the DMA engine afterwards).  The reference consumes
+ * u_data / J in place on the host (PODProjector.py:726, operatorWrappers.py:62-64); this is the host half of getting a plain
+ * NumPy array across PCIe at link rate (the device half is cudaMemcpyAsync from the staging ring).  Blocking; no CUDA call.
+ */
+int hfb_host_copy(void* dst, const void* src, size_t bytes, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,22 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 # ... nor through the CPU test double of tests/ (numbers produced under it say nothing about the kernels)
                 assert "cpu_device_shim" not in src and "emulated_device" not in src, f
+
+
+def test_host_copy_threads_and_tails():
+    """hfb_host_copy (pageable -> pinned leg of the staged upload): every byte arrives for sizes around the thread / cache-line
+    boundaries, unaligned destinations and thread counts above the chunk count."""
+    import numpy as np
+    import torch
+    from hippyflow_b200 import _lib
+    assert _lib.lib().hfb_host_copy(None, None, 10, 1) == -1
+    rng = np.random.default_rng(0)
+    for count, threads, offset in [(1, 4, 0), (7, 1, 0), (8, 3, 1), (131072, 4, 0), (131072 + 5, 4, 1), (300001, 7, 0),
+                                   (1 << 18, 64, 0), (263169 * 3, 8, 0)]:
+        src = torch.from_numpy(rng.standard_normal(count))
+        dst = torch.full((count + 4,), -7.0, dtype=torch.float64)
+        _lib.host_copy_(dst[offset:offset + count], src, threads)
+        assert torch.equal(dst[offset:offset + count], src)
+        assert float(dst[offset + count]) == -7.0 and (offset == 0 or float(dst[0]) == -7.0)      # nothing written outside
+    with pytest.raises(_lib.HfbError):
+        _lib.host_copy_(torch.zeros(4), torch.zeros(4, dtype=torch.float64), 1)                     # dtype mismatch
