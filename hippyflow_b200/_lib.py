@@ -63,6 +63,11 @@ def lib():
         "hfb_csr_pack_clusters_frag": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
         "hfb_csr_spmm_dmma_frag": (i32, [i64, i64, vp, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_dmma_ring": (i32, [i64, i64, vp, i32, i32, vp, i64, vp, i64, vp]),
+        "hfb_csr_runs_measure": (i32, [i64, vp, vp, vp, vp, i64, vp]),
+        "hfb_csr_runs_blob_stride": (i64, [i32, i32, i32]),
+        "hfb_csr_pack_clusters_runs": (i32, [i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+        "hfb_csr_spmm_runs_slots": (i32, [i64, i64, i32, i32, i32, i32]),
+        "hfb_csr_spmm_runs": (i32, [i64, i64, vp, i32, i32, i32, i32, vp, i64, vp, i64, vp]),
         "hfb_csr_spmm_rows": (i32, [i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]),
         "hfb_coldot_workspace_bytes": (sz, [i64, i64]),
         "hfb_coldot": (i32, [i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
@@ -107,7 +112,9 @@ EXPORTED = ["hfb_version", "hfb_launch_count", "hfb_dgemm_workspace_bytes", "hfb
             "hfb_dgemm_batched_small", "hfb_csr_spmm", "hfb_csr_spmm_ordered", 
             "hfb_csr_cluster_rows_capped", 
             "hfb_csr_cluster_blob_stride", "hfb_csr_pack_clusters", "hfb_csr_spmm_dmma",
-            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", "hfb_csr_spmm_dmma_ring", 
+            "hfb_csr_frag_blob_stride", "hfb_csr_pack_clusters_frag", "hfb_csr_spmm_dmma_frag", "hfb_csr_spmm_dmma_ring",
+            "hfb_csr_runs_measure", "hfb_csr_runs_blob_stride", "hfb_csr_pack_clusters_runs", "hfb_csr_spmm_runs_slots",
+            "hfb_csr_spmm_runs",
             "hfb_csr_spmm_rows", "hfb_coldot_workspace_bytes",
             "hfb_coldot", "hfb_rowdot", "hfb_colscale", "hfb_colmean_workspace_bytes", "hfb_colsum", "hfb_colsum_weighted", "hfb_subtract_row",
             "hfb_rank1_update", "hfb_axpby", "hfb_axpby_cols", "hfb_rowscale", "hfb_fill_random",
@@ -408,6 +415,55 @@ def csr_spmm_dmma_ring(plan, B, out=None):
     rc = L.hfb_csr_spmm_dmma_ring(plan["nclusters"], m, plan["fblobs"].data_ptr(), plan["max_rows"], plan["max_cols_cap"],
                                   B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
     _check(rc, "hfb_csr_spmm_dmma_ring")
+    return out
+
+
+def csr_pack_clusters_runs(indptr, indices, data, order, cptr):
+    """Host preprocessing for the run-staged FMA SpMM (hfb_csr_pack_clusters_runs): returns (uint8 NumPy buffer of per-cluster
+    run records, caps dict) or raises HfbError when the plan does not fit the kernel (> 16 rows or > 32 runs per cluster)."""
+    import numpy as np
+    L = lib()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    cptr = np.ascontiguousarray(cptr, dtype=np.int32)
+    ncl = cptr.size - 1
+    caps = np.zeros(4, dtype=np.int32)
+    rc = L.hfb_csr_runs_measure(indptr.size - 1, indptr.ctypes.data, indices.ctypes.data, order.ctypes.data, cptr.ctypes.data,
+                                ncl, caps.ctypes.data)
+    _check(rc, "hfb_csr_runs_measure")
+    max_rows, max_runs, max_brow, max_entries = (int(v) for v in caps)
+    stride = int(L.hfb_csr_runs_blob_stride(max_rows, max_runs, max_entries))
+    if stride <= 0:
+        raise HfbError("hfb_csr_runs_blob_stride: unsupported cluster plan (rows %d, runs %d per cluster; limits 16 / 32)"
+                       % (max_rows, max_runs))
+    blobs = np.empty(ncl * stride, dtype=np.uint8)
+    rc = L.hfb_csr_pack_clusters_runs(indptr.size - 1, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data,
+                                      order.ctypes.data, cptr.ctypes.data, ncl, max_rows, max_runs, max_entries,
+                                      blobs.ctypes.data)
+    _check(rc, "hfb_csr_pack_clusters_runs")
+    return blobs, {"max_rows": max_rows, "max_runs": max_runs, "max_brow": max_brow,
+                   "max_entries": max_entries, "stride": stride}
+
+
+def csr_spmm_runs_slots(rplan, m, ldb):
+    """Ring slots the run-staged kernel would use for an (n, m) block of pitch ldb; 0 = unsupported shape."""
+    return int(lib().hfb_csr_spmm_runs_slots(int(m), int(ldb), rplan["max_rows"], rplan["max_runs"], rplan["max_brow"],
+                                             rplan["max_entries"]))
+
+
+def csr_spmm_runs(rplan, B, out=None):
+    """C = M @ B with the run-staged FMA kernel (hfb_csr_spmm_runs); ``rplan`` = caps of csr_pack_clusters_runs plus
+    ``nclusters`` and the device tensor ``blobs`` (linalg.CsrMatrix._runs_blobs)."""
+    L = lib()
+    _req(B, "B")
+    n, m = B.shape
+    if out is None:
+        out = padded_empty(n, m, B.device)
+    rc = L.hfb_csr_spmm_runs(rplan["nclusters"], m, rplan["blobs"].data_ptr(), rplan["max_rows"], rplan["max_runs"],
+                             rplan["max_brow"], rplan["max_entries"], B.data_ptr(), _ld(B), out.data_ptr(), _ld(out), _stream())
+    _check(rc, "hfb_csr_spmm_runs")
     return out
 
 

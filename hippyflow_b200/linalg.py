@@ -27,6 +27,7 @@ class CsrMatrix:
     WIDE_DEFAULT = "frag"       # kernel 'auto' uses over the cluster plan (r02: 5 / 3 / 2 column groups per warp by width)
     # narrower blocks go to the generic L1-panel kernel (r02, m = 74: fragment kernel 0.129 ms = 2601 GB/s vs 0.222 ms)
     CLUSTER_MIN_COLS = int(__import__("os").environ.get("HFB_SPMM_MIN_COLS", 32))
+    RUNS_MIN_COLS = 96          # 'auto': run-staged FMA kernel from this width up to 384 columns
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
@@ -45,7 +46,8 @@ class CsrMatrix:
         self.plan = None
         import os
         # SpMM kernel for blocks of >= 96 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
-        #   "auto"  (default) "frag" (measured r02: 0.164 ms vs 0.183 ms for "dmma" at m = 138, 0.271 vs 0.306 ms at m = 266)
+        #   "auto"  (default) "runs" for 96 <= m <= 384, else "frag"
+        #   "runs"  run-staged FMA kernel: runs of consecutive B rows staged by one TMA copy each, CSR-order FMAs (m <= 384)
         #   "frag"  dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
         #   "ring"  the same records through resident CTAs with producer warps + a ring of cluster buffers (m <= 384)
         #   "dmma"  same arithmetic, records decoded in the kernel, double-buffered 64-column panels
@@ -108,6 +110,21 @@ class CsrMatrix:
                                                                       plan["max_cols_cap"]), device=device)
         return plan
 
+    @staticmethod
+    def _runs_blobs(plan, device):
+        """Run records of the run-staged FMA kernel, packed on first use.  Returns the record plan, or None when the
+        cluster plan does not fit the kernel (> 32 runs of consecutive columns in a cluster)."""
+        if "rblobs" not in plan:
+            indptr, indices, data, order, cptr = plan["_host"]
+            try:
+                blobs, caps = K.csr_pack_clusters_runs(indptr, indices, data, order, cptr)
+                caps["blobs"] = torch.as_tensor(blobs, device=device)
+                caps["nclusters"] = plan["nclusters"]
+                plan["rblobs"] = caps
+            except K.HfbError:
+                plan["rblobs"] = None
+        return plan["rblobs"]
+
     def matmat(self, B, out=None):
         """out (n, m) = M @ B for a dense row-major (n, m) block."""
         if K.TIMING is None:
@@ -128,11 +145,15 @@ class CsrMatrix:
             import os
             impl = self.impl
             if impl == "auto":
-                # measured on B200 (profiles/r01_spmm_variants.md): whole-row fragment-record kernel for wide blocks,
-                # double-buffered 64-column panels for narrow ones (a CTA's share is too small to amortise its latency chain)
-                # whole-row fragment kernel; ring-pipelined form of it for 192 <= m <= 384 (r02: 0.244 ms vs 0.272 ms at m = 266;
-                # narrower blocks are bound by its per-cluster TMA request count and stay with the per-cluster kernel)
-                impl = os.environ.get("HFB_SPMM_WIDE", "ring" if 192 <= m <= 384 else self.WIDE_DEFAULT)
+                # measured on B200 (profiles/r02_spmm_runs.md): run-staged FMA kernel for 96 <= m <= 384 (m = 266: 0.215 ms vs
+                # 0.241 ms ring / 0.271 ms frag; m = 138: 0.142 ms vs 0.164 ms frag); below that a cluster's fixed costs
+                # dominate and the per-cluster fragment kernel is level or ahead (m = 74: 0.128 ms vs 0.133 ms)
+                impl = os.environ.get("HFB_SPMM_WIDE", "runs" if self.RUNS_MIN_COLS <= m <= 384 else self.WIDE_DEFAULT)
+            if impl == "runs":
+                rplan = self._runs_blobs(self.plan, self.device) if m <= 384 else None
+                if rplan is not None and K.csr_spmm_runs_slots(rplan, m, K._ld(B)) > 0:
+                    return K.csr_spmm_runs(rplan, B, out), "csr_spmm_runs_kernel"
+                impl = "ring" if 192 <= m <= 384 else "frag"          # wide pitch / many runs: the fragment kernels
             if impl == "ring" and 8 < self.plan["max_rows"] <= 16 and m <= 384:
                 return K.csr_spmm_dmma_ring(self._frag_blobs(self.plan, self.device), B, out), "csr_spmm_ring_kernel"
             if impl in ("frag", "ring"):
@@ -140,7 +161,7 @@ class CsrMatrix:
                                             int(os.environ.get("HFB_SPMM_FRAG_W", 0))), "csr_spmm_dmma_frag_kernel"
             if impl == "dmma":
                 return K.csr_spmm_dmma(self._panel_blobs(self.plan, self.device), B, out), "csr_spmm_dmma_kernel"
-            raise K.HfbError("unknown HFB_SPMM_IMPL '%s' (auto | frag | ring | dmma)" % impl)
+            raise K.HfbError("unknown HFB_SPMM_IMPL '%s' (auto | runs | frag | ring | dmma)" % impl)
         return K.csr_spmm(self.rowptr, self.colind, self.val, B, out, order=self.order), "csr_spmm_panel_kernel"
 
     def matmat_rows(self, X, out=None):

@@ -170,6 +170,30 @@ int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int3
  * HFB_E_UNSUPPORTED and the caller uses hfb_csr_spmm_dmma_frag. */
 int hfb_csr_spmm_dmma_ring(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                            const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
+/* Run-staged FMA form over the same clusters (hippyflow_b200/csrc/spmm_runs.cu; default for 96 <= m <= 384; same call sites:
+ * `M_csr @ phi`, PODProjector.py:769,830; hp.MatMvMult(M, decoder, encoder), KLEProjector.py:167-168).  The sorted distinct
+ * columns of a mesh-neighbour cluster fall into a few RUNS of consecutive B rows; consecutive rows of a row-major block are
+ * contiguous, so each run is staged by ONE linear TMA copy at the block's own pitch (7 requests per cluster instead of 33),
+ * and the product is evaluated entry by entry on the FP64 FMA pipe (a consumer warp owns a cluster row, its lanes own column
+ * pairs) instead of as a dense DMMA block: a row's entries are summed in ascending column order with fused multiply-adds
+ * from 0, the order of a sequential CSR product.
+ * HOST preprocessing: hfb_csr_runs_measure -> caps_out[4] = {max_rows, max_runs, max_brow, max_entries} of the plan;
+ * hfb_csr_runs_blob_stride (< 0: more than 16 rows or 32 runs per cluster -- use the fragment kernels);
+ * hfb_csr_pack_clusters_runs writes nclusters * stride bytes the caller uploads.  hfb_csr_spmm_runs_slots = ring slots the
+ * kernel would use for an (n, m) block of pitch ldb, 0 when the shape is unsupported (m > 384, or fewer than two slots of
+ * max_brow * ldb doubles fit in shared memory: e.g. a narrow column view of a wide block); hfb_csr_spmm_runs then returns
+ * HFB_E_UNSUPPORTED.  B, C, blobs 16-byte aligned, ldb and ldc even, ldb >= m + (m & 1) (the padding column of an odd
+ * width is read), B != C. */
+int hfb_csr_runs_measure(int64_t n, const int32_t* rowptr, const int32_t* colind, const int32_t* order,
+                         const int32_t* cluster_ptr, int64_t nclusters, int32_t* caps_out /* HOST */);
+int64_t hfb_csr_runs_blob_stride(int32_t max_rows, int32_t max_runs, int32_t max_entries);
+int hfb_csr_pack_clusters_runs(int64_t n, const int32_t* rowptr, const int32_t* colind, const double* val, const int32_t* order,
+                               const int32_t* cluster_ptr, int64_t nclusters, int32_t max_rows, int32_t max_runs,
+                               int32_t max_entries, void* blobs_out /* HOST, nclusters * stride bytes */);
+int32_t hfb_csr_spmm_runs_slots(int64_t m, int64_t ldb, int32_t max_rows, int32_t max_runs, int32_t max_brow,
+                                int32_t max_entries);
+int hfb_csr_spmm_runs(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_runs, int32_t max_brow,
+                      int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
 /*
  * Same sparse matrix applied to sample-major data: C[N x n] (row i = Mat * row i of X), i.e.

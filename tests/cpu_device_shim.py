@@ -106,6 +106,30 @@ def decode_frag_blobs(K, fblobs, max_rows, max_cols, n):
     return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
 
 
+def decode_runs_blobs(rplan, n):
+    """Rebuild the matrix from the run records of csr_spmm_runs_kernel: a staged row index maps back to a B row through
+    the run table (first B row, length, first staged row), the way the producer's copies place the rows."""
+    mr, stride = rplan["max_rows"], rplan["stride"]
+    r4 = lambda x: (x + 3) // 4 * 4
+    off_outrow = 16
+    off_goff = off_outrow + 4 * r4(mr)
+    off_runs = off_goff + 4 * r4(mr + 1)
+    off_ent = (off_runs + 8 * rplan["max_runs"] + 15) // 16 * 16
+    rows, cols, vals = [], [], []
+    for b in np.asarray(rplan["blobs"]).reshape(-1, stride):
+        nrow, nrun, nbrow, nent = (int(x) for x in b[:16].view(np.int32))
+        orow = b[off_outrow:off_outrow + 4 * nrow].view(np.int32)
+        goff = b[off_goff:off_goff + 4 * (nrow + 1)].view(np.int32)
+        staged = np.full(nbrow, -1, dtype=np.int64)
+        for start, lo in b[off_runs:off_runs + 8 * nrun].view(np.int32).reshape(-1, 2):
+            ln, off = int(lo) & 0xffff, (int(lo) >> 16) & 0xffff
+            staged[off:off + ln] = start + np.arange(ln)
+        ent = b[off_ent:off_ent + 16 * nent]
+        slot, v = ent.view(np.int32).reshape(-1, 4)[:, 0], ent.view(np.float64)[1::2]
+        rows.append(np.repeat(orow, np.diff(goff))); cols.append(staged[slot]); vals.append(v)
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+
+
 @contextlib.contextmanager
 def emulated_device():
     """Context manager: hippyflow_b200 runs on torch CPU tensors.  Yields the torch.device to pass as ``device=``."""
@@ -182,6 +206,12 @@ def emulated_device():
     def csr_spmm_dmma_ring(plan, B, out=None):
         return csr_spmm_dmma_frag(plan, B, out)      # same records
 
+    def csr_spmm_runs(rplan, B, out=None):
+        key = ("runs", id(rplan))
+        if key not in cache:
+            cache[key] = decode_runs_blobs({**rplan, "blobs": rplan["blobs"].numpy()}, B.shape[0])
+        return _spmm(cache[key], B, out)
+
     def csr_spmm_rows(rowptr, colind, val, X, out=None):
         Msp = _scipy_csr(rowptr, colind, val, X.shape[1])
         res = torch.from_numpy(np.ascontiguousarray((Msp @ X.numpy().T).T))
@@ -247,7 +277,7 @@ def emulated_device():
         k.pop("pin_memory", None)
         return saved_empty(*a, **k)
 
-    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_dmma_ring=csr_spmm_dmma_ring, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
+    patches = dict(dgemm=dgemm, dgemm_batched_small=dgemm_batched_small, csr_spmm=csr_spmm, csr_spmm_dmma=csr_spmm_dmma, csr_spmm_dmma_frag=csr_spmm_dmma_frag, csr_spmm_dmma_ring=csr_spmm_dmma_ring, csr_spmm_runs=csr_spmm_runs, csr_spmm_rows=csr_spmm_rows, coldot=coldot, rowdot=rowdot, colscale_=colscale_,
                    colsum=colsum, subtract_row_=subtract_row_, rank1_update_=rank1_update_, axpby_=axpby_,
                    axpby_cols_=axpby_cols_, rowscale=rowscale, fill_random_=fill_random_,
                    measure_dmma_peak=lambda device: 1.0, launch_count=lambda: counter["n"],

@@ -56,6 +56,22 @@ def test_argument_validation_without_gpu():
     assert L.hfb_csr_spmm_dmma(10, 266, 64, 32, 64, 200, 16, 272, 32, 272, None) == -5
     assert L.hfb_csr_frag_blob_stride(16, 32) == 4352 and L.hfb_csr_frag_blob_stride(8, 24) == 1792
     assert L.hfb_csr_frag_blob_stride(17, 32) < 0 and L.hfb_csr_frag_blob_stride(16, 49) < 0
+    # run-staged FMA SpMM: signature (nclusters, m, blobs, max_rows, max_runs, max_brow, max_entries, B, ldb, C, ldc, stream)
+    runs = L.hfb_csr_spmm_runs
+    assert runs(10, 266, None, 16, 11, 32, 112, 16, 272, 32, 272, None) == -1              # no records
+    assert runs(10, 266, 64, 16, 11, 32, 112, 16, 272, 16, 272, None) == -1                # B == C
+    assert runs(10, 267, 64, 16, 11, 32, 112, 16, 267, 32, 272, None) == -1                # ldb < m rounded up to even
+    assert runs(10, 266, 64, 16, 11, 32, 112, 24, 272, 32, 272, None) == -2                # B not 16-byte aligned
+    assert runs(10, 266, 64, 16, 11, 32, 112, 16, 273, 32, 272, None) == -2                # odd ldb
+    assert runs(10, 400, 64, 16, 11, 32, 112, 16, 400, 32, 400, None) == -5                # m > 384
+    assert runs(10, 266, 64, 17, 11, 32, 112, 16, 272, 32, 272, None) == -5                # more rows than consumer warps
+    assert runs(10, 266, 64, 16, 33, 40, 112, 16, 272, 32, 272, None) == -5                # more runs than producer lanes
+    assert runs(10, 266, 64, 16, 11, 32, 112, 16, 4096, 32, 272, None) == -5               # pitch too wide for two ring slots
+    assert L.hfb_csr_runs_blob_stride(16, 11, 112) == 2048
+    assert L.hfb_csr_runs_blob_stride(17, 11, 112) < 0 and L.hfb_csr_runs_blob_stride(16, 33, 112) < 0
+    assert L.hfb_csr_spmm_runs_slots(266, 266, 16, 11, 32, 112) == 3
+    assert L.hfb_csr_spmm_runs_slots(138, 138, 16, 11, 32, 112) == 6 and L.hfb_csr_spmm_runs_slots(74, 74, 16, 11, 32, 112) == 8
+    assert L.hfb_csr_spmm_runs_slots(266, 4096, 16, 11, 32, 112) == 0 and L.hfb_csr_spmm_runs_slots(385, 386, 16, 11, 32, 112) == 0
     # round-2 entry points: strided-batch GEMM, device Cholesky-QR factor, batched Jacobi SVD
     assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 16, 32, 4, 16, 64, 4, 8, 3, 0, 0, None, 0, None) == -1      # outputs overlap
     assert L.hfb_dgemm_batched(0, 4, 4, 4, 1.0, 16, 4, 15, 32, 4, 16, 64, 4, 16, 3, 0, 0, None, 0, None) == -2     # odd batch stride

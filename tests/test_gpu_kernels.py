@@ -115,7 +115,7 @@ def test_csr_spmm(K, cuda_device, m):
     np.testing.assert_allclose(outr, (M @ X.T).T, rtol=1e-13, atol=1e-16)
 
 
-@pytest.mark.parametrize("impl", ["dmma", "frag", "ring"])
+@pytest.mark.parametrize("impl", ["dmma", "frag", "ring", "runs"])
 @pytest.mark.parametrize("m", [33, 96, 137, 138, 266, 300, 383, 511, 1100])
 def test_csr_spmm_clustered_kernels(K, cuda_device, impl, m):
     """The cluster-plan kernels (panel records / fragment records) on a mesh matrix large enough to get a
@@ -214,6 +214,80 @@ def test_csr_spmm_ring_vs_scipy_and_frag(K, cuda_device, caps, m):
     assert torch.equal(K.csr_spmm_dmma_ring(plan, Bd), out)
 
 
+@pytest.mark.parametrize("caps", [(16, 32), (16, 24), (12, 24), (9, 20)])
+@pytest.mark.parametrize("m", [10, 63, 74, 138, 139, 200, 266, 267, 330, 384])
+def test_csr_spmm_runs_vs_scipy(K, cuda_device, caps, m, monkeypatch):
+    """Run-staged FMA kernel: every column-pairs-per-lane instantiation, odd widths, a mesh large enough that every
+    resident CTA walks several clusters through its 2-8 slot ring; bitwise reproducible and independent of the ring
+    depth; padding columns stay untouched."""
+    from hippyflow_b200 import synthetic as syn
+    from hippyflow_b200.linalg import CsrMatrix
+    M = syn.p1_mass_matrix(120, 100).tocsr()
+    n = M.shape[0]
+    plan = CsrMatrix._build_plan(M, cuda_device, max_rows=caps[0], max_cols=caps[1])
+    rplan = CsrMatrix._runs_blobs(plan, cuda_device)
+    assert rplan is not None and rplan["nclusters"] > 4 * 148
+    B = np.random.default_rng(m).standard_normal((n, m))
+    Bd = K.to_padded(B, cuda_device)
+    out = K.padded_empty(n, m, cuda_device)
+    full = out.as_strided((n, K._ld(out)), (K._ld(out), 1))
+    full.fill_(7.0)
+    assert K.csr_spmm_runs_slots(rplan, m, K._ld(Bd)) >= 2
+    K.csr_spmm_runs(rplan, Bd, out)
+    np.testing.assert_allclose(out.cpu().numpy(), M @ B, rtol=1e-13, atol=1e-16)
+    if K._ld(out) > m:
+        assert bool((full[:, m:] == 7.0).all())
+    assert torch.equal(K.csr_spmm_runs(rplan, Bd), out)
+    monkeypatch.setenv("HFB_RUNS_SLOTS", "2")
+    assert torch.equal(K.csr_spmm_runs(rplan, Bd), out)          # same sums whatever the schedule
+
+
+def test_csr_spmm_runs_irregular_matrix_views_and_fallback(K, cuda_device):
+    """Ragged pattern with empty rows; a result block whose rows are only 16-byte aligned; a B block with a wide pitch
+    (column view of a wider array) staged at that pitch; CsrMatrix falls back to the fragment kernel when the pitch is too
+    wide for the ring or the plan has too many runs."""
+    import scipy.sparse as sp
+    from hippyflow_b200.linalg import CsrMatrix
+    rng = np.random.default_rng(3)
+    n = 6000
+    A = sp.random(n, n, density=4.0 / n, random_state=7, format="csr")
+    A = (A + A.T + sp.diags(rng.standard_normal(n))).tolil()
+    for r in (0, 17, n - 1):
+        A[r, :] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    Md = CsrMatrix(A, cuda_device, cluster_rows=False)
+    Md.plan = CsrMatrix._build_plan(A, cuda_device, max_rows=16, max_cols=32)
+    Md.order = Md.plan["order"]
+    B = rng.standard_normal((n, 138))
+    for impl in ("runs",):
+        Md.impl = impl
+        rplan = CsrMatrix._runs_blobs(Md.plan, cuda_device)
+        assert rplan is not None
+        Bd = K.to_padded(B, cuda_device)
+        out = K.csr_spmm_runs(rplan, Bd).cpu().numpy()
+        np.testing.assert_allclose(out, A @ B, rtol=1e-12, atol=1e-14)
+        assert np.all(out[[0, 17, n - 1]] == 0.0)
+        wide = torch.zeros((n, 146), dtype=torch.float64, device=cuda_device)      # ld = 146: even, not a multiple of 4
+        view = wide[:, 2:140]
+        K.csr_spmm_runs(rplan, Bd, view)
+        np.testing.assert_allclose(view.cpu().numpy(), A @ B, rtol=1e-12, atol=1e-14)
+        assert bool((wide[:, :2] == 0).all()) and bool((wide[:, 140:] == 0).all())
+        # B as a column view of a wider block: pitch 160 is staged as is; the LAST rows' copies stop at the view's width
+        Bw = torch.full((n, 160), float("nan"), dtype=torch.float64, device=cuda_device)
+        Bw[:, 16:154] = torch.as_tensor(B, device=cuda_device)
+        np.testing.assert_allclose(K.csr_spmm_runs(rplan, Bw[:, 16:154]).cpu().numpy(), A @ B, rtol=1e-12, atol=1e-14)
+        # pitch 4096: no two slots fit -> CsrMatrix uses the fragment kernel instead
+        Bx = torch.zeros((n, 4096), dtype=torch.float64, device=cuda_device)
+        Bx[:, :138] = torch.as_tensor(B, device=cuda_device)
+        assert K.csr_spmm_runs_slots(rplan, 138, 4096) == 0
+        np.testing.assert_allclose(Md.matmat(Bx[:, :138]).cpu().numpy(), A @ B, rtol=1e-12, atol=1e-14)
+    # more than 32 runs in a cluster: no run records, 'runs' falls back
+    Md.plan = CsrMatrix._build_plan(A, cuda_device, max_rows=16, max_cols=48)
+    Md.impl = "runs"
+    np.testing.assert_allclose(Md.matmat(K.to_padded(B, cuda_device)).cpu().numpy(), A @ B, rtol=1e-12, atol=1e-14)
+
+
 def test_csr_spmm_dmma_frag_irregular_and_unaligned_rows(K, cuda_device):
     """Ragged pattern with empty rows; result block whose rows are only 16-byte aligned (128-bit store path)."""
     import scipy.sparse as sp
@@ -261,7 +335,7 @@ def test_csr_spmm_dmma_irregular_matrix_and_limits(K, cuda_device):
         K.csr_spmm_dmma(big, K.to_padded(B, cuda_device))
 
 
-@pytest.mark.parametrize("impl", ["dmma", "frag", "ring", "auto"])
+@pytest.mark.parametrize("impl", ["dmma", "frag", "ring", "runs", "auto"])
 def test_csr_spmm_clustered_irregular_matrix(K, cuda_device, impl):
     """Non-mesh sparsity: random symmetric pattern with ragged rows (1..20 entries) plus a few empty rows."""
     import scipy.sparse as sp

@@ -105,10 +105,12 @@ def test_shim_decodes_the_cluster_plans():
 
 def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
     """Host side of the SpMM dispatch: a 7-point mesh matrix gets (16, 32) clusters, a 21-point one the (16, 48) budget
-    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the fragment kernel for blocks of >= 32 columns, the generic
-    CSR kernel below, and duplicates in the input matrix are summed first."""
+    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the run-staged kernel for 96..384 columns, the fragment kernel
+    for other blocks of >= 32 columns, the generic CSR kernel below, and falls back from the run-staged kernel when the block's
+    pitch is too wide for its ring; duplicates in the input matrix are summed first."""
     import numpy as np
     import scipy.sparse as sp
+    import torch
     from hippyflow_b200 import _lib as K, synthetic as syn
     from hippyflow_b200.linalg import CsrMatrix
     nx = 70
@@ -129,12 +131,17 @@ def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
         assert Dd.plan is not None and 32 < Dd.plan["max_cols_cap"] <= 48
         assert Dd.shape[0] / Dd.plan["nclusters"] > 6                      # (16, 32) would leave ~2.4 rows per cluster
         rng = np.random.default_rng(0)
-        for m, kernel in ((266, "csr_spmm_ring_kernel"), (500, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_dmma_frag_kernel"),
+        for m, kernel in ((266, "csr_spmm_runs_kernel"), (500, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_runs_kernel"),
                           (40, "csr_spmm_dmma_frag_kernel"), (20, "csr_spmm_panel_kernel")):
             B = K.to_padded(rng.standard_normal((dense.shape[0], m)), dev)
             out, used = Dd._matmat(B, None)
             assert used == kernel
             np.testing.assert_allclose(out.numpy(), dense @ B.numpy(), rtol=1e-12, atol=1e-13)
+        wide = torch.zeros((dense.shape[0], 4096), dtype=torch.float64)      # a 138-column view of a 4096-column block
+        wide[:, :138] = torch.from_numpy(rng.standard_normal((dense.shape[0], 138)))
+        out, used = Dd._matmat(wide[:, :138], None)
+        assert used == "csr_spmm_dmma_frag_kernel"                           # no two ring slots at this pitch
+        np.testing.assert_allclose(out.numpy(), dense @ wide[:, :138].numpy(), rtol=1e-12, atol=1e-13)
         # duplicate entries (non-canonical CSR) are summed before the plan is built
         raw = sp.csr_matrix(dense.shape)                                   # row 0 carries its first 7 entries twice
         raw.data, raw.indices, raw.indptr = np.r_[dense.data[:7], dense.data], np.r_[dense.indices[:7], dense.indices], \

@@ -122,3 +122,103 @@ def test_peer_exchange_block_rows():
         b = block_rows_for(n, P)
         assert b % 128 == 0 and b * P >= n and (b - 128) * P < n
     assert block_rows_for(263169, 8) == 33024
+
+
+# ------------------------------------------------------------------------------------------- run records (spmm_runs.cu)
+def _runs_apply(M, Bfull, m, max_rows, max_cols, plan_from=None):
+    """Interpret the run records exactly the way csr_spmm_runs_kernel does: stage the runs of B rows as linear copies of
+    (len - 1) * ldb + width doubles at the block's pitch, then walk each row's entry list with fused multiply-adds from 0.0
+    in record order.  ``Bfull`` is the (n, ldb) storage of an (n, m) block."""
+    M = M.tocsr()
+    n, ldb = Bfull.shape
+    width = m + (m & 1)
+    P = M if plan_from is None else plan_from.tocsr()          # the matrix whose pattern is clustered
+    order, cptr = K.csr_cluster_rows_capped(P.indptr, P.indices, max_rows, max_cols)
+    blobs, caps = K.csr_pack_clusters_runs(M.indptr, M.indices, M.data, order, cptr)
+    ncl, stride, mr = cptr.size - 1, caps["stride"], caps["max_rows"]
+    assert stride % 128 == 0 and blobs.size == ncl * stride
+    off_outrow = 16
+    off_goff = off_outrow + 4 * _r4(mr)
+    off_runs = off_goff + 4 * _r4(mr + 1)
+    off_ent = (off_runs + 8 * caps["max_runs"] + 15) // 16 * 16
+    flat = Bfull.reshape(-1)
+    C = np.full((n, m), np.nan)
+    seen_rows = []
+    tot_runs = 0
+    for c in range(ncl):
+        blob = blobs[c * stride:(c + 1) * stride]
+        nrow, nrun, nbrow, nent = (int(v) for v in blob[:16].view(np.int32))
+        assert 0 < nrow <= mr and nrun <= caps["max_runs"] and nbrow <= caps["max_brow"] and nent <= caps["max_entries"]
+        outrow = blob[off_outrow:off_outrow + 4 * nrow].view(np.int32)
+        assert np.all(np.diff(outrow) > 0)                               # rows sorted ascending
+        goff = blob[off_goff:off_goff + 4 * (mr + 1)].view(np.int32)
+        runs = blob[off_runs:off_runs + 8 * nrun].view(np.int32).reshape(-1, 2)
+        stage = np.full(caps["max_brow"] * ldb, np.nan)                  # shared-memory staging area (doubles)
+        tx = 0
+        for start, lo in runs:
+            ln, off = int(lo) & 0xffff, (int(lo) >> 16) & 0xffff
+            cnt = (ln - 1) * ldb + width
+            assert start * ldb + cnt <= flat.size                        # the copy stays inside the block
+            assert off * ldb + cnt <= stage.size
+            stage[off * ldb:off * ldb + cnt] = flat[start * ldb:start * ldb + cnt]
+            tx += cnt
+        assert tx == (nbrow - nrun) * ldb + nrun * width                 # the producer's expect_tx byte count / 8
+        tot_runs += nrun
+        assert goff[0] == 0 and goff[nrow] == nent and np.all(goff[nrow:] == nent)
+        for r in range(nrow):
+            acc = np.zeros(width)
+            last = -1
+            for e in range(goff[r], goff[r + 1]):
+                ent = blob[off_ent + e * 16:off_ent + (e + 1) * 16]
+                slot = int(ent[:4].view(np.int32)[0])
+                v = float(ent[8:].view(np.float64)[0])
+                assert last < slot < nbrow                               # ascending columns, each staged
+                last = slot
+                b = stage[slot * ldb:slot * ldb + width]
+                assert not np.isnan(b[:m]).any()                         # every staged row an entry names was copied
+                acc = v * b + acc
+            C[outrow[r]] = acc[:m]
+            seen_rows.append(int(outrow[r]))
+    assert sorted(seen_rows) == list(range(n))                           # every result row written exactly once
+    return C, tot_runs / ncl
+
+
+@pytest.mark.parametrize("caps", [(16, 32), (12, 24), (16, 48), (5, 20)])
+@pytest.mark.parametrize("m,pad", [(10, 0), (37, 1), (74, 6)])
+def test_run_records_reproduce_the_product(caps, m, pad):
+    M = syn.p1_mass_matrix(23, 31).tocsr()
+    n = M.shape[0]
+    ldb = m + (m & 1) + pad * 2
+    rng = np.random.default_rng(m)
+    Bfull = rng.standard_normal((n, ldb))
+    C, runs_per_cluster = _runs_apply(M, Bfull, m, caps[0], caps[1])
+    np.testing.assert_allclose(C, M @ Bfull[:, :m], rtol=1e-13, atol=1e-16)
+    assert runs_per_cluster < caps[1] / 2                                 # mesh clusters: a handful of runs, not one per column
+
+
+def test_run_records_irregular_matrix_duplicates_and_limits():
+    """Ragged non-mesh pattern with empty rows; a non-canonical CSR with duplicate entries (summed); a plan with more than
+    32 runs in a cluster is refused (the caller keeps the fragment kernels for it)."""
+    rng = np.random.default_rng(3)
+    n = 3000
+    A = sp.random(n, n, density=4.0 / n, random_state=7, format="csr")
+    A = (A + A.T + sp.diags(rng.standard_normal(n))).tolil()
+    for r in (0, 17, n - 1):
+        A[r, :] = 0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    B = rng.standard_normal((n, 12))
+    C, _ = _runs_apply(A, B, 12, 16, 32)
+    np.testing.assert_allclose(C, A @ B, rtol=1e-12, atol=1e-14)
+    assert np.all(C[[0, 17, n - 1]] == 0.0)
+    # duplicates: the same pattern stored twice with half the values, columns unsorted within the rows
+    indptr = 2 * A.indptr
+    indices = np.concatenate([np.concatenate([A.indices[a:b][::-1], A.indices[a:b]]) for a, b in zip(A.indptr[:-1], A.indptr[1:])])
+    data = np.concatenate([np.concatenate([0.5 * A.data[a:b][::-1], 0.5 * A.data[a:b]]) for a, b in zip(A.indptr[:-1], A.indptr[1:])])
+    D = sp.csr_matrix((data, indices, indptr), shape=A.shape)
+    assert not D.has_canonical_format
+    C2, _ = _runs_apply(D, B, 12, 16, 32, plan_from=A)
+    np.testing.assert_allclose(C2, A @ B, rtol=1e-12, atol=1e-14)
+    order, cptr = K.csr_cluster_rows_capped(A.indptr, A.indices, 16, 64)
+    with pytest.raises(K.HfbError):
+        K.csr_pack_clusters_runs(A.indptr, A.indices, A.data, order, cptr)

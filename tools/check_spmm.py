@@ -19,7 +19,7 @@ shapes = ((263169, 266), (251001, 138), (263169, 74)) if quick else ((263169, 26
 caps = ((16, 32),) if quick else ((16, 32), (12, 32), (8, 24))
 if os.environ.get("HFB_CHECK_CAPS", "").replace(",", "").isdigit():
     caps = (tuple(int(v) for v in os.environ["HFB_CHECK_CAPS"].split(",")),)
-impls = ("dmma", "frag", "ring")
+impls = ("dmma", "frag", "ring", "runs")
 if "--impls" in sys.argv:
     impls = tuple(sys.argv[sys.argv.index("--impls") + 1].split(","))
 results = []
