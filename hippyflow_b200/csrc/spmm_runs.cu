@@ -6,7 +6,7 @@
 // cluster are non-zero but only 19 % of their entries) and (b) one TMA request per staged B row (33 per cluster) retires at
 // ~65 cycles per request whatever its length.  This kernel removes both:
 //   * the distinct columns of a mesh-neighbour cluster, sorted, fall into ~6 RUNS of consecutive B rows (cfg2: 6.0 per
-//     cluster, at most 11).  Consecutive rows of a row-major block are contiguous in memory, so a run is ONE linear TMA copy
+//     cluster, at most 14).  Consecutive rows of a row-major block are contiguous in memory, so a run is ONE linear TMA copy
 //     (cp.async.bulk, ~11 KB) at the block's own pitch: 7 requests per cluster instead of 33;
 //   * the multiply runs on the FP64 FMA pipe over the matrix entries themselves: a consumer warp owns a row of the cluster,
 //     its lanes own column pairs (lane + 32 j), and per entry of the row it issues one broadcast load of (staged row,

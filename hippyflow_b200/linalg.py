@@ -27,7 +27,7 @@ class CsrMatrix:
     WIDE_DEFAULT = "frag"       # kernel 'auto' uses over the cluster plan (r02: 5 / 3 / 2 column groups per warp by width)
     # narrower blocks go to the generic L1-panel kernel (r02, m = 74: fragment kernel 0.129 ms = 2601 GB/s vs 0.222 ms)
     CLUSTER_MIN_COLS = int(__import__("os").environ.get("HFB_SPMM_MIN_COLS", 32))
-    RUNS_MIN_COLS = 96          # 'auto': run-staged FMA kernel from this width up to 384 columns
+    RUNS_MIN_COLS = 65          # 'auto': run-staged FMA kernel from this width (two column pairs per lane) up to 384 columns
 
     def __init__(self, M_csr, device, cluster_rows=True):
         M = M_csr.tocsr()
@@ -46,7 +46,7 @@ class CsrMatrix:
         self.plan = None
         import os
         # SpMM kernel for blocks of >= 96 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
-        #   "auto"  (default) "runs" for 96 <= m <= 384, else "frag"
+        #   "auto"  (default) "runs" for 65 <= m <= 384, else "frag"
         #   "runs"  run-staged FMA kernel: runs of consecutive B rows staged by one TMA copy each, CSR-order FMAs (m <= 384)
         #   "frag"  dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async
         #   "ring"  the same records through resident CTAs with producer warps + a ring of cluster buffers (m <= 384)
@@ -145,9 +145,9 @@ class CsrMatrix:
             import os
             impl = self.impl
             if impl == "auto":
-                # measured on B200 (profiles/r02_spmm_runs.md): run-staged FMA kernel for 96 <= m <= 384 (m = 266: 0.215 ms vs
-                # 0.241 ms ring / 0.271 ms frag; m = 138: 0.142 ms vs 0.164 ms frag); below that a cluster's fixed costs
-                # dominate and the per-cluster fragment kernel is level or ahead (m = 74: 0.128 ms vs 0.133 ms)
+                # measured on B200 (profiles/r02_spmm_runs.md): run-staged FMA kernel for 65 <= m <= 384 (m = 266: 0.217 ms vs
+                # 0.241 ms ring / 0.271 ms frag; m = 138: 0.145 ms vs 0.165 ms frag; m = 74: 0.122 ms vs 0.129 ms frag);
+                # narrower blocks (one column pair per lane) stay with the per-cluster fragment kernel
                 impl = os.environ.get("HFB_SPMM_WIDE", "runs" if self.RUNS_MIN_COLS <= m <= 384 else self.WIDE_DEFAULT)
             if impl == "runs":
                 rplan = self._runs_blobs(self.plan, self.device) if m <= 384 else None

@@ -475,3 +475,17 @@ def test_pod_randomized_dominant_mean_falls_back_to_explicit_shift(hf, cuda_devi
     assert proj.shift_route == 'explicit-fallback'
     np.testing.assert_allclose(d, d0, rtol=1e-7)
     assert subspace_angle(phi[:, :8], U0[:, :8], M) < 1e-6
+
+def test_weighted_l2_norm_vector_direct(hf, cuda_device):
+    """sqrt(diag(x^T W x)) per column (PODProjector.py:658-661) against SciPy, for one column and for blocks on either side
+    of the SpMM kernel switch."""
+    from hippyflow_b200 import _lib as K
+    from hippyflow_b200.linalg import CsrMatrix
+    from hippyflow_b200.modeling import weighted_l2_norm_vector
+    W = syn.p1_mass_matrix(70, 63).tocsr()
+    rng = np.random.default_rng(5)
+    Wd = CsrMatrix(W, cuda_device)
+    for r in (1, 7, 74):
+        x = rng.standard_normal((W.shape[0], r))
+        got = weighted_l2_norm_vector(K.to_padded(x, cuda_device), Wd).cpu().numpy()
+        np.testing.assert_allclose(got, np.sqrt(np.einsum("ij,ij->j", x, W @ x)), rtol=1e-13)

@@ -105,7 +105,7 @@ def test_shim_decodes_the_cluster_plans():
 
 def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
     """Host side of the SpMM dispatch: a 7-point mesh matrix gets (16, 32) clusters, a 21-point one the (16, 48) budget
-    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the run-staged kernel for 96..384 columns, the fragment kernel
+    (so that clusters keep ~9 rows instead of ~2); 'auto' picks the run-staged kernel for 65..384 columns, the fragment kernel
     for other blocks of >= 32 columns, the generic CSR kernel below, and falls back from the run-staged kernel when the block's
     pitch is too wide for its ring; duplicates in the input matrix are summed first."""
     import numpy as np
@@ -132,7 +132,7 @@ def test_cluster_plan_adapts_to_denser_rows_and_kernel_choice():
         assert Dd.shape[0] / Dd.plan["nclusters"] > 6                      # (16, 32) would leave ~2.4 rows per cluster
         rng = np.random.default_rng(0)
         for m, kernel in ((266, "csr_spmm_runs_kernel"), (500, "csr_spmm_dmma_%s_kernel" % CsrMatrix.WIDE_DEFAULT), (138, "csr_spmm_runs_kernel"),
-                          (40, "csr_spmm_dmma_frag_kernel"), (20, "csr_spmm_panel_kernel")):
+                          (74, "csr_spmm_runs_kernel"), (40, "csr_spmm_dmma_frag_kernel"), (20, "csr_spmm_panel_kernel")):
             B = K.to_padded(rng.standard_normal((dense.shape[0], m)), dev)
             out, used = Dd._matmat(B, None)
             assert used == kernel
