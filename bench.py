@@ -393,7 +393,7 @@ def run_ours(args):
     coll = hf.TorchCollective() if world > 1 else hf.NullCollective()
 
     M = syn.p1_mass_matrix_for(n)
-    # one-time cost of a cold call: CSR upload + SpMM plan (row clustering, fragment records) -- outside the timed regions
+    # one-time cost of a cold call: CSR upload + SpMM plan (row clustering, run records) -- outside the timed regions
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     proj = hf.PODProjectorFromData(None, M_output=M, device=dev)
@@ -569,7 +569,7 @@ def run_ours(args):
                "e2e_floor_ms": (h2d_s + d2h_s) * 1e3,
                "e2e_floor_note": "concurrent copies alone on all ranks, max over ranks: the host-side ceiling of this leg",
                "plan_build_ms": plan_build_ms,
-               "plan_build_note": "one-time per mass matrix (CSR upload + SpMM row clustering + fragment records); paid by a "
+               "plan_build_note": "one-time per mass matrix (CSR upload + SpMM row clustering + run records); paid by a "
                                   "cold first call, not part of any timed region",
                "host_cpus_bound": (len(bound) if bound else None)}
         if not args.no_pageable:

@@ -418,6 +418,22 @@ def csr_spmm_dmma_ring(plan, B, out=None):
     return out
 
 
+def csr_runs_measure(indptr, indices, order, cptr):
+    """Caps of a cluster plan (hfb_csr_runs_measure, host): the largest cluster's rows, runs of consecutive columns, distinct
+    columns (= staged B rows) and entries."""
+    import numpy as np
+    L = lib()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    cptr = np.ascontiguousarray(cptr, dtype=np.int32)
+    caps = np.zeros(4, dtype=np.int32)
+    rc = L.hfb_csr_runs_measure(indptr.size - 1, indptr.ctypes.data, indices.ctypes.data, order.ctypes.data, cptr.ctypes.data,
+                                cptr.size - 1, caps.ctypes.data)
+    _check(rc, "hfb_csr_runs_measure")
+    return {"max_rows": int(caps[0]), "max_runs": int(caps[1]), "max_brow": int(caps[2]), "max_entries": int(caps[3])}
+
+
 def csr_pack_clusters_runs(indptr, indices, data, order, cptr):
     """Host preprocessing for the run-staged FMA SpMM (hfb_csr_pack_clusters_runs): returns (uint8 NumPy buffer of per-cluster
     run records, caps dict) or raises HfbError when the plan does not fit the kernel (> 16 rows or > 32 runs per cluster)."""
@@ -429,11 +445,8 @@ def csr_pack_clusters_runs(indptr, indices, data, order, cptr):
     order = np.ascontiguousarray(order, dtype=np.int32)
     cptr = np.ascontiguousarray(cptr, dtype=np.int32)
     ncl = cptr.size - 1
-    caps = np.zeros(4, dtype=np.int32)
-    rc = L.hfb_csr_runs_measure(indptr.size - 1, indptr.ctypes.data, indices.ctypes.data, order.ctypes.data, cptr.ctypes.data,
-                                ncl, caps.ctypes.data)
-    _check(rc, "hfb_csr_runs_measure")
-    max_rows, max_runs, max_brow, max_entries = (int(v) for v in caps)
+    caps = csr_runs_measure(indptr, indices, order, cptr)
+    max_rows, max_runs, max_entries = caps["max_rows"], caps["max_runs"], caps["max_entries"]
     stride = int(L.hfb_csr_runs_blob_stride(max_rows, max_runs, max_entries))
     if stride <= 0:
         raise HfbError("hfb_csr_runs_blob_stride: unsupported cluster plan (rows %d, runs %d per cluster; limits 16 / 32)"
@@ -443,8 +456,8 @@ def csr_pack_clusters_runs(indptr, indices, data, order, cptr):
                                       order.ctypes.data, cptr.ctypes.data, ncl, max_rows, max_runs, max_entries,
                                       blobs.ctypes.data)
     _check(rc, "hfb_csr_pack_clusters_runs")
-    return blobs, {"max_rows": max_rows, "max_runs": max_runs, "max_brow": max_brow,
-                   "max_entries": max_entries, "stride": stride}
+    caps["stride"] = stride
+    return blobs, caps
 
 
 def csr_spmm_runs_slots(rplan, m, ldb):

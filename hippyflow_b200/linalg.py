@@ -73,21 +73,12 @@ class CsrMatrix:
             max_cols = int(os.environ.get("HFB_SPMM_COLS", 32 if M.nnz <= 8 * M.shape[0] else 48))
         order, cptr = K.csr_cluster_rows_capped(M.indptr, M.indices, max_rows, max_cols)
         ncl = cptr.size - 1
-        indptr = np.asarray(M.indptr, dtype=np.int64)
-        counts = (indptr[1:] - indptr[:-1])[order]                        # nnz per row, cluster order
-        ent_ptr = np.zeros(order.size + 1, dtype=np.int64)
-        np.cumsum(counts, out=ent_ptr[1:])
-        # largest number of distinct columns any cluster actually touches (selects the kernel instantiation)
-        indices = np.asarray(M.indices, dtype=np.int64)
-        src = np.repeat(indptr[:-1][order], counts) + (np.arange(ent_ptr[-1]) - np.repeat(ent_ptr[:-1], counts))
-        cl_of_nnz = np.repeat(np.repeat(np.arange(ncl), np.diff(cptr)), counts)
-        ukey = np.unique(cl_of_nnz * M.shape[0] + indices[src])
-        distinct = np.bincount(ukey // M.shape[0], minlength=ncl)
-        assert distinct.max() <= max_cols
+        # caps of the plan (largest cluster: rows, runs of consecutive columns, distinct columns, entries), one O(nnz) host pass
+        caps = K.csr_runs_measure(M.indptr, M.indices, order, cptr)
+        assert caps["max_brow"] <= max_cols
         plan = {"nclusters": int(ncl), "order": torch.as_tensor(np.ascontiguousarray(order.astype(np.int32)), device=device),
-                "max_rows": int(np.diff(cptr).max()), "max_cols_cap": int(distinct.max()),
-                "max_entries": int(np.diff(ent_ptr[cptr]).max()),
-                "_host": (M.indptr, M.indices, M.data, order, cptr)}
+                "max_rows": caps["max_rows"], "max_cols_cap": caps["max_brow"], "max_entries": caps["max_entries"],
+                "max_runs": caps["max_runs"], "_host": (M.indptr, M.indices, M.data, order, cptr)}
         return plan
 
     @staticmethod
