@@ -1,5 +1,5 @@
-// Per-cluster record ("blob") of the packed CSR matrix shared by the persistent TMA-fed SpMM (spmm_tma.cu) and the
-// register-blocked SpMM (spmm_regblock.cu).  Written on the host by hfb_csr_pack_clusters:
+// Per-cluster record ("blob") of the packed CSR matrix read by the panel DMMA SpMM (csr_spmm_dmma_kernel, spmm_dmma.cu; the
+// retired variants under tools/experiments/spmm_variants/ used it too).  Written on the host by hfb_csr_pack_clusters:
 //     int32 header[4] = {nrow, ncol, nent, 0}
 //     int32 rowoff[max_rows + 1]   entry offsets of the cluster's rows (relative to the cluster's first entry)
 //     int32 outrow[max_rows]       global row index of each cluster row (where its result goes in C)

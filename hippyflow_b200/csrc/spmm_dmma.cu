@@ -1,6 +1,6 @@
 // CSR SpMM, cluster-dense DMMA variant (v6):  C[n x m] = Mat * B[n x m], dense row-major.
 //
-// Same host-packed clusters as spmm_tma.cu / spmm_regblock.cu (spmm_blob.cuh): <= 8*RH mesh-neighbouring rows touching
+// Host-packed clusters (spmm_blob.cuh; the same clusters feed spmm_runs.cu): <= 8*RH mesh-neighbouring rows touching
 // <= 4*MAXKS distinct columns.  A CTA owns one cluster.  The cluster's entries are scattered once into a dense local block
 // D[rows][cols] (zeros where a row does not touch a column); each thread then keeps ITS DMMA A-fragments of D in registers
 // for the whole kernel (MAXKS*RH doubles).  The distinct B rows of the cluster are staged panel by panel (64*NT columns)
