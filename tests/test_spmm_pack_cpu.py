@@ -222,3 +222,36 @@ def test_run_records_irregular_matrix_duplicates_and_limits():
     order, cptr = K.csr_cluster_rows_capped(A.indptr, A.indices, 16, 64)
     with pytest.raises(K.HfbError):
         K.csr_pack_clusters_runs(A.indptr, A.indices, A.data, order, cptr)
+
+
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(n=st.integers(40, 300), per_row=st.floats(0.5, 5.0), band=st.integers(1, 40), caps=st.sampled_from([(16, 32), (16, 48), (8, 24), (3, 12)]),
+       m=st.integers(1, 20), pad=st.integers(0, 3), seed=st.integers(0, 10 ** 6))
+def test_run_records_random_symmetric_patterns(n, per_row, band, caps, m, pad, seed):
+    """Property: for any symmetric sparsity pattern (banded + random long-range couplings, empty rows allowed) the run records
+    either reproduce the product exactly as the kernel would evaluate it, or the packer refuses the plan (more than 32 runs
+    or 16 rows in a cluster) -- never a silently wrong record."""
+    rng = np.random.default_rng(seed)
+    nnz = int(per_row * n)
+    i = rng.integers(0, n, nnz)
+    j = np.clip(i + rng.integers(-band, band + 1, nnz), 0, n - 1)
+    far = rng.random(nnz) < 0.1
+    j[far] = rng.integers(0, n, int(far.sum()))
+    A = sp.coo_matrix((rng.standard_normal(nnz), (i, j)), shape=(n, n)).tocsr()
+    A = (A + A.T).tocsr()
+    A.sum_duplicates()
+    try:
+        order, cptr = K.csr_cluster_rows_capped(A.indptr, A.indices, caps[0], caps[1])
+    except K.HfbError:
+        return                                                               # a row denser than the column budget
+    ldb = m + (m & 1) + 2 * pad
+    Bfull = rng.standard_normal((n, ldb))
+    try:
+        C, _ = _runs_apply(A, Bfull, m, caps[0], caps[1])
+    except K.HfbError as e:
+        assert "unsupported" in str(e)
+        return
+    np.testing.assert_allclose(C, A @ Bfull[:, :m], rtol=1e-12, atol=1e-13)
