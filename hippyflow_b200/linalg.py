@@ -45,7 +45,7 @@ class CsrMatrix:
         self.order = None
         self.plan = None
         import os
-        # SpMM kernel for blocks of >= 96 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
+        # SpMM kernel for blocks of >= 32 columns over the cluster plan; HFB_SPMM_IMPL overrides for tuning runs and tests:
         #   "auto"  (default) "runs" for 65 <= m <= 384, else "frag"
         #   "runs"  run-staged FMA kernel: runs of consecutive B rows staged by one TMA copy each, CSR-order FMAs (m <= 384)
         #   "frag"  dense cluster block as host-packed DMMA A-fragment records, whole B rows staged by cp.async

@@ -123,7 +123,7 @@ int hfb_csr_spmm(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t*
 
 /* Same product with the rows visited in the order `order` (device int32 permutation of 0..nrows-1, from
  * hfb_csr_cluster_rows_capped): a CTA then owns 64 mesh-neighbouring rows whose B rows overlap, so most B reads hit in L1.
- * Used for narrow blocks (m < 96) and for matrices whose rows are too dense for the cluster kernels below. */
+ * Used for narrow blocks (m < 32) and for matrices whose rows are too dense for the cluster kernels below. */
 int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const int32_t* colind, const double* val,
                          const int32_t* order, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
@@ -134,7 +134,7 @@ int hfb_csr_spmm_ordered(int64_t nrows, int64_t m, const int32_t* rowptr, const 
 int hfb_csr_cluster_rows_capped(int64_t n, const int32_t* rowptr, const int32_t* colind, int32_t max_rows, int32_t max_cols,
                                 int32_t* order_out, int32_t* cluster_ptr_out, int64_t* nclusters_out);
 
-/* Cluster-dense DMMA SpMM, panel form (default for 96 <= m < 192).  HOST preprocessing hfb_csr_pack_clusters packs the
+/* Cluster-dense DMMA SpMM, panel form (a tuning aid since round 2: HFB_SPMM_IMPL=dmma).  HOST preprocessing hfb_csr_pack_clusters packs the
  * clusters of hfb_csr_cluster_rows_capped into fixed-stride records (layout in hippyflow_b200/csrc/spmm_blob.cuh; stride from
  * hfb_csr_cluster_blob_stride; max_entries = largest number of matrix entries in one cluster; max_rows <= 16, max_cols <= 48
  * for this kernel); the caller uploads the buffer.  One CTA per cluster: the cluster's entries become a dense
@@ -148,7 +148,7 @@ int hfb_csr_pack_clusters(int64_t n, const int32_t* rowptr, const int32_t* colin
 int hfb_csr_spmm_dmma(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                       int32_t max_entries, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 
-/* The same product from "fragment records" (default for m >= 192): HOST preprocessing hfb_csr_pack_clusters_frag stores each
+/* The same product from "fragment records" (default for 32 <= m <= 64 and m > 384): HOST preprocessing hfb_csr_pack_clusters_frag stores each
  * cluster's dense block already in DMMA A-fragment order together with its nonzero-block masks, distinct columns and result
  * rows (fixed stride hfb_csr_frag_blob_stride; max_rows <= 16, max_cols <= 48).  The kernel needs no record staging or
  * dense-block build: it requests the whole chunk (chunk_cols columns, 0 = whole rows up to 320 columns) of every distinct B
@@ -164,13 +164,13 @@ int hfb_csr_pack_clusters_frag(int64_t n, const int32_t* rowptr, const int32_t* 
 int hfb_csr_spmm_dmma_frag(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                            int32_t chunk_cols, const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
 /* Ring-pipelined form over the same fragment records (results bitwise equal to hfb_csr_spmm_dmma_frag): one resident CTA per
- * SM, two producer warps keep a ring of 2-3 cluster buffers (fragment record + whole B rows, cp.async completing on mbarriers)
- * full while 16 consumer warps run the DMMA k-steps and store -- the column-list / copy / multiply / store chain of a cluster
+ * SM, a producer warp keeps a ring of 2-8 cluster buffers (fragment record + whole B rows, one TMA linear copy per row
+ * completing on mbarriers) full while 16 consumer warps run the DMMA k-steps and store -- the column-list / copy / multiply / store chain of a cluster
  * overlaps its neighbours' inside the SM.  Clusters of two row halves (8 < max_rows <= 16), m <= 384; other shapes return
  * HFB_E_UNSUPPORTED and the caller uses hfb_csr_spmm_dmma_frag. */
 int hfb_csr_spmm_dmma_ring(int64_t nclusters, int64_t m, const void* blobs, int32_t max_rows, int32_t max_cols,
                            const double* B, int64_t ldb, double* C, int64_t ldc, void* stream);
-/* Run-staged FMA form over the same clusters (hippyflow_b200/csrc/spmm_runs.cu; default for 96 <= m <= 384; same call sites:
+/* Run-staged FMA form over the same clusters (hippyflow_b200/csrc/spmm_runs.cu; default for 65 <= m <= 384; same call sites:
  * `M_csr @ phi`, PODProjector.py:769,830; hp.MatMvMult(M, decoder, encoder), KLEProjector.py:167-168).  The sorted distinct
  * columns of a mesh-neighbour cluster fall into a few RUNS of consecutive B rows; consecutive rows of a row-major block are
  * contiguous, so each run is staged by ONE linear TMA copy at the block's own pitch (7 requests per cluster instead of 33),
