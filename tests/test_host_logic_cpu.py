@@ -323,3 +323,8 @@ def test_active_subspace_and_kle_random_shapes_vs_oracle():
 
     run_as()
     run_kle()
+
+
+def test_list_and_collective_operators_vs_reference_golden(request):
+    import test_gpu_operators_extra as E
+    _run(E.test_list_and_collective_operators_vs_reference_golden, request)
