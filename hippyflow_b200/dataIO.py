@@ -29,12 +29,68 @@ def shard_bounds(n_total, rank, world):
     return rank * per, (rank + 1) * per
 
 
+def _npz_member_header(fh):
+    """(shape, fortran_order, dtype) from the .npy header at the start of an open zip member."""
+    version = np.lib.format.read_magic(fh)
+    if version == (1, 0):
+        return np.lib.format.read_array_header_1_0(fh)
+    if version == (2, 0):
+        return np.lib.format.read_array_header_2_0(fh)
+    raise ValueError("unsupported .npy header version %r" % (version,))
+
+
+def _npz_member_shape(path, key):
+    """Shape of array ``key`` of an .npz archive from the .npy header of the zip member alone (``np.load(path)[key].shape``
+    would read and inflate the whole member -- every rank doing that for every archive is O(world x dataset))."""
+    import zipfile
+    with zipfile.ZipFile(path) as zf, zf.open(key + ".npy") as fh:
+        return tuple(_npz_member_header(fh)[0])
+
+
+def _npz_member_rows(path, key, lo=0, hi=None, chunk_bytes=1 << 24):
+    """Rows [lo, hi) of array ``key`` of an .npz archive, streamed from the zip member: the bytes before row ``lo`` are
+    skipped (a seek for stored members, inflate-and-discard in 16 MB pieces for deflated ones), the shard is inflated
+    straight into its own buffer and nothing after row ``hi`` is read -- host memory stays O(shard), where
+    ``np.load(path)[key][lo:hi]`` materialises the whole member on every rank.  Object arrays and Fortran-ordered members
+    take the NumPy route."""
+    import zipfile
+    with zipfile.ZipFile(path) as zf, zf.open(key + ".npy") as fh:
+        shape, fortran, dtype = _npz_member_header(fh)
+        if dtype.hasobject or fortran or len(shape) == 0:
+            with np.load(path, allow_pickle=True) as z:
+                a = z[key]
+                return a if len(shape) == 0 else a[lo:hi]
+        n = shape[0]
+        lo = max(0, min(n, lo))
+        hi = n if hi is None else max(lo, min(n, hi))
+        row_bytes = int(np.prod(shape[1:], dtype=np.int64)) * dtype.itemsize
+        out = np.empty((hi - lo,) + tuple(shape[1:]), dtype=dtype)
+        skip = lo * row_bytes
+        if skip:
+            try:
+                fh.seek(skip, 1)                                # stored members seek; deflated ones read and discard inside zipfile
+            except Exception:
+                while skip > 0:
+                    got = fh.read(min(skip, chunk_bytes))
+                    if not got:
+                        raise EOFError("%s[%s]: truncated member" % (path, key))
+                    skip -= len(got)
+        view = memoryview(out.reshape(-1).view(np.uint8)) if out.size else memoryview(b"")
+        done = 0
+        while done < len(view):
+            got = fh.readinto(view[done:done + chunk_bytes])
+            if not got:
+                raise EOFError("%s[%s]: truncated member" % (path, key))
+            done += got
+    return out
+
+
 def load_mq_data(file_path, device, rank=0, world=1, name="mq_data.npz"):
-    """(m_shard, q_shard) as padded device blocks, rows = this rank's samples."""
-    with np.load(os.path.join(file_path, name)) as z:
-        lo, hi = shard_bounds(z["m_data"].shape[0], rank, world)
-        m = K.to_padded(z["m_data"][lo:hi], device)
-        q = K.to_padded(z["q_data"][lo:hi], device)
+    """(m_shard, q_shard) as padded device blocks, rows = this rank's samples (only the shard is held on the host)."""
+    path = os.path.join(file_path, name)
+    lo, hi = shard_bounds(_npz_member_shape(path, "m_data")[0], rank, world)
+    m = K.to_padded(_npz_member_rows(path, "m_data", lo, hi), device)
+    q = K.to_padded(_npz_member_rows(path, "q_data", lo, hi), device)
     return m, q
 
 
@@ -51,10 +107,10 @@ def load_jacobian_svd_factor(file_path, device, rank=0, world=1, name="Jsvd_data
     """Stored low-rank Jacobians J_i = U_i diag(sigma_i) V_i^T  ->  the stacked factor rows sigma_i * V_i^T,
     shape (N_loc * r, dM), with block size r: since U_i^T U_i = I, (1/N) sum J_i^T J_i = (1/N) sum V_i sigma_i^2 V_i^T,
     so the factor is the ``Xt`` of linalg.SampleCovariance (block = r).  Returns (Xt, r)."""
-    with np.load(os.path.join(file_path, name)) as z:
-        lo, hi = shard_bounds(z["sigma_data"].shape[0], rank, world)
-        V = z["V_data"][lo:hi]                                   # (N_loc, dM, r)
-        s = z["sigma_data"][lo:hi]                               # (N_loc, r)
+    path = os.path.join(file_path, name)
+    lo, hi = shard_bounds(_npz_member_shape(path, "sigma_data")[0], rank, world)
+    V = _npz_member_rows(path, "V_data", lo, hi)                 # (N_loc, dM, r)
+    s = _npz_member_rows(path, "sigma_data", lo, hi)             # (N_loc, r)
     F = np.ascontiguousarray(np.transpose(V * s[:, None, :], (0, 2, 1)))   # (N_loc, r, dM)
     n_loc, r, dM = F.shape
     return K.to_padded(F.reshape(n_loc * r, dM), device), r
@@ -119,10 +175,7 @@ def _rank_files(data_dir, patterns):
 def _sharded_rows_from_archives(files, keys, rank, world):
     """Rows [lo, hi) of the virtual concatenation of ``keys`` over ``files`` without materialising the whole dataset:
     only archives that intersect this rank's shard are decompressed.  Returns {key: ndarray}."""
-    counts = []
-    for f in files:
-        with np.load(f) as z:
-            counts.append(int(z[keys[0]].shape[0]))
+    counts = [int(_npz_member_shape(f, keys[0])[0]) for f in files]     # headers only: nothing is decompressed here
     offs = np.concatenate([[0], np.cumsum(counts)])
     lo, hi = shard_bounds(int(offs[-1]), rank, world)
     parts = {k: [] for k in keys}
@@ -130,9 +183,8 @@ def _sharded_rows_from_archives(files, keys, rank, world):
         s0, s1 = max(lo, int(a)), min(hi, int(b))
         if s0 >= s1:
             continue
-        with np.load(f) as z:
-            for k in keys:
-                parts[k].append(z[k][s0 - int(a):s1 - int(a)])
+        for k in keys:
+            parts[k].append(_npz_member_rows(f, k, s0 - int(a), s1 - int(a)))
     return {k: np.concatenate(v, axis=0) for k, v in parts.items()}
 
 
@@ -162,10 +214,10 @@ def load_reduced_jacobians(file_path, device, kind="JstarPhi", rank=0, world=1):
     if kind not in ("JstarPhi", "JPsi"):
         raise ValueError("kind must be 'JstarPhi' or 'JPsi'")
     b_key, e_key = ("Phi", "MPhi") if kind == "JstarPhi" else ("Psi", "input_encoder")
-    with np.load(os.path.join(file_path, kind + "_data.npz"), allow_pickle=True) as z:
-        data = z[kind + "_data"]
-        lo, hi = shard_bounds(data.shape[0], rank, world)
-        block = torch.as_tensor(np.ascontiguousarray(data[lo:hi], dtype=np.float64), device=device)
+    path = os.path.join(file_path, kind + "_data.npz")
+    lo, hi = shard_bounds(_npz_member_shape(path, kind + "_data")[0], rank, world)
+    block = torch.as_tensor(np.ascontiguousarray(_npz_member_rows(path, kind + "_data", lo, hi), dtype=np.float64), device=device)
+    with np.load(path, allow_pickle=True) as z:                  # the bases are small; members are only read on access
         opt = lambda k: (None if (k not in z.files or z[k].dtype == object) else np.asarray(z[k]))
         return block, opt(b_key), opt(e_key)
 

@@ -143,3 +143,36 @@ def test_compress_dataset_matches_reference_bit_for_bit(tmp_path):
             assert sorted(a.files) == sorted(b.files), name
             for k in a.files:
                 assert np.array_equal(a[k], b[k]), (name, k)
+
+
+def test_streamed_shard_reader_matches_numpy(tmp_path):
+    """dataIO._npz_member_rows / _npz_member_shape: rows [lo, hi) of an archive member streamed from the zip file equal
+    ``np.load(path)[key][lo:hi]`` for deflated and stored archives, any dtype, 1-/2-/3-D members, empty and clipped ranges;
+    Fortran-ordered, scalar and object members take the NumPy route; shapes come from the member header alone."""
+    import numpy as np
+    from hippyflow_b200 import dataIO
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((301, 57, 3))
+    b = rng.integers(0, 9, (301, 5)).astype(np.int32)
+    v = rng.standard_normal(301).astype(np.float32)
+    f = np.asfortranarray(rng.standard_normal((301, 4)))
+    for comp in (True, False):
+        fn = str(tmp_path / ("x%d.npz" % comp))
+        (np.savez_compressed if comp else np.savez)(fn, a=a, b=b, v=v, f=f, s=np.float64(3.5), o=np.array(None, dtype=object))
+        for lo, hi in ((0, None), (0, 0), (17, 18), (100, 301), (250, 400), (301, 301)):
+            for k, ref in (("a", a), ("b", b), ("v", v), ("f", f)):
+                got = dataIO._npz_member_rows(fn, k, lo, hi, chunk_bytes=4096)
+                assert got.dtype == ref.dtype and np.array_equal(got, ref[lo:hi]), (comp, k, lo, hi)
+        assert dataIO._npz_member_shape(fn, "a") == (301, 57, 3) and dataIO._npz_member_shape(fn, "s") == ()
+        assert float(dataIO._npz_member_rows(fn, "s")) == 3.5
+        assert dataIO._npz_member_rows(fn, "o").dtype == object
+    # a truncated archive is an error, not a short shard
+    raw = open(str(tmp_path / "x0.npz"), "rb").read()
+    import zipfile
+    with zipfile.ZipFile(str(tmp_path / "t.npz"), "w") as zf:
+        import io
+        buf = io.BytesIO()
+        np.lib.format.write_array(buf, a)
+        zf.writestr("a.npy", buf.getvalue()[:-1000])
+    with pytest.raises(EOFError):
+        dataIO._npz_member_rows(str(tmp_path / "t.npz"), "a", 290, 301)
